@@ -1,0 +1,200 @@
+/*
+ * pcv_attn.h — C ABI of libpcv_attn.so: the B200 (sm_100a) latent-attention hot path.
+ *
+ * This is the drop-in boundary (level 2).  Every entry point takes plain
+ * pointers and sizes; no torch types cross it.  The Python host side
+ * (perceiver_io_b200/ops.py) binds these symbols with ctypes and passes
+ * `tensor.data_ptr()` and the raw `cudaStream_t` of torch's current stream.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *
+ *   pcv_attn_fwd            perceiver/model/core/modules.py:146-164  (the head-chunk loop:
+ *                           einsum QK^T -> masked_fill_(pad) -> masked_fill_(causal) ->
+ *                           softmax -> einsum PV) plus the head split/merge rearranges at
+ *                           :123 and :166-167 (done by strides, never materialised) and the
+ *                           q*dp_scale at :124 (folded into the softmax exponent).
+ *   pcv_attn_combine        no counterpart: merges per-shard partial softmax states
+ *                           (numerator, row max, denominator) when M is split inside one GPU
+ *                           or across GPUs.
+ *   pcv_rotary_apply        perceiver/model/core/position.py:30-50
+ *                           (RotaryPositionEmbedding.rotate + _rotate_half).
+ *   pcv_kv_append           perceiver/model/core/modules.py:117-121 (torch.cat onto the cache).
+ *
+ * Conventions
+ *   - All device pointers must belong to the current CUDA device of the calling thread.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *   - Return value 0 = success; non-zero = failure, message via pcv_last_error() (thread local).
+ *   - Strides are in ELEMENTS of the tensor's dtype.
+ *   - Inputs are borrowed and never written; outputs are caller-allocated.
+ */
+#ifndef PCV_ATTN_H_
+#define PCV_ATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCV_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PCV_API __attribute__((visibility("default")))
+#else
+#define PCV_API
+#endif
+
+/* element type of q/k/v/out */
+enum pcv_dtype { PCV_BF16 = 0, PCV_F16 = 1, PCV_F32 = 2 /* pcv_kv_append only */ };
+
+/* kernel selection; AUTO picks the tcgen05 kernel whenever the shape is supported */
+enum pcv_impl { PCV_IMPL_AUTO = 0, PCV_IMPL_TCGEN05 = 1, PCV_IMPL_SIMT = 2 };
+
+/* status codes */
+enum pcv_status {
+  PCV_OK = 0,
+  PCV_ERR_INVALID = 1,      /* bad argument (message says which)              */
+  PCV_ERR_UNSUPPORTED = 2,  /* shape/dtype not supported by the requested impl */
+  PCV_ERR_CUDA = 3,         /* a CUDA runtime/driver call failed               */
+  PCV_ERR_WORKSPACE = 4     /* workspace missing or too small                  */
+};
+
+/*
+ * Fused attention forward for one MultiHeadAttention call.
+ *
+ *   q   : (Bq, N, H, dqk)  Bq is B or 1 (q_stride_b == 0 broadcasts the latents, the
+ *                           encoder case: adapter.py:82-83 returns a batch-1 latent array)
+ *   k   : (B,  M, H, dqk)
+ *   v   : (B,  M, H, dv)
+ *   out : (B,  N, H, dv)   normalised attention output, same dtype as q
+ *
+ * Score of query i / key j (before softmax), with jg = m_offset + j the key's global index:
+ *     s_ij = scale * <q_i, k_j>
+ *     masked (set to -FLT_MAX, the reference's finite fill, modules.py:152-158) when
+ *         pad_mask[b, j] != 0, or
+ *         causal != 0 and jg > i + (m_total - N)      (right-aligned causal, modules.py:135-140)
+ *   A fully masked row therefore becomes the uniform average of all M value rows, exactly as
+ *   in the reference.
+ *
+ * M-sharding: a shard passes its local M keys, the global key count m_total and its first
+ * key's global index m_offset; with write_partial != 0 the kernel emits the un-normalised
+ * state instead of `out`:
+ *     part_o (B,H,N,dv) f32 = sum_j exp2(t_ij - m_i) v_j,   part_m (B,H,N) f32 = m_i (log2 domain,
+ *     t = s*log2(e)),   part_l (B,H,N) f32 = sum_j exp2(t_ij - m_i)
+ * which pcv_attn_combine merges exactly.
+ */
+typedef struct pcv_attn_params {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int64_t q_stride_b, q_stride_n, q_stride_h;
+  int64_t k_stride_b, k_stride_m, k_stride_h;
+  int64_t v_stride_b, v_stride_m, v_stride_h;
+  int64_t o_stride_b, o_stride_n, o_stride_h;
+  int32_t B, H, N, M;
+  int32_t dqk, dv;
+  float scale;             /* dp_scale = dqk^-0.5 (modules.py:73)                       */
+  int32_t dtype;           /* enum pcv_dtype                                            */
+  int32_t causal;          /* 0 / 1                                                     */
+  int32_t m_total;         /* global number of keys (== M when not sharded)             */
+  int32_t m_offset;        /* global index of this call's key 0                         */
+  const uint8_t* pad_mask; /* (B, M) bytes, non-zero = padding key; NULL = none         */
+  int64_t pad_stride_b;    /* bytes between batch rows of pad_mask                      */
+  int32_t write_partial;   /* 0: write `out`; 1: write part_o/part_m/part_l             */
+  float* part_o;
+  float* part_m;
+  float* part_l;
+  void* workspace;         /* device scratch of at least pcv_attn_workspace_bytes()     */
+  size_t workspace_bytes;
+  int32_t impl;            /* enum pcv_impl                                             */
+  int32_t reserved;
+} pcv_attn_params;
+
+/*
+ * Merge `num_parts` partial softmax states of identical shape into the final output.
+ *   part_o : (num_parts, B, H, N, dv) f32   part_m, part_l : (num_parts, B, H, N) f32
+ *   out    : (B, N, H, dv) in `dtype`, strides as in pcv_attn_params
+ *   m = max_g m_g ;  l = sum_g l_g 2^(m_g-m) ;  out = sum_g part_o_g 2^(m_g-m) / l
+ */
+typedef struct pcv_combine_params {
+  const float* part_o;
+  const float* part_m;
+  const float* part_l;
+  void* out;
+  int64_t o_stride_b, o_stride_n, o_stride_h;
+  int32_t num_parts;
+  int32_t B, H, N, dv;
+  int32_t dtype;
+} pcv_combine_params;
+
+/*
+ * Rotary position embedding of a (B, n, H, d) tensor (position.py:30-50).
+ *   angles : (Ba, n_angles, rotate_dim) f32, Ba is B or 1 — the `frq_pos_enc` tensor the
+ *            reference's RotaryPositionEmbedding holds (position.py:23-28)
+ *   row i of x uses angle row `angle_row0 + i`  (right_align: n_angles - n, else 0)
+ *   channels [0, rotate_dim) of every head are rotated pairwise, the rest pass through:
+ *     y[2p]   = x[2p]  *cos(a[2p])   - x[2p+1]*sin(a[2p])
+ *     y[2p+1] = x[2p+1]*cos(a[2p+1]) + x[2p]  *sin(a[2p+1])
+ *   y is written with its own strides (may alias neither x nor angles).
+ */
+typedef struct pcv_rotary_params {
+  const void* x;
+  void* y;
+  const float* angles;
+  int64_t x_stride_b, x_stride_n, x_stride_h;
+  int64_t y_stride_b, y_stride_n, y_stride_h;
+  int64_t a_stride_b, a_stride_n; /* a_stride_b == 0 broadcasts */
+  int32_t B, n, H, d;
+  int32_t rotate_dim;
+  int32_t angle_row0;
+  int32_t dtype;
+  int32_t reserved;
+} pcv_rotary_params;
+
+/*
+ * KV-cache append (modules.py:117-121): dst[:, :L_old] = cache, dst[:, L_old:L_old+n] = fresh
+ * for both K and V in one launch.  Tensors are (B, L, C) with explicit batch/row strides.
+ * A cache pointer may equal its dst pointer (in-place arena append): that half is skipped.
+ */
+typedef struct pcv_kv_append_params {
+  const void* k_cache; const void* v_cache;   /* (B, L_old, Ck) / (B, L_old, Cv); may be NULL if L_old == 0 */
+  const void* k_new;   const void* v_new;     /* (B, n, Ck) / (B, n, Cv) */
+  void* k_dst;         void* v_dst;           /* (B, L_old + n, Ck) / (.., Cv) */
+  int64_t kc_stride_b, kc_stride_l, vc_stride_b, vc_stride_l;
+  int64_t kn_stride_b, kn_stride_l, vn_stride_b, vn_stride_l;
+  int64_t kd_stride_b, kd_stride_l, vd_stride_b, vd_stride_l;
+  int32_t B, L_old, n, Ck, Cv;
+  int32_t dtype;
+} pcv_kv_append_params;
+
+/* library / device introspection */
+typedef struct pcv_device_info {
+  int32_t device;
+  int32_t sm_major, sm_minor;
+  int32_t num_sms;
+  int32_t smem_optin_bytes;
+  int32_t tcgen05_ok;      /* 1 when the tcgen05 kernels can run on this device */
+} pcv_device_info;
+
+PCV_API int pcv_abi_version(void);
+PCV_API const char* pcv_last_error(void);
+PCV_API int pcv_get_device_info(pcv_device_info* info);
+
+/* 1 if the tcgen05 kernel family covers this problem (shape, dtype, alignment), else 0 */
+PCV_API int pcv_attn_supported_tcgen05(const pcv_attn_params* p);
+PCV_API int pcv_attn_workspace_bytes(const pcv_attn_params* p, size_t* bytes);
+PCV_API int pcv_attn_fwd(const pcv_attn_params* p, void* stream);
+PCV_API int pcv_attn_combine(const pcv_combine_params* p, void* stream);
+PCV_API int pcv_rotary_apply(const pcv_rotary_params* p, void* stream);
+PCV_API int pcv_kv_append(const pcv_kv_append_params* p, void* stream);
+
+/* number of kernel launches issued by this library in the calling process (for bench.py's
+ * gpu_launches claim) */
+PCV_API uint64_t pcv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCV_ATTN_H_ */

@@ -1,0 +1,152 @@
+"""ctypes binding of ``libpcv_attn.so`` — the C-ABI declared in ``include/pcv_attn.h``.
+
+The structures below mirror the header field by field (tests/test_abi.py checks the sizes and
+that every declared symbol is exported).  There is deliberately no fallback: if the shared
+library is missing the import of this module's :func:`lib` raises, and every op in
+:mod:`perceiver_io_b200.ops` with it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpcv_attn.so")
+
+PCV_BF16, PCV_F16, PCV_F32 = 0, 1, 2
+PCV_IMPL_AUTO, PCV_IMPL_TCGEN05, PCV_IMPL_SIMT = 0, 1, 2
+IMPL_BY_NAME = {"auto": PCV_IMPL_AUTO, "tcgen05": PCV_IMPL_TCGEN05, "simt": PCV_IMPL_SIMT}
+
+EXPORTS = (
+    "pcv_abi_version",
+    "pcv_last_error",
+    "pcv_get_device_info",
+    "pcv_attn_supported_tcgen05",
+    "pcv_attn_workspace_bytes",
+    "pcv_attn_fwd",
+    "pcv_attn_combine",
+    "pcv_rotary_apply",
+    "pcv_kv_append",
+    "pcv_launch_count",
+)
+
+
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("q_stride_b", C.c_int64), ("q_stride_n", C.c_int64), ("q_stride_h", C.c_int64),
+        ("k_stride_b", C.c_int64), ("k_stride_m", C.c_int64), ("k_stride_h", C.c_int64),
+        ("v_stride_b", C.c_int64), ("v_stride_m", C.c_int64), ("v_stride_h", C.c_int64),
+        ("o_stride_b", C.c_int64), ("o_stride_n", C.c_int64), ("o_stride_h", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("M", C.c_int32),
+        ("dqk", C.c_int32), ("dv", C.c_int32),
+        ("scale", C.c_float),
+        ("dtype", C.c_int32),
+        ("causal", C.c_int32),
+        ("m_total", C.c_int32),
+        ("m_offset", C.c_int32),
+        ("pad_mask", C.c_void_p),
+        ("pad_stride_b", C.c_int64),
+        ("write_partial", C.c_int32),
+        ("part_o", C.c_void_p), ("part_m", C.c_void_p), ("part_l", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+        ("impl", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class CombineParams(C.Structure):
+    _fields_ = [
+        ("part_o", C.c_void_p), ("part_m", C.c_void_p), ("part_l", C.c_void_p), ("out", C.c_void_p),
+        ("o_stride_b", C.c_int64), ("o_stride_n", C.c_int64), ("o_stride_h", C.c_int64),
+        ("num_parts", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("dv", C.c_int32),
+        ("dtype", C.c_int32),
+    ]
+
+
+class RotaryParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("angles", C.c_void_p),
+        ("x_stride_b", C.c_int64), ("x_stride_n", C.c_int64), ("x_stride_h", C.c_int64),
+        ("y_stride_b", C.c_int64), ("y_stride_n", C.c_int64), ("y_stride_h", C.c_int64),
+        ("a_stride_b", C.c_int64), ("a_stride_n", C.c_int64),
+        ("B", C.c_int32), ("n", C.c_int32), ("H", C.c_int32), ("d", C.c_int32),
+        ("rotate_dim", C.c_int32),
+        ("angle_row0", C.c_int32),
+        ("dtype", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class KvAppendParams(C.Structure):
+    _fields_ = [
+        ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+        ("k_new", C.c_void_p), ("v_new", C.c_void_p),
+        ("k_dst", C.c_void_p), ("v_dst", C.c_void_p),
+        ("kc_stride_b", C.c_int64), ("kc_stride_l", C.c_int64), ("vc_stride_b", C.c_int64), ("vc_stride_l", C.c_int64),
+        ("kn_stride_b", C.c_int64), ("kn_stride_l", C.c_int64), ("vn_stride_b", C.c_int64), ("vn_stride_l", C.c_int64),
+        ("kd_stride_b", C.c_int64), ("kd_stride_l", C.c_int64), ("vd_stride_b", C.c_int64), ("vd_stride_l", C.c_int64),
+        ("B", C.c_int32), ("L_old", C.c_int32), ("n", C.c_int32), ("Ck", C.c_int32), ("Cv", C.c_int32),
+        ("dtype", C.c_int32),
+    ]
+
+
+class DeviceInfo(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("sm_major", C.c_int32), ("sm_minor", C.c_int32),
+        ("num_sms", C.c_int32), ("smem_optin_bytes", C.c_int32), ("tcgen05_ok", C.c_int32),
+    ]
+
+
+class PcvError(RuntimeError):
+    """A libpcv_attn entry point returned a non-zero status."""
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise PcvError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C perceiver_io_b200/csrc`). There is no CPU/PyTorch fallback for the attention path."
+            )
+        l = C.CDLL(LIB_PATH)
+        l.pcv_abi_version.restype = C.c_int
+        l.pcv_last_error.restype = C.c_char_p
+        l.pcv_launch_count.restype = C.c_uint64
+        l.pcv_get_device_info.argtypes = [C.POINTER(DeviceInfo)]
+        l.pcv_attn_supported_tcgen05.argtypes = [C.POINTER(AttnParams)]
+        l.pcv_attn_workspace_bytes.argtypes = [C.POINTER(AttnParams), C.POINTER(C.c_size_t)]
+        l.pcv_attn_fwd.argtypes = [C.POINTER(AttnParams), C.c_void_p]
+        l.pcv_attn_combine.argtypes = [C.POINTER(CombineParams), C.c_void_p]
+        l.pcv_rotary_apply.argtypes = [C.POINTER(RotaryParams), C.c_void_p]
+        l.pcv_kv_append.argtypes = [C.POINTER(KvAppendParams), C.c_void_p]
+        for name in ("pcv_get_device_info", "pcv_attn_supported_tcgen05", "pcv_attn_workspace_bytes",
+                     "pcv_attn_fwd", "pcv_attn_combine", "pcv_rotary_apply", "pcv_kv_append"):
+            getattr(l, name).restype = C.c_int
+        if l.pcv_abi_version() != 1:
+            raise PcvError(f"libpcv_attn ABI version {l.pcv_abi_version()} != 1 expected by the Python host")
+        _lib = l
+        return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().pcv_last_error()
+        raise PcvError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().pcv_launch_count())

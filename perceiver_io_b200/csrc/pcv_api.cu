@@ -1,0 +1,119 @@
+// pcv_api.cu — the extern "C" surface of libpcv_attn.so (see include/pcv_attn.h).
+// Argument validation, kernel-family dispatch and error reporting live here; kernels live in
+// pcv_attn_tc.cu (tcgen05), pcv_attn_simt.cu (CUDA cores) and pcv_aux.cu.
+#include "pcv_common.cuh"
+
+#include <atomic>
+#include <cstring>
+
+namespace pcv {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int validate_attn(const pcv_attn_params* p) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "attn: params is NULL");
+  PCV_REQUIRE(p->q && p->k && p->v, PCV_ERR_INVALID, "attn: q/k/v pointer is NULL");
+  PCV_REQUIRE(p->B >= 1 && p->H >= 1 && p->N >= 1 && p->M >= 1, PCV_ERR_INVALID,
+              "attn: B=%d H=%d N=%d M=%d must all be >= 1", p->B, p->H, p->N, p->M);
+  PCV_REQUIRE(p->dqk >= 1 && p->dv >= 1, PCV_ERR_INVALID, "attn: dqk=%d dv=%d must be >= 1", p->dqk, p->dv);
+  PCV_REQUIRE(p->dtype == PCV_BF16 || p->dtype == PCV_F16, PCV_ERR_INVALID, "attn: unknown dtype %d", p->dtype);
+  PCV_REQUIRE(p->m_total >= p->M && p->m_offset >= 0 && p->m_offset + p->M <= p->m_total, PCV_ERR_INVALID,
+              "attn: shard [%d,%d) outside m_total=%d", p->m_offset, p->m_offset + p->M, p->m_total);
+  PCV_REQUIRE(!p->causal || p->m_total >= p->N, PCV_ERR_INVALID,
+              "attn: causal attention needs m_total (%d) >= N (%d)", p->m_total, p->N);
+  if (p->write_partial) {
+    PCV_REQUIRE(p->part_o && p->part_m && p->part_l, PCV_ERR_INVALID, "attn: write_partial set but part_* NULL");
+  } else {
+    PCV_REQUIRE(p->out != nullptr, PCV_ERR_INVALID, "attn: out pointer is NULL");
+  }
+  PCV_REQUIRE(p->impl >= PCV_IMPL_AUTO && p->impl <= PCV_IMPL_SIMT, PCV_ERR_INVALID, "attn: unknown impl %d", p->impl);
+  return PCV_OK;
+}
+
+static bool use_tc(const pcv_attn_params& p, const char** why) {
+  if (p.impl == PCV_IMPL_SIMT) {
+    *why = "simt requested";
+    return false;
+  }
+  return attn_tc_supported(p, why);
+}
+
+}  // namespace pcv
+
+using namespace pcv;
+
+extern "C" {
+
+int pcv_abi_version(void) { return PCV_ABI_VERSION; }
+
+const char* pcv_last_error(void) { return g_err; }
+
+uint64_t pcv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int pcv_get_device_info(pcv_device_info* info) {
+  PCV_REQUIRE(info != nullptr, PCV_ERR_INVALID, "device_info: NULL argument");
+  int dev = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  PCV_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  info->device = dev;
+  info->sm_major = prop.major;
+  info->sm_minor = prop.minor;
+  info->num_sms = prop.multiProcessorCount;
+  info->smem_optin_bytes = (int)prop.sharedMemPerBlockOptin;
+  info->tcgen05_ok = (prop.major == 10) ? 1 : 0;
+  return PCV_OK;
+}
+
+int pcv_attn_supported_tcgen05(const pcv_attn_params* p) {
+  if (validate_attn(p) != PCV_OK) return 0;
+  const char* why = "";
+  const bool ok = attn_tc_supported(*p, &why);
+  if (!ok) set_error("tcgen05 path not applicable: %s", why);
+  return ok ? 1 : 0;
+}
+
+int pcv_attn_workspace_bytes(const pcv_attn_params* p, size_t* bytes) {
+  int rc = validate_attn(p);
+  if (rc != PCV_OK) return rc;
+  PCV_REQUIRE(bytes != nullptr, PCV_ERR_INVALID, "attn: bytes is NULL");
+  const char* why = "";
+  if (use_tc(*p, &why)) return attn_tc_workspace_bytes(*p, bytes);
+  PCV_REQUIRE(p->impl != PCV_IMPL_TCGEN05, PCV_ERR_UNSUPPORTED, "attn: tcgen05 kernel requested but %s", why);
+  return attn_simt_workspace_bytes(*p, bytes);
+}
+
+int pcv_attn_fwd(const pcv_attn_params* p, void* stream) {
+  int rc = validate_attn(p);
+  if (rc != PCV_OK) return rc;
+  const char* why = "";
+  if (use_tc(*p, &why)) return launch_attn_tc(*p, reinterpret_cast<cudaStream_t>(stream));
+  PCV_REQUIRE(p->impl != PCV_IMPL_TCGEN05, PCV_ERR_UNSUPPORTED, "attn: tcgen05 kernel requested but %s", why);
+  return launch_attn_simt(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pcv_attn_combine(const pcv_combine_params* p, void* stream) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "combine: params is NULL");
+  return launch_combine(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pcv_rotary_apply(const pcv_rotary_params* p, void* stream) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "rotary: params is NULL");
+  return launch_rotary(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pcv_kv_append(const pcv_kv_append_params* p, void* stream) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "kv_append: params is NULL");
+  return launch_kv_append(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

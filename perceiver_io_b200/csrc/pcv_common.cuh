@@ -1,0 +1,86 @@
+// pcv_common.cuh — shared host/device helpers for libpcv_attn.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cfloat>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/pcv_attn.h"
+
+namespace pcv {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PCV_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::pcv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                         \
+      return PCV_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define PCV_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::pcv::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// ---- numeric conventions shared by every kernel ---------------------------------------------
+// Scores live in the log2 domain: t = s * scale * log2(e).  Masked keys (padding / causal) take
+// the reference's finite fill, keys beyond the end of the tensor are excluded with -inf.
+constexpr float kMaskedScore = -FLT_MAX;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---- element traits --------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<__nv_bfloat16> {
+  using T2 = __nv_bfloat162;
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float x) { return __float2bfloat16_rn(x); }
+  static __device__ __forceinline__ float2 to_f2(__nv_bfloat162 x) { return __bfloat1622float2(x); }
+};
+template <> struct Elem<__half> {
+  using T2 = __half2;
+  static __device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+  static __device__ __forceinline__ __half from_f(float x) { return __float2half_rn(x); }
+  static __device__ __forceinline__ float2 to_f2(__half2 x) { return __half22float2(x); }
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- launchers implemented in the individual .cu files ---------------------------------------
+int launch_attn_simt(const pcv_attn_params& p, cudaStream_t stream);
+int attn_simt_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
+
+bool attn_tc_supported(const pcv_attn_params& p, const char** why);
+int launch_attn_tc(const pcv_attn_params& p, cudaStream_t stream);
+int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
+
+int launch_combine(const pcv_combine_params& p, cudaStream_t stream);
+// Merge `nparts` partial states laid out [part][B][H][N]([dv]) either into p.out (normalised) or,
+// when p.write_partial is set, into p.part_o / p.part_m / p.part_l (still un-normalised).
+int launch_combine_ex(const float* po, const float* pm, const float* pl, int nparts,
+                      const pcv_attn_params& p, cudaStream_t stream);
+int launch_rotary(const pcv_rotary_params& p, cudaStream_t stream);
+int launch_kv_append(const pcv_kv_append_params& p, cudaStream_t stream);
+
+}  // namespace pcv

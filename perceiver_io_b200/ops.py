@@ -1,0 +1,307 @@
+"""Torch-facing wrappers of the C-ABI ops (``include/pcv_attn.h``).
+
+PyTorch is plumbing here: it owns device memory and the stream.  Every function below passes raw
+``data_ptr()`` values, element strides and ``torch.cuda.current_stream().cuda_stream`` to
+``libpcv_attn.so``; nothing synchronises.  Inputs must live on a CUDA device — there is no CPU
+path and no PyTorch re-implementation to fall back to (``PcvError`` / ``RuntimeError`` instead).
+
+dtype policy (SURVEY.md §8(b) "dtype / device"): the kernels compute on bf16 (or fp16) operands
+with fp32 accumulation.  fp32 inputs are explicitly rounded to bf16 at this boundary and the
+result is returned in the caller's dtype; parity tolerances are defined against the reference
+evaluated on the same bf16-rounded operands.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AttnParams, CombineParams, KvAppendParams, RotaryParams, PcvError, check
+
+__all__ = [
+    "attention", "attention_partial", "combine_partials", "rotary", "kv_append",
+    "device_info", "tcgen05_supported",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "perceiver_io_b200 ops run on CUDA (sm_100a) tensors only; got a tensor on "
+                f"{t.device}. There is no CPU fallback for the attention path."
+            )
+
+
+def _pcv_dtype(dt: torch.dtype) -> int:
+    if dt == torch.bfloat16:
+        return _lib.PCV_BF16
+    if dt == torch.float16:
+        return _lib.PCV_F16
+    raise RuntimeError(f"unsupported compute dtype {dt}")
+
+
+def _compute_dtype(dt: torch.dtype) -> torch.dtype:
+    return dt if dt in (torch.bfloat16, torch.float16) else torch.bfloat16
+
+
+def _rows_contiguous(t: torch.Tensor) -> torch.Tensor:
+    """(B, L, C) with unit channel stride (other strides are passed through to the kernel)."""
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def device_info() -> dict:
+    info = _lib.DeviceInfo()
+    check(_lib.lib().pcv_get_device_info(C.byref(info)), "pcv_get_device_info")
+    return {f[0]: getattr(info, f[0]) for f in info._fields_}
+
+
+def _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, m_total, m_offset, impl) -> Tuple[AttnParams, tuple]:
+    if q.dim() != 3 or k.dim() != 3 or v.dim() != 3:
+        raise ValueError("q, k, v must be (B, L, C) tensors")
+    Bq, N, Cq = q.shape
+    B, M, Ck = k.shape
+    if v.shape[0] != B or v.shape[1] != M:
+        raise ValueError(f"k {tuple(k.shape)} and v {tuple(v.shape)} disagree on (B, M)")
+    if Bq not in (1, B):
+        raise ValueError(f"query batch {Bq} must be 1 or equal to key batch {B}")
+    if Cq != Ck:
+        raise ValueError(f"q channels {Cq} != k channels {Ck}")
+    if Cq % num_heads or v.shape[2] % num_heads:
+        raise ValueError("channel counts must be divisible by num_heads")
+    H = num_heads
+    dqk, dv = Cq // H, v.shape[2] // H
+    p = AttnParams()
+    p.q, p.k, p.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    p.q_stride_b = 0 if (Bq == 1 and B > 1) else q.stride(0)
+    p.q_stride_n, p.q_stride_h = q.stride(1), dqk
+    p.k_stride_b, p.k_stride_m, p.k_stride_h = k.stride(0), k.stride(1), dqk
+    p.v_stride_b, p.v_stride_m, p.v_stride_h = v.stride(0), v.stride(1), dv
+    p.B, p.H, p.N, p.M, p.dqk, p.dv = B, H, N, M, dqk, dv
+    p.scale = float(scale)
+    p.dtype = _pcv_dtype(q.dtype)
+    p.causal = 1 if causal else 0
+    p.m_total = M if m_total is None else int(m_total)
+    p.m_offset = int(m_offset)
+    keep = [q, k, v]
+    if pad_mask is not None:
+        if pad_mask.shape != (B, M):
+            raise ValueError(f"pad_mask shape {tuple(pad_mask.shape)} != {(B, M)}")
+        pm = pad_mask
+        if pm.dtype == torch.bool:
+            pm = pm.view(torch.uint8) if pm.stride(-1) == 1 else pm.contiguous().view(torch.uint8)
+        elif pm.dtype != torch.uint8:
+            pm = (pm != 0).view(torch.uint8)
+        if pm.stride(-1) != 1:
+            pm = pm.contiguous()
+        p.pad_mask = pm.data_ptr()
+        p.pad_stride_b = pm.stride(0)
+        keep.append(pm)
+    p.impl = _lib.IMPL_BY_NAME[impl]
+    return p, tuple(keep)
+
+
+def _run_attn(p: AttnParams, device) -> None:
+    need = C.c_size_t(0)
+    check(_lib.lib().pcv_attn_workspace_bytes(C.byref(p), C.byref(need)), "pcv_attn_workspace_bytes")
+    ws = None
+    if need.value:
+        ws = torch.empty(need.value, dtype=torch.uint8, device=device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), need.value
+    check(_lib.lib().pcv_attn_fwd(C.byref(p), _stream()), "pcv_attn_fwd")
+
+
+def _prep(q, k, v):
+    _require_cuda(q, k, v)
+    out_dtype = q.dtype
+    cdt = _compute_dtype(q.dtype)
+    q, k, v = (_rows_contiguous(t if t.dtype == cdt else t.to(cdt)) for t in (q, k, v))
+    return q, k, v, out_dtype
+
+
+def _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl):
+    q, k, v, out_dtype = _prep(q, k, v)
+    if pad_mask is not None:
+        _require_cuda(pad_mask)
+    with torch.cuda.device(k.device):
+        p, keep = _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, None, 0, impl)
+        out = torch.empty(p.B, p.N, p.H * p.dv, dtype=q.dtype, device=k.device)
+        p.out = out.data_ptr()
+        p.o_stride_b, p.o_stride_n, p.o_stride_h = out.stride(0), out.stride(1), p.dv
+        _run_attn(p, k.device)
+    del keep
+    return out if out.dtype == out_dtype else out.to(out_dtype)
+
+
+class _FusedAttention(torch.autograd.Function):
+    """Forward = the fused CUDA kernel.  Backward = TRAINING-SUPPORT SHIM, not a kernel:
+    it recomputes softmax(QK^T)V with plain torch ops on the same device so that the reference's
+    Lightning wrappers can still call ``loss.backward()`` (SURVEY.md §7.3 "Training"); a fused
+    backward is listed under §8(f) rank 2.  The forward never routes through it."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, num_heads, scale, pad_mask, causal, impl):
+        ctx.save_for_backward(q, k, v, pad_mask)
+        ctx.meta = (num_heads, scale, causal)
+        return _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, k, v, pad_mask = ctx.saved_tensors
+        H, scale, causal = ctx.meta
+        with torch.enable_grad():
+            qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+            B, M = kf.shape[0], kf.shape[1]
+            N = qf.shape[1]
+            qh = qf.expand(B, -1, -1).reshape(B, N, H, -1).transpose(1, 2)
+            kh = kf.reshape(B, M, H, -1).transpose(1, 2)
+            vh = vf.reshape(B, M, H, -1).transpose(1, 2)
+            s = torch.matmul(qh * scale, kh.transpose(-1, -2))
+            neg = -torch.finfo(s.dtype).max
+            if pad_mask is not None:
+                s = s.masked_fill(pad_mask.bool()[:, None, None, :], neg)
+            if causal:
+                s = s.masked_fill(torch.ones(N, M, dtype=torch.bool, device=s.device).triu(M - N + 1), neg)
+            o = torch.matmul(s.softmax(-1), vh).transpose(1, 2).reshape(B, N, -1)
+            gq, gk, gv = torch.autograd.grad(o, (qf, kf, vf), grad_out.float())
+        return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), None, None, None, None, None
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, scale: float,
+              pad_mask: Optional[torch.Tensor] = None, causal: bool = False, impl: str = "auto") -> torch.Tensor:
+    """softmax(scale * Q K^T + masks) V with heads split by stride.
+
+    q: (B or 1, N, H*dqk), k: (B, M, H*dqk), v: (B, M, H*dv) -> (B, N, H*dv).
+    Semantics of the reference's ``MultiHeadAttention.forward`` lines 123-167
+    (/root/reference/perceiver/model/core/modules.py): q is scaled by ``scale``, ``pad_mask`` (True =
+    padding) and the right-aligned causal mask use the finite fill ``-finfo.max``.
+    """
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        return _FusedAttention.apply(q, k, v, num_heads, scale, pad_mask, causal, impl)
+    return _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl)
+
+
+def attention_partial(q, k, v, num_heads: int, scale: float, pad_mask=None, causal: bool = False,
+                      m_total: Optional[int] = None, m_offset: int = 0, impl: str = "auto"):
+    """One M-shard's un-normalised softmax state: (part_o (B,H,N,dv) f32, part_m (B,H,N), part_l (B,H,N)).
+
+    ``k``/``v``/``pad_mask`` hold this shard's keys [m_offset, m_offset+M) of ``m_total``."""
+    q, k, v, _ = _prep(q, k, v)
+    with torch.cuda.device(k.device):
+        p, keep = _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, m_total, m_offset, impl)
+        part_o = torch.empty(p.B, p.H, p.N, p.dv, dtype=torch.float32, device=k.device)
+        part_m = torch.empty(p.B, p.H, p.N, dtype=torch.float32, device=k.device)
+        part_l = torch.empty(p.B, p.H, p.N, dtype=torch.float32, device=k.device)
+        p.write_partial = 1
+        p.part_o, p.part_m, p.part_l = part_o.data_ptr(), part_m.data_ptr(), part_l.data_ptr()
+        _run_attn(p, k.device)
+    del keep
+    return part_o, part_m, part_l
+
+
+def combine_partials(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.Tensor,
+                     out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """Merge G partial states (G,B,H,N,dv)/(G,B,H,N)/(G,B,H,N) -> (B, N, H*dv)."""
+    _require_cuda(part_o, part_m, part_l)
+    G, B, H, N, dv = part_o.shape
+    part_o, part_m, part_l = part_o.contiguous(), part_m.contiguous(), part_l.contiguous()
+    cdt = _compute_dtype(out_dtype)
+    with torch.cuda.device(part_o.device):
+        out = torch.empty(B, N, H * dv, dtype=cdt, device=part_o.device)
+        p = CombineParams()
+        p.part_o, p.part_m, p.part_l, p.out = part_o.data_ptr(), part_m.data_ptr(), part_l.data_ptr(), out.data_ptr()
+        p.o_stride_b, p.o_stride_n, p.o_stride_h = out.stride(0), out.stride(1), dv
+        p.num_parts, p.B, p.H, p.N, p.dv = G, B, H, N, dv
+        p.dtype = _pcv_dtype(cdt)
+        check(_lib.lib().pcv_attn_combine(C.byref(p), _stream()), "pcv_attn_combine")
+    return out if cdt == out_dtype else out.to(out_dtype)
+
+
+def rotary(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: bool) -> torch.Tensor:
+    """Rotate the first ``angles.shape[-1]`` channels of every head of x (B, n, H*d).
+
+    ``angles`` is the reference's ``frq_pos_enc`` (B or 1, n_angles, rotate_dim); row selection follows
+    /root/reference/perceiver/model/core/position.py:32-37 (last n rows if right_align else first n)."""
+    _require_cuda(x, angles)
+    out_dtype = x.dtype
+    cdt = _compute_dtype(x.dtype)
+    x = _rows_contiguous(x if x.dtype == cdt else x.to(cdt))
+    if angles.dim() == 4:  # (B, 1, n, f) as stored by RotaryPositionEmbedding
+        angles = angles[:, 0]
+    angles = angles.float()
+    if angles.stride(-1) != 1:
+        angles = angles.contiguous()
+    B, n, Cx = x.shape
+    d = Cx // num_heads
+    Ba, n_angles, f = angles.shape
+    if Ba not in (1, B):
+        raise ValueError(f"angle batch {Ba} must be 1 or {B}")
+    if n_angles < n:
+        raise ValueError(f"rotary: {n_angles} angle rows for a sequence of {n}")
+    y = torch.empty(B, n, Cx, dtype=cdt, device=x.device)
+    if n == 0:
+        return y.to(out_dtype)
+    p = RotaryParams()
+    p.x, p.y, p.angles = x.data_ptr(), y.data_ptr(), angles.data_ptr()
+    p.x_stride_b, p.x_stride_n, p.x_stride_h = x.stride(0), x.stride(1), d
+    p.y_stride_b, p.y_stride_n, p.y_stride_h = y.stride(0), y.stride(1), d
+    p.a_stride_b = 0 if (Ba == 1 and B > 1) else angles.stride(0)
+    p.a_stride_n = angles.stride(1)
+    p.B, p.n, p.H, p.d = B, n, num_heads, d
+    p.rotate_dim = f
+    p.angle_row0 = (n_angles - n) if right_align else 0
+    p.dtype = _pcv_dtype(cdt)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().pcv_rotary_apply(C.byref(p), _stream()), "pcv_rotary_apply")
+    return y if cdt == out_dtype else y.to(out_dtype)
+
+
+def kv_append(k_cache: torch.Tensor, v_cache: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor):
+    """Functional KV-cache concat along dim 1 in one launch (reference modules.py:117-121).
+
+    Returns freshly allocated ``(B, L_old+n, C)`` tensors, as ``torch.cat`` does, so the
+    🤗-side cache consumers may slice / ``index_select`` them freely (SURVEY.md §8(b) ownership)."""
+    _require_cuda(k_cache, v_cache, k_new, v_new)
+    dt = k_new.dtype
+    codes = {torch.bfloat16: _lib.PCV_BF16, torch.float16: _lib.PCV_F16, torch.float32: _lib.PCV_F32}
+    if dt not in codes or any(t.dtype != dt for t in (k_cache, v_cache, v_new)):
+        raise RuntimeError(f"kv_append expects matching bf16/fp16/fp32 tensors, got {k_cache.dtype}/{k_new.dtype}")
+    k_cache, v_cache, k_new, v_new = (_rows_contiguous(t) for t in (k_cache, v_cache, k_new, v_new))
+    B, L_old, Ck = k_cache.shape
+    n = k_new.shape[1]
+    Cv = v_new.shape[2]
+    k_dst = torch.empty(B, L_old + n, Ck, dtype=dt, device=k_new.device)
+    v_dst = torch.empty(B, L_old + n, Cv, dtype=dt, device=k_new.device)
+    if L_old + n == 0:
+        return k_dst, v_dst
+    p = KvAppendParams()
+    p.k_cache, p.v_cache = (k_cache.data_ptr(), v_cache.data_ptr()) if L_old else (None, None)
+    p.k_new, p.v_new, p.k_dst, p.v_dst = k_new.data_ptr(), v_new.data_ptr(), k_dst.data_ptr(), v_dst.data_ptr()
+    p.kc_stride_b, p.kc_stride_l = k_cache.stride(0), k_cache.stride(1)
+    p.vc_stride_b, p.vc_stride_l = v_cache.stride(0), v_cache.stride(1)
+    p.kn_stride_b, p.kn_stride_l = k_new.stride(0), k_new.stride(1)
+    p.vn_stride_b, p.vn_stride_l = v_new.stride(0), v_new.stride(1)
+    p.kd_stride_b, p.kd_stride_l = k_dst.stride(0), k_dst.stride(1)
+    p.vd_stride_b, p.vd_stride_l = v_dst.stride(0), v_dst.stride(1)
+    p.B, p.L_old, p.n, p.Ck, p.Cv = B, L_old, n, Ck, Cv
+    p.dtype = codes[dt]
+    with torch.cuda.device(k_new.device):
+        check(_lib.lib().pcv_kv_append(C.byref(p), _stream()), "pcv_kv_append")
+    return k_dst, v_dst
+
+
+def tcgen05_supported(q, k, v, num_heads: int, pad_mask=None, causal: bool = False) -> bool:
+    """True when pcv_attn_fwd would pick the tcgen05 kernel for these operands."""
+    q, k, v, _ = _prep(q, k, v)
+    p, keep = _fill_attn_params(q, k, v, num_heads, 1.0, pad_mask, causal, None, 0, "auto")
+    dummy = torch.empty(1, device=k.device)
+    p.out = dummy.data_ptr()
+    ok = bool(_lib.lib().pcv_attn_supported_tcgen05(C.byref(p)))
+    del keep
+    return ok
