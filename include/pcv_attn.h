@@ -169,6 +169,21 @@ typedef struct pcv_kv_append_params {
   int32_t dtype;
 } pcv_kv_append_params;
 
+/*
+ * In-place change of reference maximum of a partial state (used between the two all-reduces of the
+ * M-sharded path, perceiver_io_b200/dist.py):  w = 2^(part_m[r] - new_m[r]);  part_o[r,:] *= w;
+ * part_l[r] *= w;  part_m[r] = new_m[r].   rows = B*H*N.  new_m[r] >= part_m[r] is expected.
+ */
+typedef struct pcv_rescale_params {
+  float* part_o;        /* (rows, dv) */
+  float* part_m;        /* (rows)     */
+  float* part_l;        /* (rows)     */
+  const float* new_m;   /* (rows)     */
+  int64_t rows;
+  int32_t dv;
+  int32_t reserved;
+} pcv_rescale_params;
+
 /* library / device introspection */
 typedef struct pcv_device_info {
   int32_t device;
@@ -187,8 +202,17 @@ PCV_API int pcv_attn_supported_tcgen05(const pcv_attn_params* p);
 PCV_API int pcv_attn_workspace_bytes(const pcv_attn_params* p, size_t* bytes);
 PCV_API int pcv_attn_fwd(const pcv_attn_params* p, void* stream);
 PCV_API int pcv_attn_combine(const pcv_combine_params* p, void* stream);
+PCV_API int pcv_partial_rescale(const pcv_rescale_params* p, void* stream);
 PCV_API int pcv_rotary_apply(const pcv_rotary_params* p, void* stream);
 PCV_API int pcv_kv_append(const pcv_kv_append_params* p, void* stream);
+
+/*
+ * Live timing of the dominant kernel (bench.py's roofline leg): between pcv_profile_begin() and
+ * pcv_profile_end() every attention main-kernel launch is bracketed by CUDA events on its own
+ * stream; pcv_profile_end() synchronises those events and returns their summed duration.
+ */
+PCV_API int pcv_profile_begin(void);
+PCV_API int pcv_profile_end(double* main_kernel_ms_total, int32_t* main_kernel_launches);
 
 /* number of kernel launches issued by this library in the calling process (for bench.py's
  * gpu_launches claim) */

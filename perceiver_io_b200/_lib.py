@@ -26,9 +26,12 @@ EXPORTS = (
     "pcv_attn_workspace_bytes",
     "pcv_attn_fwd",
     "pcv_attn_combine",
+    "pcv_partial_rescale",
     "pcv_rotary_apply",
     "pcv_kv_append",
     "pcv_launch_count",
+    "pcv_profile_begin",
+    "pcv_profile_end",
 )
 
 
@@ -64,6 +67,13 @@ class CombineParams(C.Structure):
         ("num_parts", C.c_int32),
         ("B", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("dv", C.c_int32),
         ("dtype", C.c_int32),
+    ]
+
+
+class RescaleParams(C.Structure):
+    _fields_ = [
+        ("part_o", C.c_void_p), ("part_m", C.c_void_p), ("part_l", C.c_void_p), ("new_m", C.c_void_p),
+        ("rows", C.c_int64), ("dv", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -132,9 +142,14 @@ def lib() -> C.CDLL:
         l.pcv_attn_fwd.argtypes = [C.POINTER(AttnParams), C.c_void_p]
         l.pcv_attn_combine.argtypes = [C.POINTER(CombineParams), C.c_void_p]
         l.pcv_rotary_apply.argtypes = [C.POINTER(RotaryParams), C.c_void_p]
+        l.pcv_partial_rescale.argtypes = [C.POINTER(RescaleParams), C.c_void_p]
+        l.pcv_profile_begin.restype = C.c_int
+        l.pcv_profile_end.restype = C.c_int
+        l.pcv_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         l.pcv_kv_append.argtypes = [C.POINTER(KvAppendParams), C.c_void_p]
         for name in ("pcv_get_device_info", "pcv_attn_supported_tcgen05", "pcv_attn_workspace_bytes",
-                     "pcv_attn_fwd", "pcv_attn_combine", "pcv_rotary_apply", "pcv_kv_append"):
+                     "pcv_attn_fwd", "pcv_attn_combine", "pcv_rotary_apply", "pcv_kv_append",
+                     "pcv_partial_rescale"):
             getattr(l, name).restype = C.c_int
         if l.pcv_abi_version() != 1:
             raise PcvError(f"libpcv_attn ABI version {l.pcv_abi_version()} != 1 expected by the Python host")
@@ -146,6 +161,17 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().pcv_last_error()
         raise PcvError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")
+
+
+def profile_begin() -> None:
+    check(lib().pcv_profile_begin(), "pcv_profile_begin")
+
+
+def profile_end():
+    """-> (summed device ms of the attention main kernel, number of launches) since profile_begin()."""
+    ms, n = C.c_double(0.0), C.c_int32(0)
+    check(lib().pcv_profile_end(C.byref(ms), C.byref(n)), "pcv_profile_end")
+    return ms.value, n.value
 
 
 def launch_count() -> int:

@@ -5,6 +5,9 @@
 
 #include <atomic>
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 namespace pcv {
 
@@ -18,6 +21,24 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+
+void prof_mark_begin(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on) return;
+  cudaEvent_t a, b;
+  if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+  cudaEventRecord(a, stream);
+  g_prof_events.emplace_back(a, b);
+}
+void prof_mark_end(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on || g_prof_events.empty()) return;
+  cudaEventRecord(g_prof_events.back().second, stream);
+}
 
 static int validate_attn(const pcv_attn_params* p) {
   PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "attn: params is NULL");
@@ -56,6 +77,32 @@ extern "C" {
 int pcv_abi_version(void) { return PCV_ABI_VERSION; }
 
 const char* pcv_last_error(void) { return g_err; }
+
+int pcv_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = true;
+  return PCV_OK;
+}
+
+int pcv_profile_end(double* main_kernel_ms_total, int32_t* main_kernel_launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  double total = 0.0;
+  int n = 0;
+  for (auto& ev : g_prof_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+      total += ms;
+      ++n;
+    }
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  g_prof_events.clear();
+  if (main_kernel_ms_total) *main_kernel_ms_total = total;
+  if (main_kernel_launches) *main_kernel_launches = n;
+  return PCV_OK;
+}
 
 uint64_t pcv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -104,6 +151,11 @@ int pcv_attn_fwd(const pcv_attn_params* p, void* stream) {
 int pcv_attn_combine(const pcv_combine_params* p, void* stream) {
   PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "combine: params is NULL");
   return launch_combine(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pcv_partial_rescale(const pcv_rescale_params* p, void* stream) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "rescale: params is NULL");
+  return launch_rescale(*p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int pcv_rotary_apply(const pcv_rotary_params* p, void* stream) {

@@ -223,7 +223,9 @@ int launch_t(const pcv_attn_params& p, const SimtPlan& pl, cudaStream_t stream) 
     }
   }
   dim3 grid((p.N + kRowsPerCta - 1) / kRowsPerCta, p.B * p.H, pl.nsplit);
+  prof_mark_begin(stream);
   kern<<<grid, kWarps * 32, pl.smem_bytes, stream>>>(p, pl.nsplit, pl.keys_per_split, wo, wm, wl);
+  prof_mark_end(stream);
   PCV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return PCV_OK;

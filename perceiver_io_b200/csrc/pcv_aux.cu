@@ -69,6 +69,33 @@ int combine_t(const float* po, const float* pm, const float* pl, int nparts, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// rescale: one warp per row, float4 where the row length allows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rescale_kernel(const pcv_rescale_params p) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= p.rows) return;
+  const float mo = p.part_m[r], mn = p.new_m[r];
+  const float w = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+  float* row = p.part_o + r * p.dv;
+  if ((p.dv & 3) == 0) {
+    float4* row4 = reinterpret_cast<float4*>(row);
+    for (int c = lane; c < (p.dv >> 2); c += 32) {
+      float4 x = row4[c];
+      x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+      row4[c] = x;
+    }
+  } else {
+    for (int c = lane; c < p.dv; c += 32) row[c] *= w;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    p.part_l[r] *= w;
+    p.part_m[r] = mn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // rotary: one thread per channel pair.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -178,6 +205,16 @@ int launch_combine(const pcv_combine_params& p, cudaStream_t stream) {
                                     p.o_stride_b, p.o_stride_n, p.o_stride_h, nullptr, nullptr, nullptr, stream);
   return combine_t<__half>(p.part_o, p.part_m, p.part_l, p.num_parts, p.B, p.H, p.N, p.dv, p.out, p.o_stride_b,
                            p.o_stride_n, p.o_stride_h, nullptr, nullptr, nullptr, stream);
+}
+
+int launch_rescale(const pcv_rescale_params& p, cudaStream_t stream) {
+  PCV_REQUIRE(p.part_o && p.part_m && p.part_l && p.new_m, PCV_ERR_INVALID, "rescale: null pointer argument");
+  PCV_REQUIRE(p.rows >= 1 && p.dv >= 1, PCV_ERR_INVALID, "rescale: bad dimension");
+  const int warps = 8;
+  rescale_kernel<<<(unsigned)((p.rows + warps - 1) / warps), warps * 32, 0, stream>>>(p);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PCV_OK;
 }
 
 int launch_rotary(const pcv_rotary_params& p, cudaStream_t stream) {

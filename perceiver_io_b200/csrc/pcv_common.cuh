@@ -16,6 +16,9 @@ namespace pcv {
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// bracket the dominant kernel with events while profiling is enabled (no-ops otherwise)
+void prof_mark_begin(cudaStream_t stream);
+void prof_mark_end(cudaStream_t stream);
 
 #define PCV_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
@@ -80,6 +83,7 @@ int launch_combine(const pcv_combine_params& p, cudaStream_t stream);
 // when p.write_partial is set, into p.part_o / p.part_m / p.part_l (still un-normalised).
 int launch_combine_ex(const float* po, const float* pm, const float* pl, int nparts,
                       const pcv_attn_params& p, cudaStream_t stream);
+int launch_rescale(const pcv_rescale_params& p, cudaStream_t stream);
 int launch_rotary(const pcv_rotary_params& p, cudaStream_t stream);
 int launch_kv_append(const pcv_kv_append_params& p, cudaStream_t stream);
 

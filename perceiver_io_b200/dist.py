@@ -1,0 +1,112 @@
+"""M-sharded latent cross-attention across the GPUs of one box.
+
+The key/value axis M is the only axis that shards naturally when N << M: rank g holds keys
+[m_offset, m_offset + M_g) of ``m_total`` (and the matching slice of ``pad_mask``), computes the
+partial softmax state of ALL B*H*N query rows over its keys with the fused kernel
+(``pcv_attn_fwd`` with ``write_partial``), and the ranks merge:
+
+    m  = max_g m_g                               all_reduce(MAX) on (B,H,N) floats        131 KB
+    Õ_g, l_g *= 2^(m_g - m)                      pcv_partial_rescale (in place)
+    [Õ ‖ l] = sum_g [Õ_g ‖ l_g]                  ONE all_reduce(SUM) over NVLink/NVSwitch  ~17 MB
+    out = Õ / l                                  pcv_attn_combine (num_parts = 1)
+
+Q, the projection weights and everything after the merge (o_proj, MLP, the latent self-attention
+stack) are replicated: no further communication.  The reference has no counterpart (its only
+multi-GPU modes are DDP/FSDP replicas).
+
+The communication backend is whatever ``torch.distributed`` group is passed (NCCL on GPUs).  The
+device math is injectable (``ShardKernels``) so the host-side protocol is testable with ``gloo`` on
+CPU boxes (tests/test_dist_cpu.py injects the oracle's math); the default is the CUDA path and
+nothing else.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(m_total: int, world_size: int, rank: int, align: int = 128) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of the key axis owned by ``rank``: equal counts of ``align``-key
+    tiles, remainder tiles to the lowest ranks, the ragged tail to the last non-empty rank."""
+    tiles = (m_total + align - 1) // align
+    base, extra = divmod(tiles, world_size)
+    first_tile = rank * base + min(rank, extra)
+    n_tiles = base + (1 if rank < extra else 0)
+    begin = min(first_tile * align, m_total)
+    end = min((first_tile + n_tiles) * align, m_total)
+    return begin, end
+
+
+def _cuda_partial(q, k, v, num_heads, scale, pad_mask, causal, m_total, m_offset, out):
+    from . import ops
+
+    return ops.attention_partial(q, k, v, num_heads, scale, pad_mask=pad_mask, causal=causal, m_total=m_total,
+                                 m_offset=m_offset, out=out)
+
+
+def _cuda_rescale(po, pm, pl, new_m):
+    from . import ops
+
+    ops.rescale_partial_(po, pm, pl, new_m)
+
+
+def _cuda_finalize(po, pl, out_dtype):
+    from . import ops
+
+    return ops.combine_partials(po[None], torch.zeros_like(pl)[None], pl[None], out_dtype)
+
+
+@dataclass
+class ShardKernels:
+    """Device math of the sharded path; the defaults are the sm_100a kernels."""
+    partial: Callable = _cuda_partial
+    rescale_: Callable = _cuda_rescale
+    finalize: Callable = _cuda_finalize
+
+
+def sharded_attention(q: torch.Tensor, k_shard: torch.Tensor, v_shard: torch.Tensor, num_heads: int, scale: float,
+                      m_total: int, m_offset: int, pad_mask_shard: Optional[torch.Tensor] = None,
+                      causal: bool = False, group=None, kernels: Optional[ShardKernels] = None) -> torch.Tensor:
+    """softmax(QK^T)V with K/V sharded along M over ``group``; every rank returns the full (B,N,H*dv)."""
+    kernels = kernels or ShardKernels()
+    B, M_local = k_shard.shape[0], k_shard.shape[1]
+    N = q.shape[1]
+    dv = v_shard.shape[2] // num_heads
+    rows = B * num_heads * N
+    if M_local == 0:
+        raise ValueError("every rank must own at least one key (shard_bounds guarantees it for M >= world*align)")
+    # one allocation so that numerator and denominator ride the same all-reduce
+    flat = torch.empty(rows * dv + rows, dtype=torch.float32, device=k_shard.device)
+    po = flat[: rows * dv].view(B, num_heads, N, dv)
+    pl = flat[rows * dv:].view(B, num_heads, N)
+    pm = torch.empty(B, num_heads, N, dtype=torch.float32, device=k_shard.device)
+    kernels.partial(q, k_shard, v_shard, num_heads, scale, pad_mask_shard, causal, m_total, m_offset, (po, pm, pl))
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        m_glob = pm.clone()
+        dist.all_reduce(m_glob, op=dist.ReduceOp.MAX, group=group)
+        kernels.rescale_(po, pm, pl, m_glob)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return kernels.finalize(po, pl, q.dtype)
+
+
+def cross_attention_sharded(module, x_q: torch.Tensor, x_kv_shard: torch.Tensor, m_total: int, m_offset: int,
+                            pad_mask_shard: Optional[torch.Tensor] = None, group=None,
+                            kernels: Optional[ShardKernels] = None):
+    """``CrossAttention.forward`` (reference modules.py:204-230) with ``x_kv`` sharded along M.
+
+    ``module`` is a CrossAttention (this package's or a patched reference one).  LayerNorm and the K/V
+    projections run on the local shard only — they are 2/3 of the module's FLOPs and shard perfectly —
+    then the attention core is merged across ranks and ``o_proj`` is applied replicated."""
+    from .utils import ModuleOutput
+
+    attn = module.attention
+    x_q = module.q_norm(x_q)
+    x_kv = module.kv_norm(x_kv_shard)
+    q, k, v = attn.q_proj(x_q), attn.k_proj(x_kv), attn.v_proj(x_kv)
+    o = sharded_attention(q, k, v, attn.num_heads, attn.dp_scale, m_total, m_offset, pad_mask_shard,
+                          attn.causal_attention, group, kernels)
+    return ModuleOutput(last_hidden_state=attn.o_proj(o), kv_cache=None)

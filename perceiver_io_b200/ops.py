@@ -18,10 +18,10 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import AttnParams, CombineParams, KvAppendParams, RotaryParams, PcvError, check
+from ._lib import AttnParams, CombineParams, KvAppendParams, RescaleParams, RotaryParams, PcvError, check
 
 __all__ = [
-    "attention", "attention_partial", "combine_partials", "rotary", "kv_append",
+    "attention", "attention_partial", "combine_partials", "rescale_partial_", "rotary", "kv_append",
     "device_info", "tcgen05_supported",
 ]
 
@@ -188,16 +188,26 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int,
 
 
 def attention_partial(q, k, v, num_heads: int, scale: float, pad_mask=None, causal: bool = False,
-                      m_total: Optional[int] = None, m_offset: int = 0, impl: str = "auto"):
+                      m_total: Optional[int] = None, m_offset: int = 0, impl: str = "auto", out=None):
     """One M-shard's un-normalised softmax state: (part_o (B,H,N,dv) f32, part_m (B,H,N), part_l (B,H,N)).
 
-    ``k``/``v``/``pad_mask`` hold this shard's keys [m_offset, m_offset+M) of ``m_total``."""
+    ``k``/``v``/``pad_mask`` hold this shard's keys [m_offset, m_offset+M) of ``m_total``.  ``out`` may
+    supply the three (contiguous, float32) destination tensors."""
     q, k, v, _ = _prep(q, k, v)
     with torch.cuda.device(k.device):
         p, keep = _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, m_total, m_offset, impl)
-        part_o = torch.empty(p.B, p.H, p.N, p.dv, dtype=torch.float32, device=k.device)
-        part_m = torch.empty(p.B, p.H, p.N, dtype=torch.float32, device=k.device)
-        part_l = torch.empty(p.B, p.H, p.N, dtype=torch.float32, device=k.device)
+        if out is not None:
+            part_o, part_m, part_l = out
+            if (tuple(part_o.shape) != (p.B, p.H, p.N, p.dv) or tuple(part_m.shape) != (p.B, p.H, p.N)
+                    or tuple(part_l.shape) != (p.B, p.H, p.N)):
+                raise ValueError("attention_partial: `out` tensors have the wrong shape")
+            for t in out:
+                if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                    raise ValueError("attention_partial: `out` tensors must be contiguous float32 CUDA tensors")
+        else:
+            part_o = torch.empty(p.B, p.H, p.N, p.dv, dtype=torch.float32, device=k.device)
+            part_m = torch.empty(p.B, p.H, p.N, dtype=torch.float32, device=k.device)
+            part_l = torch.empty(p.B, p.H, p.N, dtype=torch.float32, device=k.device)
         p.write_partial = 1
         p.part_o, p.part_m, p.part_l = part_o.data_ptr(), part_m.data_ptr(), part_l.data_ptr()
         _run_attn(p, k.device)
@@ -221,6 +231,19 @@ def combine_partials(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.T
         p.dtype = _pcv_dtype(cdt)
         check(_lib.lib().pcv_attn_combine(C.byref(p), _stream()), "pcv_attn_combine")
     return out if cdt == out_dtype else out.to(out_dtype)
+
+
+def rescale_partial_(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.Tensor, new_m: torch.Tensor) -> None:
+    """In place: re-express a partial state relative to the row maxima ``new_m`` (>= part_m)."""
+    _require_cuda(part_o, part_m, part_l, new_m)
+    for t in (part_o, part_m, part_l, new_m):
+        if not t.is_contiguous() or t.dtype != torch.float32:
+            raise ValueError("rescale_partial_ expects contiguous float32 tensors")
+    p = RescaleParams()
+    p.part_o, p.part_m, p.part_l, p.new_m = part_o.data_ptr(), part_m.data_ptr(), part_l.data_ptr(), new_m.data_ptr()
+    p.rows, p.dv = part_m.numel(), part_o.shape[-1]
+    with torch.cuda.device(part_o.device):
+        check(_lib.lib().pcv_partial_rescale(C.byref(p), _stream()), "pcv_partial_rescale")
 
 
 def rotary(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: bool) -> torch.Tensor:

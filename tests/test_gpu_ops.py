@@ -1,0 +1,174 @@
+"""-m gpu parity tests of the C-ABI ops against the CPU oracle (same seeded, bf16-rounded operands)."""
+import pytest
+import torch
+
+from gpu_util import assert_close, oracle_core
+from oracle import mha_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_SIMT = 6e-3
+REL_TC = 1.2e-2
+
+
+def _qkv(B, N, M, H, dqk, dv, Bq=None, seed=0, q_gain=1.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    Bq = B if Bq is None else Bq
+    q = (torch.randn(Bq, N, H * dqk, generator=g) * q_gain).to(dtype).cuda()
+    k = torch.randn(B, M, H * dqk, generator=g).to(dtype).cuda()
+    v = torch.randn(B, M, H * dv, generator=g).to(dtype).cuda()
+    return q, k, v
+
+
+SHAPES = [
+    # B, N, M, H, dqk, dv
+    (2, 8, 24, 4, 8, 8),
+    (1, 33, 100, 2, 16, 16),
+    (2, 64, 257, 8, 32, 160),     # MLM encoder head dims
+    (1, 32, 784, 1, 131, 131),    # MNIST encoder: odd head dim
+    (2, 1, 77, 4, 24, 24),        # decode step: one query
+    (1, 130, 200, 2, 96, 96),     # Perceiver AR head dim
+    (1, 40, 96, 1, 322, 322),     # optical-flow encoder head dim
+    (1, 70, 64, 1, 512, 512),     # optical-flow decoder head dim
+    (2, 256, 512, 2, 128, 128),   # north-star head dim, small
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_attention_matches_oracle(shape, impl):
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, dqk, dv = shape
+    q, k, v = _qkv(B, N, M, H, dqk, dv)
+    scale = dqk ** -0.5
+    out = ops.attention(q, k, v, H, scale, impl=impl)
+    assert out.shape == (B, N, H * dv) and out.dtype == torch.bfloat16
+    assert_close(out, oracle_core(q, k, v, H, scale), REL_SIMT if impl == "simt" else REL_TC, f"{impl} {shape}")
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_masks_broadcast_and_degenerate_rows(impl):
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, d = 3, 40, 300, 2, 64
+    q, k, v = _qkv(B, N, M, H, d, d, Bq=1, seed=3)
+    pad = torch.zeros(B, M, dtype=torch.bool)
+    pad[0, :37] = True            # left padding
+    pad[1, :] = True              # fully padded row -> uniform average over ALL M values
+    pad[2, 250:] = True           # right padding across a tile boundary
+    rel = REL_SIMT if impl == "simt" else REL_TC
+    for causal in (False, True):
+        out = ops.attention(q, k, v, H, d ** -0.5, pad_mask=pad.cuda(), causal=causal, impl=impl)
+        assert_close(out, oracle_core(q, k, v, H, d ** -0.5, pad, causal), rel, f"{impl} causal={causal}")
+    # the fully padded batch row equals the plain mean of its values
+    mean_v = v[1].float().mean(0).cpu()
+    assert_close(out[1, 0], mean_v, 2e-2, "uniform row")
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_peaked_and_flat_softmax_regimes(impl):
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, d = 1, 128, 4096, 2, 128
+    rel = REL_SIMT if impl == "simt" else REL_TC
+    for gain, name in ((0.02, "flat"), (6.0, "peaked")):
+        q, k, v = _qkv(B, N, M, H, d, d, seed=11, q_gain=gain)
+        out = ops.attention(q, k, v, H, d ** -0.5, impl=impl)
+        assert_close(out, oracle_core(q, k, v, H, d ** -0.5), rel, f"{impl} {name}")
+
+
+def test_fp32_inputs_are_rounded_to_bf16_at_the_boundary():
+    from perceiver_io_b200 import ops
+
+    q, k, v = _qkv(1, 16, 64, 2, 32, 32, dtype=torch.float32)
+    out = ops.attention(q, k, v, 2, 32 ** -0.5)
+    assert out.dtype == torch.float32
+    ref = oracle_core(q.bfloat16(), k.bfloat16(), v.bfloat16(), 2, 32 ** -0.5)
+    assert_close(out, ref, REL_TC, "fp32 boundary")
+
+
+def test_fp16_inputs():
+    from perceiver_io_b200 import ops
+
+    q, k, v = _qkv(2, 16, 100, 2, 64, 64, dtype=torch.float16)
+    out = ops.attention(q, k, v, 2, 0.125)
+    assert out.dtype == torch.float16
+    assert_close(out, oracle_core(q, k, v, 2, 0.125), 4e-3, "fp16")
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("causal", [False, True])
+def test_m_shards_merge_to_the_unsharded_result(impl, causal):
+    """Partial states of uneven M-shards (one of them fully padded for batch row 0) merged by
+    pcv_attn_combine equal the single-pass output and the oracle."""
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, d = 2, 48, 1000, 4, 64
+    q, k, v = _qkv(B, N, M, H, d, d, seed=5, q_gain=3.0)
+    pad = torch.zeros(B, M, dtype=torch.bool)
+    pad[0, 300:700] = True
+    pad[1, :10] = True
+    padc = pad.cuda()
+    cuts = [0, 300, 700, 1000]
+    parts = [ops.attention_partial(q, k[:, a:b], v[:, a:b], H, d ** -0.5, pad_mask=padc[:, a:b], causal=causal,
+                                   m_total=M, m_offset=a, impl=impl) for a, b in zip(cuts[:-1], cuts[1:])]
+    merged = ops.combine_partials(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]),
+                                  torch.stack([p[2] for p in parts]))
+    ref = oracle_core(q, k, v, H, d ** -0.5, pad, causal)
+    rel = REL_SIMT if impl == "simt" else REL_TC
+    assert_close(merged, ref, rel, "merged shards")
+    single = ops.attention(q, k, v, H, d ** -0.5, pad_mask=padc, causal=causal, impl=impl)
+    assert_close(merged, single.double(), 1e-2, "merged vs single pass")
+    # the partial state itself matches the oracle's (log2-domain max, denominator)
+    qh = O.split_heads(q.cpu().double(), H)
+    kh, vh = O.split_heads(k.cpu().double(), H), O.split_heads(v.cpu().double(), H)
+    po, pm, pl = O.partial_state(qh, kh[:, :, :300], vh[:, :, :300], d ** -0.5, pad[:, :300], causal, M, 0)
+    w = torch.exp2(parts[0][1].cpu().double() - pm)     # kernel max may differ from the true max (lazy rescale)
+    assert_close(parts[0][2].cpu().double() * w, pl, 1e-2, "denominator")
+
+
+def test_rotary_matches_oracle():
+    from perceiver_io_b200 import ops
+
+    g = torch.Generator().manual_seed(2)
+    B, n, H, d, f = 2, 37, 4, 24, 12
+    x = torch.randn(B, n, H * d, generator=g).bfloat16()
+    pos = O.positions(B, n + 5, torch.tensor([[0], [7]]))
+    angles = O.frequency_angles(pos, f)
+    for right in (True, False):
+        y = ops.rotary(x.cuda(), H, angles.cuda(), right)
+        ref = O.merge_heads(O.rotate(O.split_heads(x.double(), H), angles.double(), right))
+        assert_close(y, ref, 5e-3, f"rotary right_align={right}")
+    # batch-1 angles broadcast, full-width rotation
+    y = ops.rotary(x.cuda(), H, O.frequency_angles(O.positions(1, n), d).cuda(), False)
+    ref = O.merge_heads(O.rotate(O.split_heads(x.double(), H), O.frequency_angles(O.positions(1, n), d).double(), False))
+    assert_close(y, ref, 5e-3, "rotary broadcast")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_kv_append_is_bit_exact(dtype):
+    from perceiver_io_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    for (B, L, n, Ck, Cv) in [(2, 0, 5, 64, 96), (3, 17, 1, 64, 64), (1, 9, 4, 20, 6)]:
+        kc, vc = torch.randn(B, L, Ck, generator=g).to(dtype), torch.randn(B, L, Cv, generator=g).to(dtype)
+        kn, vn = torch.randn(B, n, Ck, generator=g).to(dtype), torch.randn(B, n, Cv, generator=g).to(dtype)
+        k, v = ops.kv_append(kc.cuda(), vc.cuda(), kn.cuda(), vn.cuda())
+        assert torch.equal(k.cpu(), torch.cat([kc, kn], 1)) and torch.equal(v.cpu(), torch.cat([vc, vn], 1))
+    # strided (sliced) cache views, as produced by the HF-side truncation (core/huggingface.py:146-156)
+    big_k, big_v = torch.randn(2, 12, 32, generator=g).bfloat16().cuda(), torch.randn(2, 12, 32, generator=g).bfloat16().cuda()
+    kn = torch.randn(2, 1, 32, generator=g).bfloat16().cuda()
+    k, v = ops.kv_append(big_k[:, -7:], big_v[:, -7:], kn, kn)
+    assert torch.equal(k, torch.cat([big_k[:, -7:], kn], 1)) and torch.equal(v, torch.cat([big_v[:, -7:], kn], 1))
+
+
+def test_errors_surface_as_exceptions():
+    from perceiver_io_b200 import ops
+    from perceiver_io_b200._lib import PcvError
+
+    q, k, v = _qkv(1, 8, 16, 2, 16, 16)
+    with pytest.raises(ValueError):
+        ops.attention(q, k[:, :, :16], v, 2, 1.0)
+    with pytest.raises(PcvError, match="m_total"):
+        ops.attention_partial(q, k, v, 2, 1.0, m_total=8, m_offset=0)
