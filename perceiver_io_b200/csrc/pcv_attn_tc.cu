@@ -1,7 +1,848 @@
-// placeholder until the tcgen05 kernel lands
+// pcv_attn_tc.cu — fused attention forward on the 5th-generation tensor cores (sm_100a only).
+//
+//   S = Q K^T  (tcgen05.mma, SS: Q and K tiles in SWIZZLE_128B shared memory, S in TMEM)
+//   P = 2^(S*scale*log2e - m)   (softmax warps: one thread per query row, S read with tcgen05.ld,
+//                                 P written back to TMEM as bf16 over the S columns, tcgen05.st)
+//   O += P V   (tcgen05.mma, TS: P from TMEM, V tile MN-major in shared memory, O in TMEM)
+//
+// CTA = 2 query tiles of 128 rows of one (batch, head) x a contiguous range of 128-key tiles.
+// Warp roles (384 threads, warps 10-11 idle): warps 0-3 softmax of query tile 0, warps 4-7 softmax of query tile 1,
+// warp 8 (one lane) issues every tcgen05.mma, warp 9 (one lane) issues every TMA load.  While the
+// softmax warps of one query tile exponentiate, the tensor core works on the other tile.
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i aliases S_i[0,64).
+//
+// Online softmax with a lazily updated reference maximum: the exponent reference m only moves when the
+// running row maximum exceeds it by more than 8 (log2 units), so O is rescaled in TMEM rarely; the
+// softmax warp that owns the row does that rescale itself (S_i(j) complete implies P_i V_(j-1) complete
+// because tcgen05.mma executes in issue order).
+//
+// Work distribution is a host-built segment table (stream-K over the key axis): segments that cover a
+// whole (b,h,query-block) write the final output; split ones write (numerator, max, denominator) slots that
+// tc_combine_kernel merges.  Semantics are those of include/pcv_attn.h (finite mask fill, uniform rows).
 #include "pcv_common.cuh"
+#include "pcv_sm100.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
 namespace pcv {
-bool attn_tc_supported(const pcv_attn_params& p, const char** why) { *why = "tcgen05 kernel not built yet"; return false; }
-int launch_attn_tc(const pcv_attn_params& p, cudaStream_t stream) { set_error("tcgen05 kernel not built yet"); return PCV_ERR_UNSUPPORTED; }
-int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) { *bytes = 0; return PCV_OK; }
+namespace {
+
+using namespace sm100;
+
+constexpr int kTileM = 128;            // query rows per tile (UMMA M)
+constexpr int kTileN = 128;            // keys per tile (UMMA N of QK^T, K of PV)
+constexpr int kBoxBytes = kTileN * 128;  // one TMA box: 128 rows x 64 16-bit channels, SWIZZLE_128B
+constexpr int kRowsPerUnit = 2 * kTileM;
+constexpr int kThreads = 384;  // 12 warps: 8 softmax + MMA + TMA + 2 idle (fills the 3rd warpgroup for setmaxnreg)
+constexpr int kMmaWarp = 8;
+constexpr int kTmaWarp = 9;
+constexpr float kRescaleThreshold = 8.f;  // log2 units
+
+struct Segment {
+  int b, h;
+  int q0;      // first query row of the block (multiple of 256)
+  int ntile;   // 1 or 2 active query tiles
+  int t0, t1;  // key tiles [t0, t1)
+  int slot;    // >= 0: partial slot index; -1: the segment covers every key tile (final)
+  int pad_;
+};
+
+struct UnitRec {  // a (b,h,query-block) whose key range was split over several segments
+  int b, h, q0;
+  int slot_begin, slot_count;
+  int pad_[3];
+};
+
+struct TcParams {
+  const Segment* segs;
+  const int* cta_seg_begin;
+  int B, H, N, M, dv;
+  float scale_log2;
+  int causal, causal_shift;  // key j (local) masked for query n iff j > n + causal_shift
+  const uint32_t* pad_bits;  // (B, pad_wpr) bit set = padding key; nullptr if no mask
+  int pad_wpr;
+  int q_bcast;
+  void* out;
+  int64_t osb, osn, osh;
+  int write_partial;
+  float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
+  float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
+};
+
+template <int DQK, int DV>
+struct Cfg {
+  static constexpr int kQBoxes = DQK / 64;
+  static constexpr int kVBoxes = DV / 64;
+  static constexpr int kQTileBytes = kQBoxes * kBoxBytes;
+  static constexpr int kQBytes = 2 * kQTileBytes;
+  static constexpr int kStageBytes = (DQK > DV ? DQK : DV) / 64 * kBoxBytes;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kMaxSmem = 232448 - 1024;  // leave room for the 1024-byte alignment slack
+  static constexpr int kStagesRaw = (kMaxSmem - kQBytes - kBarrierBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kBarrierBytes + 1024;
+  static_assert(kStages >= 3, "need at least K_j, V_j, K_(j+1) in flight");
+  static_assert(DQK % 64 == 0 && DV % 64 == 0 && DQK <= 128 && DV <= 128, "padded head dims");
+};
+
+struct Barriers {
+  uint64_t q_full, q_empty;
+  uint64_t kv_full[8], kv_empty[8];
+  uint64_t s_full[2], p_full[2], o_full[2], o_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, bool bf16) {
+  uint32_t r;
+  if (bf16)
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
+
+// --------------------------------------------------------------------------------------------------
+// softmax + epilogue role: 128 threads, thread = one query row of tile `wg`
+// --------------------------------------------------------------------------------------------------
+template <int DQK, int DV, bool BF16>
+__device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, int wg, int row, int seg_lo,
+                                             int seg_hi) {
+  const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
+  const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
+  const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
+  uint32_t n_s = 0, n_o = 0;
+
+  for (int sg = seg_lo; sg < seg_hi; ++sg) {
+    const Segment seg = p.segs[sg];
+    if (wg == 1 && seg.ntile < 2) continue;
+    const int n = seg.q0 + wg * kTileM + row;
+    const int cshift = n + p.causal_shift;  // local key index j is causally masked iff j > cshift
+    float m_ref = -INFINITY, l = 0.f;
+
+    for (int t = seg.t0; t < seg.t1; ++t) {
+      mbar_wait(&bar.s_full[wg], n_s & 1);
+      ++n_s;
+      tc_fence_after_sync();
+
+      uint32_t s[4][32];
+      tmem_ld32(tS + 0, s[0]);
+      tmem_ld32(tS + 32, s[1]);
+      tmem_ld32(tS + 64, s[2]);
+      tmem_ld32(tS + 96, s[3]);
+      tmem_wait_ld();
+
+      const int j0 = t * kTileN;
+      uint4 mw = make_uint4(0, 0, 0, 0);
+      if (p.pad_bits != nullptr)
+        mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
+      // warp-uniform on purpose: the tcgen05.st below is .sync.aligned and must not sit behind a
+      // lane-divergent branch (the causal test differs between the rows of a warp on diagonal tiles)
+      const bool masked_tile =
+          __any_sync(0xffffffffu, (j0 + kTileN > p.M) || ((mw.x | mw.y | mw.z | mw.w) != 0u) ||
+                                      (p.causal && (j0 + kTileN - 1 > cshift)));
+
+      float m_tile;
+      if (!masked_tile) {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[0][c]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[1][c]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[2][c]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[3][c]));
+        }
+        m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      } else {
+        // scores -> log2 domain with the reference's finite fill for padding / causal keys and -inf
+        // (weight exactly 0) for keys beyond the end of the tensor
+        const int oob_from = p.M - j0;
+        const int cmax = p.causal ? (cshift - j0) : 0x7fffffff;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t word = q4 == 0 ? mw.x : (q4 == 1 ? mw.y : (q4 == 2 ? mw.z : mw.w));
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int col = q4 * 32 + c;
+            float tv = __uint_as_float(s[q4][c]) * p.scale_log2;
+            if (((word >> c) & 1u) || col > cmax) tv = kMaskedScore;
+            if (col >= oob_from) tv = -INFINITY;
+            mx = fmaxf(mx, tv);
+            s[q4][c] = __float_as_uint(tv);
+          }
+        }
+        m_tile = mx;
+      }
+
+      // lazily move the exponent reference; rescale the accumulator row when it moves
+      const float m_new = fmaxf(m_ref, m_tile);
+      float alpha = 1.f;
+      bool moved = false;
+      if (m_new - m_ref > kRescaleThreshold) {
+        alpha = ex2(m_ref - m_new);
+        l *= alpha;
+        m_ref = m_new;
+        moved = (t > seg.t0);
+      }
+      if (__any_sync(0xffffffffu, moved)) {
+#pragma unroll
+        for (int ch = 0; ch < DV / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          tmem_st32(tO + ch * 32, o);
+        }
+      }
+
+      float sum0 = 0.f, sum1 = 0.f;
+      const float neg_m = -m_ref;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int q4 = half * 2 + qq;
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float e0, e1;
+            if (!masked_tile) {
+              e0 = ex2(fmaf(__uint_as_float(s[q4][c]), p.scale_log2, neg_m));
+              e1 = ex2(fmaf(__uint_as_float(s[q4][c + 1]), p.scale_log2, neg_m));
+            } else {
+              e0 = ex2(__uint_as_float(s[q4][c]) + neg_m);
+              e1 = ex2(__uint_as_float(s[q4][c + 1]) + neg_m);
+            }
+            sum0 += e0;
+            sum1 += e1;
+            pk[qq * 16 + (c >> 1)] = pack2(e0, e1, BF16);
+          }
+        }
+        tmem_st32(tS + half * 32, pk);  // P (16-bit) over S columns [0,64)
+      }
+      l += sum0 + sum1;
+      tmem_wait_st();
+      tc_fence_before_sync();
+      mbar_arrive(&bar.p_full[wg]);
+    }
+
+    // ---- epilogue: O row -> global ------------------------------------------------------------------
+    mbar_wait(&bar.o_full[wg], n_o & 1);
+    ++n_o;
+    tc_fence_after_sync();
+    const bool valid = n < p.N;
+    if (seg.slot < 0 && !p.write_partial) {
+      const float inv = 1.f / l;
+      char* orow = reinterpret_cast<char*>(p.out) +
+                   2 * ((int64_t)seg.b * p.osb + (int64_t)n * p.osn + (int64_t)seg.h * p.osh);
+#pragma unroll
+      for (int ch = 0; ch < DV / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tO + ch * 32, o);
+        tmem_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const int col = ch * 32 + c8 * 8;
+            if (col < p.dv) {
+              uint4 w;
+              w.x = pack2(__uint_as_float(o[c8 * 8 + 0]) * inv, __uint_as_float(o[c8 * 8 + 1]) * inv, BF16);
+              w.y = pack2(__uint_as_float(o[c8 * 8 + 2]) * inv, __uint_as_float(o[c8 * 8 + 3]) * inv, BF16);
+              w.z = pack2(__uint_as_float(o[c8 * 8 + 4]) * inv, __uint_as_float(o[c8 * 8 + 5]) * inv, BF16);
+              w.w = pack2(__uint_as_float(o[c8 * 8 + 6]) * inv, __uint_as_float(o[c8 * 8 + 7]) * inv, BF16);
+              *reinterpret_cast<uint4*>(orow + 2 * col) = w;
+            }
+          }
+        }
+      }
+    } else {
+      float* dst;
+      int ncols;
+      bool store;
+      if (seg.slot < 0) {  // whole key range, caller wants the un-normalised state
+        const int64_t r = ((int64_t)seg.b * p.H + seg.h) * p.N + n;
+        dst = p.fin_o + r * p.dv;
+        ncols = p.dv;
+        store = valid;
+        if (valid) {
+          p.fin_m[r] = m_ref;
+          p.fin_l[r] = l;
+        }
+      } else {
+        const int64_t r = (int64_t)seg.slot * kRowsPerUnit + wg * kTileM + row;
+        dst = p.slot_o + r * DV;
+        ncols = DV;
+        store = true;
+        p.slot_m[r] = m_ref;
+        p.slot_l[r] = l;
+      }
+#pragma unroll
+      for (int ch = 0; ch < DV / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tO + ch * 32, o);
+        tmem_wait_ld();
+        if (store) {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const int col = ch * 32 + c4 * 4;
+            if (col < ncols)
+              *reinterpret_cast<uint4*>(dst + col) = make_uint4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+    mbar_arrive(&bar.o_empty[wg]);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// the kernel
+// --------------------------------------------------------------------------------------------------
+template <int DQK, int DV, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+               const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
+  using C = Cfg<DQK, DV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + C::kQBytes;
+  Barriers& bar = *reinterpret_cast<Barriers*>(smem + C::kQBytes + C::kStages * C::kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seg_lo = p.cta_seg_begin[blockIdx.x];
+  const int seg_hi = p.cta_seg_begin[blockIdx.x + 1];
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar.q_full, 1);
+    mbar_init(&bar.q_empty, 1);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&bar.kv_full[i], 1);
+      mbar_init(&bar.kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar.s_full[i], 1);
+      mbar_init(&bar.p_full[i], kTileM);
+      mbar_init(&bar.o_full[i], 1);
+      mbar_init(&bar.o_empty[i], kTileM);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(&bar.tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  if (warp < 8) {
+    reg_alloc<224>();  // softmax warpgroups take the registers the control warpgroup gives up
+    softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
+  } else {
+    reg_dealloc<64>();
+  }
+  if (warp == kTmaWarp) {
+    if (lane == 0) {
+      // ===== TMA producer: Q once per segment, then K_j, V_j through the ring =====
+      uint32_t it = 0, n_q = 0;
+      for (int sg = seg_lo; sg < seg_hi; ++sg) {
+        const Segment seg = p.segs[sg];
+        const int bq = p.q_bcast ? 0 : seg.b;
+        mbar_wait(&bar.q_empty, (n_q & 1) ^ 1);
+        ++n_q;
+        mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(seg.ntile * C::kQTileBytes));
+        for (int i = 0; i < seg.ntile; ++i)
+          for (int bx = 0; bx < C::kQBoxes; ++bx)
+            tma_load_4d(q_smem + i * C::kQTileBytes + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64,
+                        seg.q0 + i * kTileM, seg.h, bq);
+        for (int t = seg.t0; t < seg.t1; ++t) {
+          {
+            const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+            mbar_wait(&bar.kv_empty[slot], par ^ 1);
+            mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(C::kQBoxes * kBoxBytes));
+            for (int bx = 0; bx < C::kQBoxes; ++bx)
+              tma_load_4d(kv_smem + slot * C::kStageBytes + bx * kBoxBytes, &tmap_k, &bar.kv_full[slot], bx * 64,
+                          t * kTileN, seg.h, seg.b);
+            ++it;
+          }
+          {
+            const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+            mbar_wait(&bar.kv_empty[slot], par ^ 1);
+            mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(C::kVBoxes * kBoxBytes));
+            for (int bx = 0; bx < C::kVBoxes; ++bx)
+              tma_load_4d(kv_smem + slot * C::kStageBytes + bx * kBoxBytes, &tmap_v, &bar.kv_full[slot], bx * 64,
+                          t * kTileN, seg.h, seg.b);
+            ++it;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_qk = make_idesc(kTileM, kTileN, BF16, false);
+      constexpr uint32_t idesc_pv = make_idesc(kTileM, DV, BF16, true);
+      const uint32_t tmem = bar.tmem_base;
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t kv_addr = smem_u32(kv_smem);
+      uint32_t it = 0, n_q = 0, n_p[2] = {0, 0}, n_oe[2] = {0, 0};
+
+      auto issue_qk = [&](int i, uint32_t k_slot) {
+        const uint32_t a0 = q_addr + i * C::kQTileBytes;
+        const uint32_t b0 = kv_addr + k_slot * C::kStageBytes;
+#pragma unroll
+        for (int kk = 0; kk < DQK / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+          mma_ss(tmem + i * 128, make_smem_desc(a0 + off, 16, 1024), make_smem_desc(b0 + off, 16, 1024), idesc_qk,
+                 kk > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int i, uint32_t v_slot, bool accumulate) {
+        const uint32_t b0 = kv_addr + v_slot * C::kStageBytes;
+#pragma unroll
+        for (int kk = 0; kk < kTileN / 16; ++kk) {
+          // V tile is MN-major: 16 keys = 16 rows of 128 bytes; 64-channel blocks kBoxBytes apart
+          mma_ts(tmem + 256 + i * 128, tmem + i * 128 + kk * 8, make_smem_desc(b0 + kk * 2048, kBoxBytes, 1024),
+                 idesc_pv, (accumulate || kk > 0) ? 1u : 0u);
+        }
+      };
+
+      for (int sg = seg_lo; sg < seg_hi; ++sg) {
+        const Segment seg = p.segs[sg];
+        const bool two = seg.ntile == 2;
+        const int nt = seg.t1 - seg.t0;
+        mbar_wait(&bar.q_full, n_q & 1);
+        ++n_q;
+
+        uint32_t k_slot = it % C::kStages;
+        mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1);
+        ++it;
+        tc_fence_after_sync();
+        issue_qk(0, k_slot);
+        tc_commit(&bar.s_full[0]);
+        if (two) {
+          issue_qk(1, k_slot);
+          tc_commit(&bar.s_full[1]);
+        }
+        tc_commit(&bar.kv_empty[k_slot]);
+
+        for (int j = 0; j < nt; ++j) {
+          const uint32_t v_slot = it % C::kStages;
+          mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1);
+          ++it;
+          if (j == 0) {
+            mbar_wait(&bar.o_empty[0], (n_oe[0] & 1) ^ 1);
+            ++n_oe[0];
+          }
+          mbar_wait(&bar.p_full[0], n_p[0] & 1);
+          ++n_p[0];
+          tc_fence_after_sync();
+          issue_pv(0, v_slot, j > 0);
+          const bool more = (j + 1 < nt);
+          if (more) {
+            k_slot = it % C::kStages;
+            mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1);
+            ++it;
+            tc_fence_after_sync();
+            issue_qk(0, k_slot);
+            tc_commit(&bar.s_full[0]);
+          }
+          if (two) {
+            if (j == 0) {
+              mbar_wait(&bar.o_empty[1], (n_oe[1] & 1) ^ 1);
+              ++n_oe[1];
+            }
+            mbar_wait(&bar.p_full[1], n_p[1] & 1);
+            ++n_p[1];
+            tc_fence_after_sync();
+            issue_pv(1, v_slot, j > 0);
+          }
+          tc_commit(&bar.kv_empty[v_slot]);
+          if (more) {
+            if (two) {
+              issue_qk(1, k_slot);
+              tc_commit(&bar.s_full[1]);
+            }
+            tc_commit(&bar.kv_empty[k_slot]);
+          }
+        }
+        tc_commit(&bar.q_empty);
+        tc_commit(&bar.o_full[0]);
+        if (two) tc_commit(&bar.o_full[1]);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(bar.tmem_base, 512);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// merge of split units (one warp per query row)
+// --------------------------------------------------------------------------------------------------
+template <int DV, bool BF16>
+__global__ void __launch_bounds__(256) tc_combine_kernel(const UnitRec* __restrict__ units, const TcParams p) {
+  const UnitRec u = units[blockIdx.x];
+  const int row = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int n = u.q0 + row;
+  if (n >= p.N) return;
+  float m = -INFINITY;
+  for (int s = 0; s < u.slot_count; ++s) m = fmaxf(m, p.slot_m[(int64_t)(u.slot_begin + s) * kRowsPerUnit + row]);
+  float l = 0.f;
+  for (int s = 0; s < u.slot_count; ++s) {
+    const int64_t r = (int64_t)(u.slot_begin + s) * kRowsPerUnit + row;
+    l += p.slot_l[r] * exp2f(p.slot_m[r] - m);
+  }
+  for (int c = lane * 4; c < DV; c += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < u.slot_count; ++s) {
+      const int64_t r = (int64_t)(u.slot_begin + s) * kRowsPerUnit + row;
+      const float w = exp2f(p.slot_m[r] - m);
+      const float4 x = *reinterpret_cast<const float4*>(p.slot_o + r * DV + c);
+      acc.x = fmaf(x.x, w, acc.x);
+      acc.y = fmaf(x.y, w, acc.y);
+      acc.z = fmaf(x.z, w, acc.z);
+      acc.w = fmaf(x.w, w, acc.w);
+    }
+    if (c >= p.dv) continue;
+    if (!p.write_partial) {
+      const float inv = 1.f / l;
+      uint2 w2;
+      w2.x = pack2(acc.x * inv, acc.y * inv, BF16);
+      w2.y = pack2(acc.z * inv, acc.w * inv, BF16);
+      char* orow = reinterpret_cast<char*>(p.out) + 2 * ((int64_t)u.b * p.osb + (int64_t)n * p.osn + (int64_t)u.h * p.osh);
+      *reinterpret_cast<uint2*>(orow + 2 * c) = w2;
+    } else {
+      const int64_t r = ((int64_t)u.b * p.H + u.h) * p.N + n;
+      *reinterpret_cast<float4*>(p.fin_o + r * p.dv + c) = acc;
+    }
+  }
+  if (p.write_partial && lane == 0) {
+    const int64_t r = ((int64_t)u.b * p.H + u.h) * p.N + n;
+    p.fin_m[r] = m;
+    p.fin_l[r] = l;
+  }
+}
+
+// pad_mask bytes (B, M) -> bit words (B, wpr), wpr = 4 * ceil(M/128); bit set = padding key
+__global__ void __launch_bounds__(256) pack_pad_kernel(const uint8_t* __restrict__ pad, int64_t stride_b, int B, int M,
+                                                       int wpr, uint32_t* __restrict__ bits) {
+  const int64_t total = (int64_t)B * wpr;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / wpr), w = (int)(idx % wpr);
+    uint32_t word = 0;
+    const int j0 = w * 32;
+    for (int i = 0; i < 32; ++i) {
+      const int j = j0 + i;
+      if (j < M && pad[(int64_t)b * stride_b + j] != 0) word |= (1u << i);
+    }
+    bits[idx] = word;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// host: plan (segment table), tensor maps, launch
+// --------------------------------------------------------------------------------------------------
+struct Plan {
+  int num_ctas = 0, num_slots = 0, num_units = 0;
+  std::vector<Segment> segs;
+  std::vector<int> cta_seg_begin;
+  std::vector<UnitRec> units;
+  Segment* d_segs = nullptr;
+  int* d_cta = nullptr;
+  UnitRec* d_units = nullptr;
+};
+
+void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms) {
+  const int QB = (N + kRowsPerUnit - 1) / kRowsPerUnit;
+  const int T = (M + kTileN - 1) / kTileN;
+  const int BH = B * H;
+  auto ntile_of = [&](int qb) { return (N - qb * kRowsPerUnit) > kTileM ? 2 : 1; };
+  std::vector<std::vector<Segment>> per_cta;
+  const bool split_mode = QB <= 8 && QB <= num_sms;
+  if (split_mode) {
+    // groups of QB CTAs walk the flattened (b*h, key tile) space together, one query block each, so that
+    // the members of a group stream the same K/V tiles at the same time (they meet in L2)
+    int ngroups = num_sms / QB;
+    const int64_t W = (int64_t)BH * T;
+    if (ngroups > W) ngroups = (int)W;
+    per_cta.resize((size_t)ngroups * QB);
+    std::map<std::pair<int, int>, std::vector<int>> unit_slots;  // (bh, qb) -> slots
+    for (int g = 0; g < ngroups; ++g) {
+      int64_t pos = W * g / ngroups;
+      const int64_t end = W * (g + 1) / ngroups;
+      while (pos < end) {
+        const int bh = (int)(pos / T), t0 = (int)(pos % T);
+        const int t1 = (int)std::min<int64_t>(T, t0 + (end - pos));
+        for (int r = 0; r < QB; ++r) {
+          Segment s{};
+          s.b = bh / H; s.h = bh % H; s.q0 = r * kRowsPerUnit; s.ntile = ntile_of(r); s.t0 = t0; s.t1 = t1;
+          if (t0 == 0 && t1 == T) {
+            s.slot = -1;
+          } else {
+            s.slot = pl.num_slots++;
+            unit_slots[{bh, r}].push_back(s.slot);
+          }
+          per_cta[(size_t)g * QB + r].push_back(s);
+        }
+        pos += t1 - t0;
+      }
+    }
+    // slots of one unit must be contiguous for the combine kernel: renumber
+    std::map<int, int> remap;
+    int next = 0;
+    for (auto& kv : unit_slots) {
+      UnitRec u{};
+      u.b = kv.first.first / H; u.h = kv.first.first % H; u.q0 = kv.first.second * kRowsPerUnit;
+      u.slot_begin = next; u.slot_count = (int)kv.second.size();
+      for (int old : kv.second) remap[old] = next++;
+      pl.units.push_back(u);
+    }
+    for (auto& v : per_cta)
+      for (auto& s : v)
+        if (s.slot >= 0) s.slot = remap[s.slot];
+  } else {
+    // many query blocks: whole (b,h,query-block) units, contiguous chunks per CTA, no splitting
+    const int64_t U = (int64_t)BH * QB;
+    const int nctas = (int)std::min<int64_t>(num_sms, U);
+    per_cta.resize(nctas);
+    for (int c = 0; c < nctas; ++c) {
+      for (int64_t u = U * c / nctas; u < U * (c + 1) / nctas; ++u) {
+        const int bh = (int)(u / QB), qb = (int)(u % QB);
+        Segment s{};
+        s.b = bh / H; s.h = bh % H; s.q0 = qb * kRowsPerUnit; s.ntile = ntile_of(qb); s.t0 = 0; s.t1 = T; s.slot = -1;
+        per_cta[c].push_back(s);
+      }
+    }
+  }
+  pl.num_ctas = (int)per_cta.size();
+  pl.cta_seg_begin.assign(1, 0);
+  for (auto& v : per_cta) {
+    for (auto& s : v) pl.segs.push_back(s);
+    pl.cta_seg_begin.push_back((int)pl.segs.size());
+  }
+  pl.num_units = (int)pl.units.size();
+}
+
+std::mutex g_plan_mu;
+std::map<std::tuple<int, int, int, int, int, int>, Plan*> g_plans;  // (device, B, H, N, M, sms)
+
+int get_plan(int B, int H, int N, int M, Plan** out) {
+  int dev = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  int sms = 0;
+  PCV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  auto key = std::make_tuple(dev, B, H, N, M, sms);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) {
+    *out = it->second;
+    return PCV_OK;
+  }
+  Plan* pl = new Plan();
+  build_plan(*pl, B, H, N, M, sms);
+  PCV_CHECK_CUDA(cudaMalloc(&pl->d_segs, sizeof(Segment) * pl->segs.size()));
+  PCV_CHECK_CUDA(cudaMalloc(&pl->d_cta, sizeof(int) * pl->cta_seg_begin.size()));
+  PCV_CHECK_CUDA(cudaMemcpy(pl->d_segs, pl->segs.data(), sizeof(Segment) * pl->segs.size(), cudaMemcpyHostToDevice));
+  PCV_CHECK_CUDA(cudaMemcpy(pl->d_cta, pl->cta_seg_begin.data(), sizeof(int) * pl->cta_seg_begin.size(),
+                            cudaMemcpyHostToDevice));
+  if (!pl->units.empty()) {
+    PCV_CHECK_CUDA(cudaMalloc(&pl->d_units, sizeof(UnitRec) * pl->units.size()));
+    PCV_CHECK_CUDA(cudaMemcpy(pl->d_units, pl->units.data(), sizeof(UnitRec) * pl->units.size(), cudaMemcpyHostToDevice));
+  }
+  if (g_plans.size() > 256) {  // bounded cache: drop everything (plans are cheap to rebuild)
+    for (auto& kv : g_plans) {
+      cudaFree(kv.second->d_segs);
+      cudaFree(kv.second->d_cta);
+      cudaFree(kv.second->d_units);
+      delete kv.second;
+    }
+    g_plans.clear();
+  }
+  g_plans[key] = pl;
+  *out = pl;
+  return PCV_OK;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// (channels, rows, heads, batch) view of a (batch, rows, heads*channels)-style tensor; box = 64 x 128 x 1 x 1
+int make_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int rows, int heads, int batch,
+              int64_t stride_row, int64_t stride_head, int64_t stride_batch) {
+  auto fn = get_encode_fn();
+  PCV_REQUIRE(fn != nullptr, PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)batch};
+  if (stride_batch == 0) stride_batch = (int64_t)rows * stride_row;  // broadcast batch: dim is 1, stride unused
+  cuuint64_t strides[3] = {(cuuint64_t)stride_row * 2, (cuuint64_t)stride_head * 2, (cuuint64_t)stride_batch * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kTileN, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = dtype == PCV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(tm, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PCV_REQUIRE(r == CUDA_SUCCESS, PCV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return PCV_OK;
+}
+
+inline int pad64(int d) { return (d + 63) / 64 * 64; }
+
+size_t slots_bytes(const Plan& pl, int DV) { return sizeof(float) * (size_t)pl.num_slots * kRowsPerUnit * (DV + 2); }
+
+template <int DQK, int DV, bool BF16>
+int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk,
+               const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
+  using C = Cfg<DQK, DV>;
+  auto kern = attn_tc_kernel<DQK, DV, BF16>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  prof_mark_begin(stream);
+  kern<<<pl.num_ctas, kThreads, C::kSmemBytes, stream>>>(tq, tk, tv, p);
+  prof_mark_end(stream);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  if (pl.num_units > 0) {
+    dim3 grid(pl.num_units, kRowsPerUnit / 8);
+    tc_combine_kernel<DV, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return PCV_OK;
+}
+
+}  // namespace
+
+bool attn_tc_supported(const pcv_attn_params& p, const char** why) {
+  auto fail = [&](const char* w) {
+    *why = w;
+    return false;
+  };
+  if (p.dqk > 128 || p.dv > 128) return fail("head dim > 128 (TMEM budget of the 2-tile kernel)");
+  if ((p.dqk % 8) || (p.dv % 8)) return fail("head dims must be multiples of 8 (16-byte TMA strides)");
+  if (!(p.scale > 0.f)) return fail("scale must be positive");
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  if (!al16(p.q) || !al16(p.k) || !al16(p.v)) return fail("q/k/v base pointers must be 16-byte aligned");
+  if ((p.q_stride_n % 8) || (p.k_stride_m % 8) || (p.v_stride_m % 8) || (p.q_stride_h % 8) || (p.k_stride_h % 8) ||
+      (p.v_stride_h % 8) || (p.q_stride_b % 8) || (p.k_stride_b % 8) || (p.v_stride_b % 8))
+    return fail("q/k/v strides must be multiples of 8 elements");
+  if (!p.write_partial) {
+    if (!al16(p.out) || (p.o_stride_n % 8) || (p.o_stride_h % 8) || (p.o_stride_b % 8))
+      return fail("output must be 16-byte aligned with strides in multiples of 8 elements");
+  } else {
+    if (!al16(p.part_o) || (p.dv % 4)) return fail("partial output alignment");
+  }
+  if ((int64_t)p.N > (1 << 24) || (int64_t)p.M > (1 << 30)) return fail("sequence too long");
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return fail("no CUDA device");
+  if (major != 10) return fail("device is not sm_100");
+  return true;
+}
+
+int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
+  Plan* pl = nullptr;
+  int rc = get_plan(p.B, p.H, p.N, p.M, &pl);
+  if (rc != PCV_OK) return rc;
+  size_t b = slots_bytes(*pl, pad64(p.dv));
+  b = (b + 255) / 256 * 256;
+  if (p.pad_mask != nullptr) b += sizeof(uint32_t) * (size_t)p.B * ((p.M + kTileN - 1) / kTileN * 4);
+  *bytes = b;
+  return PCV_OK;
+}
+
+int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
+  Plan* pl = nullptr;
+  int rc = get_plan(a.B, a.H, a.N, a.M, &pl);
+  if (rc != PCV_OK) return rc;
+  const int DQK = pad64(a.dqk), DV = pad64(a.dv);
+  size_t need = 0;
+  attn_tc_workspace_bytes(a, &need);
+  PCV_REQUIRE(need == 0 || (a.workspace != nullptr && a.workspace_bytes >= need), PCV_ERR_WORKSPACE,
+              "tcgen05 attention: workspace of %zu bytes required, %zu given", need, a.workspace_bytes);
+  PCV_REQUIRE(need == 0 || (reinterpret_cast<uintptr_t>(a.workspace) & 15) == 0, PCV_ERR_WORKSPACE,
+              "tcgen05 attention: workspace must be 16-byte aligned");
+
+  TcParams p{};
+  p.segs = pl->d_segs;
+  p.cta_seg_begin = pl->d_cta;
+  p.B = a.B; p.H = a.H; p.N = a.N; p.M = a.M; p.dv = a.dv;
+  p.scale_log2 = a.scale * kLog2e;
+  p.causal = a.causal;
+  p.causal_shift = (a.m_total - a.N) - a.m_offset;
+  p.q_bcast = (a.q_stride_b == 0) ? 1 : 0;
+  p.out = a.out; p.osb = a.o_stride_b; p.osn = a.o_stride_n; p.osh = a.o_stride_h;
+  p.write_partial = a.write_partial;
+  p.fin_o = a.part_o; p.fin_m = a.part_m; p.fin_l = a.part_l;
+  char* ws = reinterpret_cast<char*>(a.workspace);
+  const size_t nrows = (size_t)pl->num_slots * kRowsPerUnit;
+  p.slot_o = reinterpret_cast<float*>(ws);
+  p.slot_m = p.slot_o + nrows * DV;
+  p.slot_l = p.slot_m + nrows;
+  if (a.pad_mask != nullptr) {
+    size_t off = (slots_bytes(*pl, DV) + 255) / 256 * 256;
+    uint32_t* bits = reinterpret_cast<uint32_t*>(ws + off);
+    p.pad_wpr = (a.M + kTileN - 1) / kTileN * 4;
+    p.pad_bits = bits;
+    const int64_t total = (int64_t)a.B * p.pad_wpr;
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    pack_pad_kernel<<<blocks, 256, 0, stream>>>(a.pad_mask, a.pad_stride_b, a.B, a.M, p.pad_wpr, bits);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+
+  CUtensorMap tq, tk, tv;
+  const int Bq = a.q_stride_b == 0 ? 1 : a.B;
+  rc = make_tmap(&tq, a.q, a.dtype, a.dqk, a.N, a.H, Bq, a.q_stride_n, a.q_stride_h, a.q_stride_b);
+  if (rc != PCV_OK) return rc;
+  rc = make_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b);
+  if (rc != PCV_OK) return rc;
+  rc = make_tmap(&tv, a.v, a.dtype, a.dv, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
+  if (rc != PCV_OK) return rc;
+
+  const bool bf = a.dtype == PCV_BF16;
+#define PCV_TC_CASE(DQ, DVV)                                                                          \
+  if (DQK == DQ && DV == DVV)                                                                         \
+    return bf ? launch_cfg<DQ, DVV, true>(a, *pl, tq, tk, tv, p, stream)                              \
+              : launch_cfg<DQ, DVV, false>(a, *pl, tq, tk, tv, p, stream);
+  PCV_TC_CASE(128, 128)
+  PCV_TC_CASE(64, 64)
+  PCV_TC_CASE(64, 128)
+  PCV_TC_CASE(128, 64)
+#undef PCV_TC_CASE
+  set_error("tcgen05 attention: no instantiation for padded head dims (%d, %d)", DQK, DV);
+  return PCV_ERR_UNSUPPORTED;
+}
+
+}  // namespace pcv

@@ -125,8 +125,8 @@ def test_causal_sequence_model_golden_full_cached_and_errors():
         assert_close(nocache.logits, g["nocache_logits"], REL_DEEP, "nocache")
         # cached == uncached on our own path (the reference's kv_cache_test.py property), bf16-level
         assert_close(o.logits[:, -1], nocache.logits[:, -1], REL_DEEP, "cached vs uncached")
-    with pytest.raises(ValueError, match=r"prefix_len \(40\) out of valid range \[0\.\.24\)"):
-        model(tok[:, :n0], prefix_len=40)
+    with pytest.raises(ValueError, match=r"prefix_len \(6\) out of valid range \[0\.\.5\)"):
+        model(tok[:, :5], prefix_len=6)
     with pytest.raises(ValueError, match=r"exceeds max_prefix_len"):
         model(tok[:, :n0], prefix_len=model.max_prefix_len + 1)
 
