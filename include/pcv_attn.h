@@ -214,6 +214,14 @@ PCV_API int pcv_kv_append(const pcv_kv_append_params* p, void* stream);
 PCV_API int pcv_profile_begin(void);
 PCV_API int pcv_profile_end(double* main_kernel_ms_total, int32_t* main_kernel_launches);
 
+/*
+ * Watchdog record of the tcgen05 kernel: every in-kernel barrier wait is bounded (4 s); a wait that
+ * times out writes {1, site, blockIdx, threadIdx, parity, spins} to a pinned host buffer and traps, so a
+ * pipeline bug surfaces as a CUDA error instead of a hung GPU.  Copies up to 16 words; word 0 == 0 means
+ * no timeout was recorded.  Readable even after the context died.
+ */
+PCV_API int pcv_debug_read(uint32_t* out, int32_t n);
+
 /* number of kernel launches issued by this library in the calling process (for bench.py's
  * gpu_launches claim) */
 PCV_API uint64_t pcv_launch_count(void);

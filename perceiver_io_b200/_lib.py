@@ -32,6 +32,7 @@ EXPORTS = (
     "pcv_launch_count",
     "pcv_profile_begin",
     "pcv_profile_end",
+    "pcv_debug_read",
 )
 
 
@@ -172,6 +173,16 @@ def profile_end():
     ms, n = C.c_double(0.0), C.c_int32(0)
     check(lib().pcv_profile_end(C.byref(ms), C.byref(n)), "pcv_profile_end")
     return ms.value, n.value
+
+
+def debug_read():
+    """The tcgen05 kernel's watchdog record (16 words; word 0 != 0 after a barrier-wait timeout)."""
+    buf = (C.c_uint32 * 16)()
+    l = lib()
+    l.pcv_debug_read.restype = C.c_int
+    l.pcv_debug_read.argtypes = [C.POINTER(C.c_uint32), C.c_int32]
+    l.pcv_debug_read(buf, 16)
+    return list(buf)
 
 
 def launch_count() -> int:

@@ -104,6 +104,11 @@ int pcv_profile_end(double* main_kernel_ms_total, int32_t* main_kernel_launches)
   return PCV_OK;
 }
 
+int pcv_debug_read(uint32_t* out, int32_t n) {
+  PCV_REQUIRE(out != nullptr && n >= 0, PCV_ERR_INVALID, "debug_read: bad argument");
+  return debug_read(out, n);
+}
+
 uint64_t pcv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int pcv_get_device_info(pcv_device_info* info) {

@@ -126,7 +126,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     float m_ref = -INFINITY, l = 0.f;
 
     for (int t = seg.t0; t < seg.t1; ++t) {
-      mbar_wait(&bar.s_full[wg], n_s & 1);
+      mbar_wait(&bar.s_full[wg], n_s & 1, 12);
       ++n_s;
       tc_fence_after_sync();
 
@@ -234,7 +234,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     }
 
     // ---- epilogue: O row -> global ------------------------------------------------------------------
-    mbar_wait(&bar.o_full[wg], n_o & 1);
+    mbar_wait(&bar.o_full[wg], n_o & 1, 13);
     ++n_o;
     tc_fence_after_sync();
     const bool valid = n < p.N;
@@ -351,10 +351,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tc_fence_after_sync();
 
   if (warp < 8) {
-    reg_alloc<224>();  // softmax warpgroups take the registers the control warpgroup gives up
+    reg_alloc<224>();  // 256*224 + 128*56 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
     softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
   } else {
-    reg_dealloc<64>();
+    reg_dealloc<56>();
   }
   if (warp == kTmaWarp) {
     if (lane == 0) {
@@ -363,7 +363,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       for (int sg = seg_lo; sg < seg_hi; ++sg) {
         const Segment seg = p.segs[sg];
         const int bq = p.q_bcast ? 0 : seg.b;
-        mbar_wait(&bar.q_empty, (n_q & 1) ^ 1);
+        mbar_wait(&bar.q_empty, (n_q & 1) ^ 1, 1);
         ++n_q;
         mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(seg.ntile * C::kQTileBytes));
         for (int i = 0; i < seg.ntile; ++i)
@@ -373,7 +373,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int t = seg.t0; t < seg.t1; ++t) {
           {
             const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
-            mbar_wait(&bar.kv_empty[slot], par ^ 1);
+            mbar_wait(&bar.kv_empty[slot], par ^ 1, 2);
             mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(C::kQBoxes * kBoxBytes));
             for (int bx = 0; bx < C::kQBoxes; ++bx)
               tma_load_4d(kv_smem + slot * C::kStageBytes + bx * kBoxBytes, &tmap_k, &bar.kv_full[slot], bx * 64,
@@ -382,7 +382,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           {
             const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
-            mbar_wait(&bar.kv_empty[slot], par ^ 1);
+            mbar_wait(&bar.kv_empty[slot], par ^ 1, 3);
             mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(C::kVBoxes * kBoxBytes));
             for (int bx = 0; bx < C::kVBoxes; ++bx)
               tma_load_4d(kv_smem + slot * C::kStageBytes + bx * kBoxBytes, &tmap_v, &bar.kv_full[slot], bx * 64,
@@ -426,11 +426,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const Segment seg = p.segs[sg];
         const bool two = seg.ntile == 2;
         const int nt = seg.t1 - seg.t0;
-        mbar_wait(&bar.q_full, n_q & 1);
+        mbar_wait(&bar.q_full, n_q & 1, 4);
         ++n_q;
 
         uint32_t k_slot = it % C::kStages;
-        mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1);
+        mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 5);
         ++it;
         tc_fence_after_sync();
         issue_qk(0, k_slot);
@@ -443,20 +443,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
         for (int j = 0; j < nt; ++j) {
           const uint32_t v_slot = it % C::kStages;
-          mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1);
+          mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
           ++it;
           if (j == 0) {
-            mbar_wait(&bar.o_empty[0], (n_oe[0] & 1) ^ 1);
+            mbar_wait(&bar.o_empty[0], (n_oe[0] & 1) ^ 1, 7);
             ++n_oe[0];
           }
-          mbar_wait(&bar.p_full[0], n_p[0] & 1);
+          mbar_wait(&bar.p_full[0], n_p[0] & 1, 8);
           ++n_p[0];
           tc_fence_after_sync();
           issue_pv(0, v_slot, j > 0);
           const bool more = (j + 1 < nt);
           if (more) {
             k_slot = it % C::kStages;
-            mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1);
+            mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
             ++it;
             tc_fence_after_sync();
             issue_qk(0, k_slot);
@@ -464,10 +464,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           if (two) {
             if (j == 0) {
-              mbar_wait(&bar.o_empty[1], (n_oe[1] & 1) ^ 1);
+              mbar_wait(&bar.o_empty[1], (n_oe[1] & 1) ^ 1, 10);
               ++n_oe[1];
             }
-            mbar_wait(&bar.p_full[1], n_p[1] & 1);
+            mbar_wait(&bar.p_full[1], n_p[1] & 1, 11);
             ++n_p[1];
             tc_fence_after_sync();
             issue_pv(1, v_slot, j > 0);
@@ -644,6 +644,23 @@ void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms) {
   pl.num_units = (int)pl.units.size();
 }
 
+// watchdog record shared with the device (see mbar_wait in pcv_sm100.cuh)
+uint32_t* g_diag_host = nullptr;
+std::map<int, bool> g_diag_set;  // per device
+
+int ensure_diag(int dev) {
+  if (g_diag_set.count(dev)) return PCV_OK;
+  if (g_diag_host == nullptr) {
+    PCV_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_diag_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    for (int i = 0; i < 16; ++i) g_diag_host[i] = 0;
+  }
+  uint32_t* dptr = nullptr;
+  PCV_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_diag_host, 0));
+  PCV_CHECK_CUDA(cudaMemcpyToSymbol(sm100::g_wait_diag, &dptr, sizeof(dptr)));
+  g_diag_set[dev] = true;
+  return PCV_OK;
+}
+
 std::mutex g_plan_mu;
 std::map<std::tuple<int, int, int, int, int, int>, Plan*> g_plans;  // (device, B, H, N, M, sms)
 
@@ -653,6 +670,10 @@ int get_plan(int B, int H, int N, int M, Plan** out) {
   int sms = 0;
   PCV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   std::lock_guard<std::mutex> lk(g_plan_mu);
+  {
+    int rc = ensure_diag(dev);
+    if (rc != PCV_OK) return rc;
+  }
   auto key = std::make_tuple(dev, B, H, N, M, sms);
   auto it = g_plans.find(key);
   if (it != g_plans.end()) {
@@ -743,6 +764,11 @@ int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, 
 }
 
 }  // namespace
+
+int debug_read(uint32_t* out, int n) {
+  for (int i = 0; i < n; ++i) out[i] = (g_diag_host != nullptr && i < 16) ? g_diag_host[i] : 0u;
+  return PCV_OK;
+}
 
 bool attn_tc_supported(const pcv_attn_params& p, const char** why) {
   auto fail = [&](const char* w) {

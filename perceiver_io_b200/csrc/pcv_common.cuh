@@ -77,6 +77,7 @@ int attn_simt_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
 bool attn_tc_supported(const pcv_attn_params& p, const char** why);
 int launch_attn_tc(const pcv_attn_params& p, cudaStream_t stream);
 int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
+int debug_read(uint32_t* out, int n);  // watchdog record of the tcgen05 kernel (16 words)
 
 int launch_combine(const pcv_combine_params& p, cudaStream_t stream);
 // Merge `nparts` partial states laid out [part][B][H][N]([dv]) either into p.out (normalised) or,

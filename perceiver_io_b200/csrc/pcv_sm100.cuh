@@ -44,9 +44,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Watchdog record (mapped pinned host memory, set by the library at load; may stay null).  A wait that
+// does not complete within kWaitTimeoutNs is a pipeline deadlock: record where, then trap, so that a bug
+// surfaces as a CUDA error with a diagnosis instead of a hung GPU.
+__device__ uint32_t* g_wait_diag = nullptr;
+constexpr uint64_t kWaitTimeoutNs = 4000000000ull;
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Blocks until the phase with the given parity has completed.  A fresh barrier passes parity 1.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site = 0) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > kWaitTimeoutNs) {
+        uint32_t* d = g_wait_diag;
+        if (d != nullptr && atomicCAS(d, 0u, 1u) == 0u) {
+          d[1] = site;
+          d[2] = blockIdx.x;
+          d[3] = threadIdx.x;
+          d[4] = parity;
+          d[5] = spins;
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
   }
 }
 
