@@ -148,6 +148,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
                                       (p.causal && (j0 + kTileN - 1 > cshift)));
 
       float m_tile;
+      float mul = p.scale_log2;  // exponent = s * mul - m_ref
       if (!masked_tile) {
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -159,8 +160,9 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
         }
         m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
       } else {
-        // scores -> log2 domain with the reference's finite fill for padding / causal keys and -inf
-        // (weight exactly 0) for keys beyond the end of the tensor
+        // rare path: rewrite the scores in place in the log2 domain with the reference's finite fill for
+        // padding / causal keys and -inf (weight exactly 0) for keys beyond the end of the tensor; the
+        // common exponent loop below then runs with mul = 1
         const int oob_from = p.M - j0;
         const int cmax = p.causal ? (cshift - j0) : 0x7fffffff;
         float mx = -INFINITY;
@@ -178,6 +180,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
           }
         }
         m_tile = mx;
+        mul = 1.f;
       }
 
       // lazily move the exponent reference; rescale the accumulator row when it moves
@@ -202,8 +205,9 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
         }
       }
 
-      float sum0 = 0.f, sum1 = 0.f;
-      const float neg_m = -m_ref;
+      float2 sum2 = make_float2(0.f, 0.f);
+      const float2 mul2 = make_float2(mul, mul);
+      const float2 negm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t pk[32];
@@ -212,21 +216,15 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
           const int q4 = half * 2 + qq;
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            float e0, e1;
-            if (!masked_tile) {
-              e0 = ex2(fmaf(__uint_as_float(s[q4][c]), p.scale_log2, neg_m));
-              e1 = ex2(fmaf(__uint_as_float(s[q4][c + 1]), p.scale_log2, neg_m));
-            } else {
-              e0 = ex2(__uint_as_float(s[q4][c]) + neg_m);
-              e1 = ex2(__uint_as_float(s[q4][c + 1]) + neg_m);
-            }
-            sum0 += e0;
-            sum1 += e1;
-            pk[qq * 16 + (c >> 1)] = pack2(e0, e1, BF16);
+            const float2 x = fma2(make_float2(__uint_as_float(s[q4][c]), __uint_as_float(s[q4][c + 1])), mul2, negm2);
+            const float2 e = make_float2(ex2(x.x), ex2(x.y));
+            sum2 = add2(sum2, e);
+            pk[qq * 16 + (c >> 1)] = pack2(e.x, e.y, BF16);
           }
         }
         tmem_st32(tS + half * 32, pk);  // P (16-bit) over S columns [0,64)
       }
+      const float sum0 = sum2.x, sum1 = sum2.y;
       l += sum0 + sum1;
       tmem_wait_st();
       tc_fence_before_sync();
@@ -351,10 +349,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tc_fence_after_sync();
 
   if (warp < 8) {
-    reg_alloc<224>();  // 256*224 + 128*56 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
+    reg_alloc<208>();  // 256*208 + 128*88 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
     softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
   } else {
-    reg_dealloc<56>();
+    reg_dealloc<88>();
   }
   if (warp == kTmaWarp) {
     if (lane == 0) {
