@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -73,6 +74,7 @@ struct TcParams {
   int write_partial;
   float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
   float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
+  int take_turns;                   // softmax warpgroups alternate on the exponent phase
 };
 
 template <int DQK, int DV>
@@ -95,6 +97,7 @@ struct Barriers {
   uint64_t q_full, q_empty;
   uint64_t kv_full[8], kv_empty[8];
   uint64_t s_full[2], p_full[2], o_full[2], o_empty[2];
+  uint64_t turn[2];  // the two softmax warpgroups take turns on the exponent (MUFU) phase
   uint32_t tmem_base;
 };
 
@@ -116,11 +119,12 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
   const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
   const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
   const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
-  uint32_t n_s = 0, n_o = 0;
+  uint32_t n_s = 0, n_o = 0, n_turn = 0;
 
   for (int sg = seg_lo; sg < seg_hi; ++sg) {
     const Segment seg = p.segs[sg];
     if (wg == 1 && seg.ntile < 2) continue;
+    const bool take_turns = p.take_turns && seg.ntile == 2;
     const int n = seg.q0 + wg * kTileM + row;
     const int cshift = n + p.causal_shift;  // local key index j is causally masked iff j > cshift
     float m_ref = -INFINITY, l = 0.f;
@@ -205,6 +209,14 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
         }
       }
 
+      // Exponent phase, strictly alternating between the two warpgroups (WG0 first): if both ran it at the
+      // same time they would share the MUFU pipe and then both wait for the tensor core — the pipeline
+      // locks into a serialized in-phase mode.  Alternation staggers them so that one warpgroup
+      // exponentiates while the tensor core runs the other warpgroup's PV / next QK^T.
+      if (take_turns) {
+        mbar_wait(&bar.turn[wg], wg == 0 ? ((n_turn & 1) ^ 1) : (n_turn & 1), 14);
+        ++n_turn;
+      }
       float2 sum2 = make_float2(0.f, 0.f);
       const float2 mul2 = make_float2(mul, mul);
       const float2 negm2 = make_float2(-m_ref, -m_ref);
@@ -224,6 +236,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
         }
         tmem_st32(tS + half * 32, pk);  // P (16-bit) over S columns [0,64)
       }
+      if (take_turns) mbar_arrive(&bar.turn[wg ^ 1]);
       const float sum0 = sum2.x, sum1 = sum2.y;
       l += sum0 + sum1;
       tmem_wait_st();
@@ -332,6 +345,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&bar.p_full[i], kTileM);
       mbar_init(&bar.o_full[i], 1);
       mbar_init(&bar.o_empty[i], kTileM);
+      mbar_init(&bar.turn[i], kTileM);
     }
     fence_mbar_init();
   }
@@ -354,135 +368,153 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   } else {
     reg_dealloc<88>();
   }
+  // The two control roles run WARP-CONVERGED (all 32 lanes execute the loops and the barrier waits; one
+  // elected lane issues the TMA / tcgen05 instructions).  Keeping the warp converged lets the compiler hold
+  // addresses, descriptors and counters in uniform registers; a single-lane loop forced an R2UR shuffle in
+  // front of every tcgen05.mma operand and made instruction issue, not the tensor pipe, the bottleneck.
   if (warp == kTmaWarp) {
-    if (lane == 0) {
-      // ===== TMA producer: Q once per segment, then K_j, V_j through the ring =====
-      uint32_t it = 0, n_q = 0;
-      for (int sg = seg_lo; sg < seg_hi; ++sg) {
-        const Segment seg = p.segs[sg];
-        const int bq = p.q_bcast ? 0 : seg.b;
-        mbar_wait(&bar.q_empty, (n_q & 1) ^ 1, 1);
-        ++n_q;
+    // ===== TMA producer: Q once per segment, then K_j, V_j through the ring =====
+    const bool leader = elect_one();
+    uint32_t it = 0, n_q = 0;
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const int bq = p.q_bcast ? 0 : seg.b;
+      mbar_wait(&bar.q_empty, (n_q & 1) ^ 1, 1);
+      ++n_q;
+      if (leader) {
         mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(seg.ntile * C::kQTileBytes));
         for (int i = 0; i < seg.ntile; ++i)
           for (int bx = 0; bx < C::kQBoxes; ++bx)
             tma_load_4d(q_smem + i * C::kQTileBytes + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64,
                         seg.q0 + i * kTileM, seg.h, bq);
-        for (int t = seg.t0; t < seg.t1; ++t) {
-          {
-            const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
-            mbar_wait(&bar.kv_empty[slot], par ^ 1, 2);
+      }
+      for (int t = seg.t0; t < seg.t1; ++t) {
+        {
+          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+          mbar_wait(&bar.kv_empty[slot], par ^ 1, 2);
+          if (leader) {
             mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(C::kQBoxes * kBoxBytes));
+#pragma unroll
             for (int bx = 0; bx < C::kQBoxes; ++bx)
               tma_load_4d(kv_smem + slot * C::kStageBytes + bx * kBoxBytes, &tmap_k, &bar.kv_full[slot], bx * 64,
                           t * kTileN, seg.h, seg.b);
-            ++it;
           }
-          {
-            const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
-            mbar_wait(&bar.kv_empty[slot], par ^ 1, 3);
+          ++it;
+        }
+        {
+          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+          mbar_wait(&bar.kv_empty[slot], par ^ 1, 3);
+          if (leader) {
             mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(C::kVBoxes * kBoxBytes));
+#pragma unroll
             for (int bx = 0; bx < C::kVBoxes; ++bx)
               tma_load_4d(kv_smem + slot * C::kStageBytes + bx * kBoxBytes, &tmap_v, &bar.kv_full[slot], bx * 64,
                           t * kTileN, seg.h, seg.b);
-            ++it;
           }
+          ++it;
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc_qk = make_idesc(kTileM, kTileN, BF16, false);
-      constexpr uint32_t idesc_pv = make_idesc(kTileM, DV, BF16, true);
-      const uint32_t tmem = bar.tmem_base;
-      const uint32_t q_addr = smem_u32(q_smem);
-      const uint32_t kv_addr = smem_u32(kv_smem);
-      uint32_t it = 0, n_q = 0, n_p[2] = {0, 0}, n_oe[2] = {0, 0};
+    // ===== MMA issuer =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_qk = make_idesc(kTileM, kTileN, BF16, false);
+    constexpr uint32_t idesc_pv = make_idesc(kTileM, DV, BF16, true);
+    const uint32_t tmem = bar.tmem_base;
+    // descriptors of tile/stage 0; other tiles, stages and K-steps are plain adds on the 16-byte address field
+    const uint64_t dq0 = make_smem_desc(smem_u32(q_smem), 16, 1024);
+    const uint64_t dk0 = make_smem_desc(smem_u32(kv_smem), 16, 1024);
+    const uint64_t dv0 = make_smem_desc(smem_u32(kv_smem), kBoxBytes, 1024);
+    uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe0 = 0, n_oe1 = 0;
 
-      auto issue_qk = [&](int i, uint32_t k_slot) {
-        const uint32_t a0 = q_addr + i * C::kQTileBytes;
-        const uint32_t b0 = kv_addr + k_slot * C::kStageBytes;
+    auto issue_qk = [&](int i, uint32_t k_slot) {
+      if (leader) {
+        const uint64_t da = dq0 + (uint64_t)((i * C::kQTileBytes) >> 4);
+        const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes) >> 4);
 #pragma unroll
         for (int kk = 0; kk < DQK / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-          mma_ss(tmem + i * 128, make_smem_desc(a0 + off, 16, 1024), make_smem_desc(b0 + off, 16, 1024), idesc_qk,
-                 kk > 0 ? 1u : 0u);
+          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          mma_ss(tmem + i * 128, da + off, db + off, idesc_qk, kk > 0 ? 1u : 0u);
         }
-      };
-      auto issue_pv = [&](int i, uint32_t v_slot, bool accumulate) {
-        const uint32_t b0 = kv_addr + v_slot * C::kStageBytes;
+      }
+    };
+    auto issue_pv = [&](int i, uint32_t v_slot, bool accumulate) {
+      if (leader) {
+        const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes) >> 4);
 #pragma unroll
         for (int kk = 0; kk < kTileN / 16; ++kk) {
           // V tile is MN-major: 16 keys = 16 rows of 128 bytes; 64-channel blocks kBoxBytes apart
-          mma_ts(tmem + 256 + i * 128, tmem + i * 128 + kk * 8, make_smem_desc(b0 + kk * 2048, kBoxBytes, 1024),
-                 idesc_pv, (accumulate || kk > 0) ? 1u : 0u);
+          mma_ts(tmem + 256 + i * 128, tmem + i * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+                 (accumulate || kk > 0) ? 1u : 0u);
         }
-      };
-
-      for (int sg = seg_lo; sg < seg_hi; ++sg) {
-        const Segment seg = p.segs[sg];
-        const bool two = seg.ntile == 2;
-        const int nt = seg.t1 - seg.t0;
-        mbar_wait(&bar.q_full, n_q & 1, 4);
-        ++n_q;
-
-        uint32_t k_slot = it % C::kStages;
-        mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 5);
-        ++it;
-        tc_fence_after_sync();
-        issue_qk(0, k_slot);
-        tc_commit(&bar.s_full[0]);
-        if (two) {
-          issue_qk(1, k_slot);
-          tc_commit(&bar.s_full[1]);
-        }
-        tc_commit(&bar.kv_empty[k_slot]);
-
-        for (int j = 0; j < nt; ++j) {
-          const uint32_t v_slot = it % C::kStages;
-          mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
-          ++it;
-          if (j == 0) {
-            mbar_wait(&bar.o_empty[0], (n_oe[0] & 1) ^ 1, 7);
-            ++n_oe[0];
-          }
-          mbar_wait(&bar.p_full[0], n_p[0] & 1, 8);
-          ++n_p[0];
-          tc_fence_after_sync();
-          issue_pv(0, v_slot, j > 0);
-          const bool more = (j + 1 < nt);
-          if (more) {
-            k_slot = it % C::kStages;
-            mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
-            ++it;
-            tc_fence_after_sync();
-            issue_qk(0, k_slot);
-            tc_commit(&bar.s_full[0]);
-          }
-          if (two) {
-            if (j == 0) {
-              mbar_wait(&bar.o_empty[1], (n_oe[1] & 1) ^ 1, 10);
-              ++n_oe[1];
-            }
-            mbar_wait(&bar.p_full[1], n_p[1] & 1, 11);
-            ++n_p[1];
-            tc_fence_after_sync();
-            issue_pv(1, v_slot, j > 0);
-          }
-          tc_commit(&bar.kv_empty[v_slot]);
-          if (more) {
-            if (two) {
-              issue_qk(1, k_slot);
-              tc_commit(&bar.s_full[1]);
-            }
-            tc_commit(&bar.kv_empty[k_slot]);
-          }
-        }
-        tc_commit(&bar.q_empty);
-        tc_commit(&bar.o_full[0]);
-        if (two) tc_commit(&bar.o_full[1]);
       }
+    };
+    auto commit = [&](uint64_t* b) {
+      if (leader) tc_commit(b);
+    };
+
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const bool two = seg.ntile == 2;
+      const int nt = seg.t1 - seg.t0;
+      mbar_wait(&bar.q_full, n_q & 1, 4);
+      ++n_q;
+
+      uint32_t k_slot = it % C::kStages;
+      mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 5);
+      ++it;
+      tc_fence_after_sync();
+      issue_qk(0, k_slot);
+      commit(&bar.s_full[0]);
+      if (two) {
+        issue_qk(1, k_slot);
+        commit(&bar.s_full[1]);
+      }
+      commit(&bar.kv_empty[k_slot]);
+
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t v_slot = it % C::kStages;
+        mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
+        ++it;
+        if (j == 0) {
+          mbar_wait(&bar.o_empty[0], (n_oe0 & 1) ^ 1, 7);
+          ++n_oe0;
+        }
+        mbar_wait(&bar.p_full[0], n_p0 & 1, 8);
+        ++n_p0;
+        tc_fence_after_sync();
+        issue_pv(0, v_slot, j > 0);
+        const bool more = (j + 1 < nt);
+        if (more) {
+          k_slot = it % C::kStages;
+          mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
+          ++it;
+          tc_fence_after_sync();
+          issue_qk(0, k_slot);
+          commit(&bar.s_full[0]);
+        }
+        if (two) {
+          if (j == 0) {
+            mbar_wait(&bar.o_empty[1], (n_oe1 & 1) ^ 1, 10);
+            ++n_oe1;
+          }
+          mbar_wait(&bar.p_full[1], n_p1 & 1, 11);
+          ++n_p1;
+          tc_fence_after_sync();
+          issue_pv(1, v_slot, j > 0);
+        }
+        commit(&bar.kv_empty[v_slot]);
+        if (more) {
+          if (two) {
+            issue_qk(1, k_slot);
+            commit(&bar.s_full[1]);
+          }
+          commit(&bar.kv_empty[k_slot]);
+        }
+      }
+      commit(&bar.q_empty);
+      commit(&bar.o_full[0]);
+      if (two) commit(&bar.o_full[1]);
     }
   }
 
@@ -828,6 +860,10 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   p.q_bcast = (a.q_stride_b == 0) ? 1 : 0;
   p.out = a.out; p.osb = a.o_stride_b; p.osn = a.o_stride_n; p.osh = a.o_stride_h;
   p.write_partial = a.write_partial;
+  {
+    static const int turns = [] { const char* e = getenv("PCV_TURNS"); return e ? atoi(e) : 1; }();
+    p.take_turns = turns;
+  }
   p.fin_o = a.part_o; p.fin_m = a.part_m; p.fin_l = a.part_l;
   char* ws = reinterpret_cast<char*>(a.workspace);
   const size_t nrows = (size_t)pl->num_slots * kRowsPerUnit;

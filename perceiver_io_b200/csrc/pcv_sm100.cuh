@@ -13,6 +13,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// one lane of a converged warp (elect.sync); call with all 32 lanes active
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
