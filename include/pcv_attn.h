@@ -221,6 +221,9 @@ PCV_API int pcv_profile_end(double* main_kernel_ms_total, int32_t* main_kernel_l
  * no timeout was recorded.  Readable even after the context died.
  */
 PCV_API int pcv_debug_read(uint32_t* out, int32_t n);
+/* Developer aid: with PCV_TRACE=1 in the environment CTA 0 of the tcgen05 kernel stamps clock64() at fixed
+ * pipeline points; copies the 3 x 48 x 8 stamps (roles: softmax0, softmax1, mma; tile; event) of the last launch. */
+PCV_API int pcv_debug_trace_read(uint64_t* out, int32_t n);
 
 /* number of kernel launches issued by this library in the calling process (for bench.py's
  * gpu_launches claim) */

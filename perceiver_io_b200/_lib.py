@@ -33,6 +33,7 @@ EXPORTS = (
     "pcv_profile_begin",
     "pcv_profile_end",
     "pcv_debug_read",
+    "pcv_debug_trace_read",
 )
 
 

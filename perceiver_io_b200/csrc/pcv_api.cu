@@ -109,6 +109,11 @@ int pcv_debug_read(uint32_t* out, int32_t n) {
   return debug_read(out, n);
 }
 
+int pcv_debug_trace_read(uint64_t* out, int32_t n) {
+  PCV_REQUIRE(out != nullptr, PCV_ERR_INVALID, "trace_read: bad argument");
+  return debug_trace_read(reinterpret_cast<unsigned long long*>(out), n);
+}
+
 uint64_t pcv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int pcv_get_device_info(pcv_device_info* info) {

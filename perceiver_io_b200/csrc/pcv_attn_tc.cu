@@ -44,6 +44,10 @@ constexpr int kThreads = 384;  // 12 warps: 8 softmax + MMA + TMA + 2 idle (fill
 constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr float kRescaleThreshold = 8.f;  // log2 units
+#ifndef PCV_POLY_PER8
+#define PCV_POLY_PER8 3
+#endif
+constexpr int kPolyPer8 = PCV_POLY_PER8;  // of every 8 column pairs, this many use the FMA-pipe exp2
 
 struct Segment {
   int b, h;
@@ -75,6 +79,8 @@ struct TcParams {
   float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
   float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
   int take_turns;                   // softmax warpgroups alternate on the exponent phase
+  int poly;                         // 1: route part of the exponentials through the FMA pipes
+  unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
 };
 
 template <int DQK, int DV>
@@ -92,6 +98,14 @@ struct Cfg {
   static_assert(kStages >= 3, "need at least K_j, V_j, K_(j+1) in flight");
   static_assert(DQK % 64 == 0 && DV % 64 == 0 && DQK <= 128 && DV <= 128, "padded head dims");
 };
+
+constexpr int kTraceTiles = 48, kTraceEvents = 8, kTraceRoles = 3;
+// stamp event `ev` of role `role` for key tile `tile` (CTA 0 only, first kTraceTiles tiles, one lane per role)
+#define PCV_TRACE(pp, role, tile, ev, cond)                                                             \
+  do {                                                                                                  \
+    if ((pp).trace != nullptr && blockIdx.x == 0 && (tile) < kTraceTiles && (cond))                       \
+      (pp).trace[((role) * kTraceTiles + (tile)) * kTraceEvents + (ev)] = (unsigned long long)clock64(); \
+  } while (0)
 
 struct Barriers {
   uint64_t q_full, q_empty;
@@ -113,6 +127,147 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi, bool bf16) {
 // --------------------------------------------------------------------------------------------------
 // softmax + epilogue role: 128 threads, thread = one query row of tile `wg`
 // --------------------------------------------------------------------------------------------------
+struct RowState {
+  float m_ref;  // exponent reference (log2 domain); trails the running row maximum by at most 8
+  float l;      // running denominator relative to m_ref
+};
+
+struct TileCtx {
+  uint32_t tS, tO;    // TMEM addresses (lane field included) of this thread's S / O row
+  int wg, row;
+  int j0;             // first key of the tile
+  int cshift;         // key j (local) is causally masked for this row iff j > cshift
+  uint4 mw;           // padding bits of the 128 keys of the tile
+  bool first_tile;    // no accumulator content yet
+  bool take_turns;
+  uint32_t turn_parity;
+  bool trace_on;
+  int tt;
+};
+
+// 2^x for x <= ~8 on the FMA/ALU pipes (Cody-Waite split + cubic minimax on [0,1), max rel. error 7.5e-5,
+// far below the bf16 rounding of P): relieves the MUFU pipe, which is exactly co-critical with the tensor
+// pipe in this kernel (128x128 exponentials per 128x128x(128+128) MMA work).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float magic = 12582912.f;  // 1.5 * 2^23: adding it rounds to nearest integer in the low mantissa bits
+  const float xr = x + magic;
+  const float xi = xr - magic;     // round(x)
+  const float xf = x - xi;         // in [-0.5, 0.5]
+  // Remez fit of 2^t on [-0.5, 0.5] (relative error 7.5e-5)
+  float pf = fmaf(xf, 0.0551716685f, 0.2426111251f);
+  pf = fmaf(pf, xf, 0.6932609677f);
+  pf = fmaf(pf, xf, 0.9999280572f);
+  // scale by 2^round(x): add the integer (sitting in the low bits of xr) to the exponent field
+  return __int_as_float(__float_as_int(pf) + (__float_as_int(xr) << 23));
+}
+
+template <int DV, bool BF16, bool MASKED, int POLY>
+__device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, const TileCtx& c, RowState& st) {
+  uint32_t s[4][32];
+  tmem_ld32(c.tS + 0, s[0]);
+  tmem_ld32(c.tS + 32, s[1]);
+  tmem_ld32(c.tS + 64, s[2]);
+  tmem_ld32(c.tS + 96, s[3]);
+  tmem_wait_ld();
+  PCV_TRACE(p, c.wg, c.tt, 1, c.trace_on);
+
+  float m_tile;
+  float mul = p.scale_log2;  // exponent = s * mul - m_ref
+  if (!MASKED) {
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
+      mx1 = fmaxf(mx1, __uint_as_float(s[1][i]));
+      mx2 = fmaxf(mx2, __uint_as_float(s[2][i]));
+      mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
+    }
+    m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+  } else {
+    // rewrite the scores in place in the log2 domain with the reference's finite fill for padding /
+    // causal keys and -inf (weight exactly 0) for keys beyond the end of the tensor
+    const int oob_from = p.M - c.j0;
+    const int cmax = p.causal ? (c.cshift - c.j0) : 0x7fffffff;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const uint32_t word = q4 == 0 ? c.mw.x : (q4 == 1 ? c.mw.y : (q4 == 2 ? c.mw.z : c.mw.w));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = q4 * 32 + i;
+        float tv = __uint_as_float(s[q4][i]) * p.scale_log2;
+        if (((word >> i) & 1u) || col > cmax) tv = kMaskedScore;
+        if (col >= oob_from) tv = -INFINITY;
+        mx = fmaxf(mx, tv);
+        s[q4][i] = __float_as_uint(tv);
+      }
+    }
+    m_tile = mx;
+    mul = 1.f;
+  }
+
+  // lazily move the exponent reference; rescale the accumulator row when it moves
+  const float m_new = fmaxf(st.m_ref, m_tile);
+  float alpha = 1.f;
+  bool moved = false;
+  if (m_new - st.m_ref > kRescaleThreshold) {
+    alpha = ex2(st.m_ref - m_new);
+    st.l *= alpha;
+    st.m_ref = m_new;
+    moved = !c.first_tile;
+  }
+  if (__any_sync(0xffffffffu, moved)) {
+#pragma unroll
+    for (int ch = 0; ch < DV / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(c.tO + ch * 32, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st32(c.tO + ch * 32, o);
+    }
+  }
+
+  // Exponent phase.  With take_turns the two warpgroups alternate strictly (WG0 first) so that they do not
+  // share the MUFU pipe at the same moment (see TcParams::take_turns).
+  PCV_TRACE(p, c.wg, c.tt, 2, c.trace_on);
+  if (c.take_turns) mbar_wait(&bar.turn[c.wg], c.turn_parity, 14);
+  PCV_TRACE(p, c.wg, c.tt, 3, c.trace_on);
+  float2 sum2 = make_float2(0.f, 0.f);
+  const float2 mul2 = make_float2(mul, mul);
+  const float2 negm2 = make_float2(-st.m_ref, -st.m_ref);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t pk[32];
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq) {
+      const int q4 = half * 2 + qq;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float2 x = fma2(make_float2(__uint_as_float(s[q4][i]), __uint_as_float(s[q4][i + 1])), mul2, negm2);
+        float2 e;
+        // POLY of every 8 column pairs take the polynomial route (compile-time pattern)
+        if (!MASKED && ((i >> 1) & 7) < POLY) {
+          e = make_float2(exp2_poly(x.x), exp2_poly(x.y));
+        } else {
+          e = make_float2(ex2(x.x), ex2(x.y));
+        }
+        sum2 = add2(sum2, e);
+        pk[qq * 16 + (i >> 1)] = pack2(e.x, e.y, BF16);
+      }
+    }
+    tmem_st32(c.tS + half * 32, pk);  // P (16-bit) over S columns [0,64)
+  }
+  PCV_TRACE(p, c.wg, c.tt, 4, c.trace_on);
+  if (c.take_turns) mbar_arrive(&bar.turn[c.wg ^ 1]);
+  st.l += sum2.x + sum2.y;
+  tmem_wait_st();
+  tc_fence_before_sync();
+  mbar_arrive(&bar.p_full[c.wg]);
+  PCV_TRACE(p, c.wg, c.tt, 5, c.trace_on);
+}
+
 template <int DQK, int DV, bool BF16>
 __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, int wg, int row, int seg_lo,
                                              int seg_hi) {
@@ -126,123 +281,43 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     if (wg == 1 && seg.ntile < 2) continue;
     const bool take_turns = p.take_turns && seg.ntile == 2;
     const int n = seg.q0 + wg * kTileM + row;
-    const int cshift = n + p.causal_shift;  // local key index j is causally masked iff j > cshift
-    float m_ref = -INFINITY, l = 0.f;
+    RowState st;
+    st.m_ref = -INFINITY;
+    st.l = 0.f;
+    TileCtx c;
+    c.tS = tS; c.tO = tO; c.wg = wg; c.row = row;
+    c.cshift = n + p.causal_shift;
+    c.take_turns = take_turns;
+    c.trace_on = (row == 0 && sg == seg_lo);
 
     for (int t = seg.t0; t < seg.t1; ++t) {
+      c.j0 = t * kTileN;
+      c.tt = t - seg.t0;
+      c.first_tile = (t == seg.t0);
+      c.mw = make_uint4(0, 0, 0, 0);
+      if (p.pad_bits != nullptr)
+        c.mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
+      // warp-uniform on purpose: the tcgen05.ld/st in the tile body are .sync.aligned and must not sit behind
+      // a lane-divergent branch (the causal test differs between the rows of a warp on diagonal tiles)
+      const bool masked_tile =
+          __any_sync(0xffffffffu, (c.j0 + kTileN > p.M) || ((c.mw.x | c.mw.y | c.mw.z | c.mw.w) != 0u) ||
+                                      (p.causal && (c.j0 + kTileN - 1 > c.cshift)));
+      if (take_turns) {
+        c.turn_parity = wg == 0 ? ((n_turn & 1) ^ 1) : (n_turn & 1);
+        ++n_turn;
+      }
       mbar_wait(&bar.s_full[wg], n_s & 1, 12);
       ++n_s;
       tc_fence_after_sync();
-
-      uint32_t s[4][32];
-      tmem_ld32(tS + 0, s[0]);
-      tmem_ld32(tS + 32, s[1]);
-      tmem_ld32(tS + 64, s[2]);
-      tmem_ld32(tS + 96, s[3]);
-      tmem_wait_ld();
-
-      const int j0 = t * kTileN;
-      uint4 mw = make_uint4(0, 0, 0, 0);
-      if (p.pad_bits != nullptr)
-        mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
-      // warp-uniform on purpose: the tcgen05.st below is .sync.aligned and must not sit behind a
-      // lane-divergent branch (the causal test differs between the rows of a warp on diagonal tiles)
-      const bool masked_tile =
-          __any_sync(0xffffffffu, (j0 + kTileN > p.M) || ((mw.x | mw.y | mw.z | mw.w) != 0u) ||
-                                      (p.causal && (j0 + kTileN - 1 > cshift)));
-
-      float m_tile;
-      float mul = p.scale_log2;  // exponent = s * mul - m_ref
-      if (!masked_tile) {
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[0][c]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[1][c]));
-          mx2 = fmaxf(mx2, __uint_as_float(s[2][c]));
-          mx3 = fmaxf(mx3, __uint_as_float(s[3][c]));
-        }
-        m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
-      } else {
-        // rare path: rewrite the scores in place in the log2 domain with the reference's finite fill for
-        // padding / causal keys and -inf (weight exactly 0) for keys beyond the end of the tensor; the
-        // common exponent loop below then runs with mul = 1
-        const int oob_from = p.M - j0;
-        const int cmax = p.causal ? (cshift - j0) : 0x7fffffff;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t word = q4 == 0 ? mw.x : (q4 == 1 ? mw.y : (q4 == 2 ? mw.z : mw.w));
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int col = q4 * 32 + c;
-            float tv = __uint_as_float(s[q4][c]) * p.scale_log2;
-            if (((word >> c) & 1u) || col > cmax) tv = kMaskedScore;
-            if (col >= oob_from) tv = -INFINITY;
-            mx = fmaxf(mx, tv);
-            s[q4][c] = __float_as_uint(tv);
-          }
-        }
-        m_tile = mx;
-        mul = 1.f;
-      }
-
-      // lazily move the exponent reference; rescale the accumulator row when it moves
-      const float m_new = fmaxf(m_ref, m_tile);
-      float alpha = 1.f;
-      bool moved = false;
-      if (m_new - m_ref > kRescaleThreshold) {
-        alpha = ex2(m_ref - m_new);
-        l *= alpha;
-        m_ref = m_new;
-        moved = (t > seg.t0);
-      }
-      if (__any_sync(0xffffffffu, moved)) {
-#pragma unroll
-        for (int ch = 0; ch < DV / 32; ++ch) {
-          uint32_t o[32];
-          tmem_ld32(tO + ch * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-          tmem_st32(tO + ch * 32, o);
-        }
-      }
-
-      // Exponent phase, strictly alternating between the two warpgroups (WG0 first): if both ran it at the
-      // same time they would share the MUFU pipe and then both wait for the tensor core — the pipeline
-      // locks into a serialized in-phase mode.  Alternation staggers them so that one warpgroup
-      // exponentiates while the tensor core runs the other warpgroup's PV / next QK^T.
-      if (take_turns) {
-        mbar_wait(&bar.turn[wg], wg == 0 ? ((n_turn & 1) ^ 1) : (n_turn & 1), 14);
-        ++n_turn;
-      }
-      float2 sum2 = make_float2(0.f, 0.f);
-      const float2 mul2 = make_float2(mul, mul);
-      const float2 negm2 = make_float2(-m_ref, -m_ref);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int qq = 0; qq < 2; ++qq) {
-          const int q4 = half * 2 + qq;
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float2 x = fma2(make_float2(__uint_as_float(s[q4][c]), __uint_as_float(s[q4][c + 1])), mul2, negm2);
-            const float2 e = make_float2(ex2(x.x), ex2(x.y));
-            sum2 = add2(sum2, e);
-            pk[qq * 16 + (c >> 1)] = pack2(e.x, e.y, BF16);
-          }
-        }
-        tmem_st32(tS + half * 32, pk);  // P (16-bit) over S columns [0,64)
-      }
-      if (take_turns) mbar_arrive(&bar.turn[wg ^ 1]);
-      const float sum0 = sum2.x, sum1 = sum2.y;
-      l += sum0 + sum1;
-      tmem_wait_st();
-      tc_fence_before_sync();
-      mbar_arrive(&bar.p_full[wg]);
+      PCV_TRACE(p, wg, c.tt, 0, c.trace_on);
+      if (masked_tile)
+        softmax_tile<DV, BF16, true, 0>(p, bar, c, st);
+      else if (p.poly == 0)
+        softmax_tile<DV, BF16, false, 0>(p, bar, c, st);
+      else
+        softmax_tile<DV, BF16, false, kPolyPer8>(p, bar, c, st);
     }
+    const float l = st.l, m_ref = st.m_ref;
 
     // ---- epilogue: O row -> global ------------------------------------------------------------------
     mbar_wait(&bar.o_full[wg], n_o & 1, 13);
@@ -480,10 +555,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           mbar_wait(&bar.o_empty[0], (n_oe0 & 1) ^ 1, 7);
           ++n_oe0;
         }
+        PCV_TRACE(p, 2, j, 0, leader && sg == seg_lo);
         mbar_wait(&bar.p_full[0], n_p0 & 1, 8);
         ++n_p0;
         tc_fence_after_sync();
+        PCV_TRACE(p, 2, j, 1, leader && sg == seg_lo);
         issue_pv(0, v_slot, j > 0);
+        PCV_TRACE(p, 2, j, 2, leader && sg == seg_lo);
         const bool more = (j + 1 < nt);
         if (more) {
           k_slot = it % C::kStages;
@@ -493,6 +571,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           issue_qk(0, k_slot);
           commit(&bar.s_full[0]);
         }
+        PCV_TRACE(p, 2, j, 3, leader && sg == seg_lo);
         if (two) {
           if (j == 0) {
             mbar_wait(&bar.o_empty[1], (n_oe1 & 1) ^ 1, 10);
@@ -501,6 +580,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           mbar_wait(&bar.p_full[1], n_p1 & 1, 11);
           ++n_p1;
           tc_fence_after_sync();
+          PCV_TRACE(p, 2, j, 4, leader && sg == seg_lo);
           issue_pv(1, v_slot, j > 0);
         }
         commit(&bar.kv_empty[v_slot]);
@@ -511,6 +591,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           commit(&bar.kv_empty[k_slot]);
         }
+        PCV_TRACE(p, 2, j, 5, leader && sg == seg_lo);
       }
       commit(&bar.q_empty);
       commit(&bar.o_full[0]);
@@ -691,6 +772,8 @@ int ensure_diag(int dev) {
   return PCV_OK;
 }
 
+unsigned long long* g_trace_dev = nullptr;  // PCV_TRACE=1
+
 std::mutex g_plan_mu;
 std::map<std::tuple<int, int, int, int, int, int>, Plan*> g_plans;  // (device, B, H, N, M, sms)
 
@@ -795,6 +878,13 @@ int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, 
 
 }  // namespace
 
+int debug_trace_read(unsigned long long* out, int n) {
+  const int total = kTraceRoles * kTraceTiles * kTraceEvents;
+  if (g_trace_dev == nullptr || n < total) return PCV_ERR_INVALID;
+  PCV_CHECK_CUDA(cudaMemcpy(out, g_trace_dev, sizeof(unsigned long long) * total, cudaMemcpyDeviceToHost));
+  return PCV_OK;
+}
+
 int debug_read(uint32_t* out, int n) {
   for (int i = 0; i < n; ++i) out[i] = (g_diag_host != nullptr && i < 16) ? g_diag_host[i] : 0u;
   return PCV_OK;
@@ -863,6 +953,15 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   {
     static const int turns = [] { const char* e = getenv("PCV_TURNS"); return e ? atoi(e) : 1; }();
     p.take_turns = turns;
+    static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 1; }();
+    p.poly = poly;
+    static const int trace = [] { const char* e = getenv("PCV_TRACE"); return e ? atoi(e) : 0; }();
+    if (trace) {
+      const size_t bytes = sizeof(unsigned long long) * kTraceRoles * kTraceTiles * kTraceEvents;
+      if (g_trace_dev == nullptr) PCV_CHECK_CUDA(cudaMalloc(&g_trace_dev, bytes));
+      PCV_CHECK_CUDA(cudaMemsetAsync(g_trace_dev, 0, bytes, stream));
+      p.trace = g_trace_dev;
+    }
   }
   p.fin_o = a.part_o; p.fin_m = a.part_m; p.fin_l = a.part_l;
   char* ws = reinterpret_cast<char*>(a.workspace);

@@ -77,7 +77,8 @@ int attn_simt_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
 bool attn_tc_supported(const pcv_attn_params& p, const char** why);
 int launch_attn_tc(const pcv_attn_params& p, cudaStream_t stream);
 int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
-int debug_read(uint32_t* out, int n);  // watchdog record of the tcgen05 kernel (16 words)
+int debug_read(uint32_t* out, int n);
+int debug_trace_read(unsigned long long* out, int n);  // PCV_TRACE=1 clock stamps (3 x 48 x 8)  // watchdog record of the tcgen05 kernel (16 words)
 
 int launch_combine(const pcv_combine_params& p, cudaStream_t stream);
 // Merge `nparts` partial states laid out [part][B][H][N]([dv]) either into p.out (normalised) or,
