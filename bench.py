@@ -198,8 +198,13 @@ def run_ours(args, rank, world, local_rank):
     q = torch.randn(B, N, d, device=dev).bfloat16()
     if world > 1:
         dist.broadcast(q, src=0)  # Q is replicated
-    k = torch.randn(B, Mg, d, device=dev).bfloat16()
-    v = torch.randn(B, Mg, d, device=dev).bfloat16()
+    if args.kv_layout == "head_major":
+        # (B, H, M, dh) buffers viewed as (B, M, H, dh): every (b, h) streams a contiguous run of keys
+        k = torch.randn(B, H, Mg, d // H, device=dev).bfloat16().permute(0, 2, 1, 3)
+        v = torch.randn(B, H, Mg, d // H, device=dev).bfloat16().permute(0, 2, 1, 3)
+    else:
+        k = torch.randn(B, Mg, d, device=dev).bfloat16()
+        v = torch.randn(B, Mg, d, device=dev).bfloat16()
 
     def barrier():
         if world > 1:
@@ -306,7 +311,7 @@ def run_ours(args, rank, world, local_rank):
                 "parallelism": f"m-shard x{world}" if world > 1 else "single GPU",
                 "keys_per_gpu": Mg,
                 "l2": f"no flush needed: K+V per GPU = {2 * B * Mg * d * 2 / 2**20:.0f} MiB > 126 MiB L2",
-                "kernel": args.kernel,
+                "kernel": args.kernel, "kv_layout": args.kv_layout,
             },
             "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps,
@@ -329,6 +334,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--kernel", choices=["auto", "tcgen05", "simt"], default="auto")
+    ap.add_argument("--kv-layout", choices=["token_major", "head_major"], default="token_major",
+                    help="memory layout of the projected K/V: (B,M,H*dh) as nn.Linear writes it, or (B,H,M,dh)")
     ap.add_argument("--M", type=int, default=0, help="override the key count (sweep points)")
     ap.add_argument("--B", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=10)

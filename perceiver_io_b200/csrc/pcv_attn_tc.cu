@@ -79,6 +79,8 @@ struct TcParams {
   float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
   float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
   int take_turns;                   // softmax warpgroups alternate on the exponent phase
+  int dbg;                          // developer experiments (PCV_DBG): 1 = softmax skips its math, 2 = no PV MMAs, 4 = no QK MMAs
+  int optimistic;                   // 1: exponentiate against the current reference, verify the max afterwards
   int poly;                         // 1: route part of the exponentials through the FMA pipes
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
 };
@@ -175,13 +177,15 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
   float m_tile;
   float mul = p.scale_log2;  // exponent = s * mul - m_ref
   if (!MASKED) {
+    // 2-input max on purpose: the compiler's fused 3-input FMNMX3 measured ~8 issue cycles per warp
+    // instruction here (4x slower than FMNMX), which made this pass as long as half the exponent phase
     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
-      mx1 = fmaxf(mx1, __uint_as_float(s[1][i]));
-      mx2 = fmaxf(mx2, __uint_as_float(s[2][i]));
-      mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
+      mx0 = max2(mx0, __uint_as_float(s[0][i]));
+      mx1 = max2(mx1, __uint_as_float(s[1][i]));
+      mx2 = max2(mx2, __uint_as_float(s[2][i]));
+      mx3 = max2(mx3, __uint_as_float(s[3][i]));
     }
     m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
   } else {
@@ -268,6 +272,61 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
   PCV_TRACE(p, c.wg, c.tt, 5, c.trace_on);
 }
 
+// Optimistic tile: exponentiate against the CURRENT reference maximum while the scores stream in from TMEM
+// (no separate max pass on the critical path) and track the tile maximum on the side.  If any row of the warp
+// turns out to exceed the reference by more than the rescale threshold, nothing has been stored yet: the warp
+// returns false and the caller redoes the tile on the classic path (max first).  After the first few tiles of
+// a row the reference hardly ever moves, so the redo is rare.
+template <int DV, bool BF16>
+__device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barriers& bar, const TileCtx& c,
+                                                        RowState& st) {
+  uint32_t pk[64];
+  float2 sum2 = make_float2(0.f, 0.f);
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  const float2 mul2 = make_float2(p.scale_log2, p.scale_log2);
+  const float2 negm2 = make_float2(-st.m_ref, -st.m_ref);
+  uint32_t sa[32], sb[32];
+  tmem_ld32(c.tS + 0, sa);
+  tmem_wait_ld();
+  PCV_TRACE(p, c.wg, c.tt, 1, c.trace_on);
+  if (c.take_turns) mbar_wait(&bar.turn[c.wg], c.turn_parity, 14);
+  PCV_TRACE(p, c.wg, c.tt, 3, c.trace_on);
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    // double-buffered: chunk q4+1 streams from TMEM while chunk q4 is exponentiated
+    uint32_t(&cur)[32] = (q4 & 1) ? sb : sa;
+    uint32_t(&nxt)[32] = (q4 & 1) ? sa : sb;
+    if (q4 < 3) tmem_ld32(c.tS + (q4 + 1) * 32, nxt);
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
+      mx0 = fmaxf(mx0, s0);
+      mx1 = fmaxf(mx1, s1);
+      const float2 x = fma2(make_float2(s0, s1), mul2, negm2);
+      const float2 e = make_float2(ex2(x.x), ex2(x.y));
+      sum2 = add2(sum2, e);
+      pk[q4 * 16 + (i >> 1)] = pack2(e.x, e.y, BF16);
+    }
+    if (q4 < 3) tmem_wait_ld();
+  }
+  PCV_TRACE(p, c.wg, c.tt, 4, c.trace_on);
+  if (c.take_turns) mbar_arrive(&bar.turn[c.wg ^ 1]);
+  const float m_tile = fmaxf(mx0, mx1) * p.scale_log2;
+  if (__any_sync(0xffffffffu, m_tile - st.m_ref > kRescaleThreshold)) return false;
+  {
+    uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[0]);
+    uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[32]);
+    tmem_st32(c.tS + 0, lo);  // P (16-bit) over S columns [0,64); all of S is in registers by now
+    tmem_st32(c.tS + 32, hi);
+  }
+  st.l += sum2.x + sum2.y;
+  tmem_wait_st();
+  tc_fence_before_sync();
+  mbar_arrive(&bar.p_full[c.wg]);
+  PCV_TRACE(p, c.wg, c.tt, 5, c.trace_on);
+  return true;
+}
+
 template <int DQK, int DV, bool BF16>
 __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, int wg, int row, int seg_lo,
                                              int seg_hi) {
@@ -302,7 +361,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       const bool masked_tile =
           __any_sync(0xffffffffu, (c.j0 + kTileN > p.M) || ((c.mw.x | c.mw.y | c.mw.z | c.mw.w) != 0u) ||
                                       (p.causal && (c.j0 + kTileN - 1 > c.cshift)));
-      if (take_turns) {
+      if (take_turns && !(p.dbg & 1)) {
         c.turn_parity = wg == 0 ? ((n_turn & 1) ^ 1) : (n_turn & 1);
         ++n_turn;
       }
@@ -310,12 +369,26 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       ++n_s;
       tc_fence_after_sync();
       PCV_TRACE(p, wg, c.tt, 0, c.trace_on);
-      if (masked_tile)
+      if (p.dbg & 1) {  // timing experiment: protocol only
+        tc_fence_before_sync();
+        mbar_arrive(&bar.p_full[wg]);
+        continue;
+      }
+      if (masked_tile) {
         softmax_tile<DV, BF16, true, 0>(p, bar, c, st);
-      else if (p.poly == 0)
+      } else if (p.optimistic && !c.first_tile) {
+        if (!softmax_tile_optimistic<DV, BF16>(p, bar, c, st)) {
+          // the reference must move: redo on the classic path.  The turn (if any) was already consumed and
+          // handed on inside the optimistic attempt, so the redo runs without one.
+          TileCtx c2 = c;
+          c2.take_turns = false;
+          softmax_tile<DV, BF16, false, 0>(p, bar, c2, st);
+        }
+      } else if (p.poly == 0) {
         softmax_tile<DV, BF16, false, 0>(p, bar, c, st);
-      else
+      } else {
         softmax_tile<DV, BF16, false, kPolyPer8>(p, bar, c, st);
+      }
     }
     const float l = st.l, m_ref = st.m_ref;
 
@@ -503,7 +576,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe0 = 0, n_oe1 = 0;
 
     auto issue_qk = [&](int i, uint32_t k_slot) {
-      if (leader) {
+      if (leader && !(p.dbg & 4)) {
         const uint64_t da = dq0 + (uint64_t)((i * C::kQTileBytes) >> 4);
         const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes) >> 4);
 #pragma unroll
@@ -514,7 +587,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
     };
     auto issue_pv = [&](int i, uint32_t v_slot, bool accumulate) {
-      if (leader) {
+      if (leader && !(p.dbg & 2)) {
         const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes) >> 4);
 #pragma unroll
         for (int kk = 0; kk < kTileN / 16; ++kk) {
@@ -953,8 +1026,12 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   {
     static const int turns = [] { const char* e = getenv("PCV_TURNS"); return e ? atoi(e) : 1; }();
     p.take_turns = turns;
-    static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 1; }();
+    static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 0; }();
     p.poly = poly;
+    static const int opt = [] { const char* e = getenv("PCV_OPT"); return e ? atoi(e) : 1; }();
+    p.optimistic = opt;
+    static const int dbg = [] { const char* e = getenv("PCV_DBG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
     static const int trace = [] { const char* e = getenv("PCV_TRACE"); return e ? atoi(e) : 0; }();
     if (trace) {
       const size_t bytes = sizeof(unsigned long long) * kTraceRoles * kTraceTiles * kTraceEvents;

@@ -238,6 +238,13 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   return d;
 }
 
+// plain 2-input max the compiler cannot re-fuse into FMNMX3
+__device__ __forceinline__ float max2(float a, float b) {
+  float d;
+  asm volatile("max.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

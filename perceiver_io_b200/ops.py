@@ -52,7 +52,7 @@ def _compute_dtype(dt: torch.dtype) -> torch.dtype:
 
 
 def _rows_contiguous(t: torch.Tensor) -> torch.Tensor:
-    """(B, L, C) with unit channel stride (other strides are passed through to the kernel)."""
+    """Unit channel stride (every other stride is passed through to the kernel)."""
     return t if t.stride(-1) == 1 else t.contiguous()
 
 
@@ -63,26 +63,38 @@ def device_info() -> dict:
 
 
 def _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, m_total, m_offset, impl) -> Tuple[AttnParams, tuple]:
-    if q.dim() != 3 or k.dim() != 3 or v.dim() != 3:
-        raise ValueError("q, k, v must be (B, L, C) tensors")
-    Bq, N, Cq = q.shape
-    B, M, Ck = k.shape
-    if v.shape[0] != B or v.shape[1] != M:
+    # Each operand is either (B, L, H*d) — heads split by stride arithmetic — or an explicit 4-D
+    # (B, L, H, d) view with arbitrary batch/row/head strides (e.g. a head-major (B,H,L,d) buffer permuted).
+    def geom(t, name):
+        if t.dim() == 3:
+            if t.shape[2] % num_heads:
+                raise ValueError("channel counts must be divisible by num_heads")
+            d = t.shape[2] // num_heads
+            return t.shape[0], t.shape[1], d, t.stride(0), t.stride(1), d
+        if t.dim() == 4:
+            if t.shape[2] != num_heads:
+                raise ValueError(f"{name}: 4-D operands must be (B, L, H={num_heads}, d), got {tuple(t.shape)}")
+            if t.stride(3) != 1:
+                raise ValueError(f"{name}: the channel dimension must have unit stride")
+            return t.shape[0], t.shape[1], t.shape[3], t.stride(0), t.stride(1), t.stride(2)
+        raise ValueError("q, k, v must be (B, L, C) or (B, L, H, d) tensors")
+
+    Bq, N, dqk, q_sb, q_sn, q_sh = geom(q, "q")
+    B, M, dk, k_sb, k_sm, k_sh = geom(k, "k")
+    Bv, Mv, dv, v_sb, v_sm, v_sh = geom(v, "v")
+    if Bv != B or Mv != M:
         raise ValueError(f"k {tuple(k.shape)} and v {tuple(v.shape)} disagree on (B, M)")
     if Bq not in (1, B):
         raise ValueError(f"query batch {Bq} must be 1 or equal to key batch {B}")
-    if Cq != Ck:
-        raise ValueError(f"q channels {Cq} != k channels {Ck}")
-    if Cq % num_heads or v.shape[2] % num_heads:
-        raise ValueError("channel counts must be divisible by num_heads")
+    if dqk != dk:
+        raise ValueError(f"q head channels {dqk} != k head channels {dk}")
     H = num_heads
-    dqk, dv = Cq // H, v.shape[2] // H
     p = AttnParams()
     p.q, p.k, p.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
-    p.q_stride_b = 0 if (Bq == 1 and B > 1) else q.stride(0)
-    p.q_stride_n, p.q_stride_h = q.stride(1), dqk
-    p.k_stride_b, p.k_stride_m, p.k_stride_h = k.stride(0), k.stride(1), dqk
-    p.v_stride_b, p.v_stride_m, p.v_stride_h = v.stride(0), v.stride(1), dv
+    p.q_stride_b = 0 if (Bq == 1 and B > 1) else q_sb
+    p.q_stride_n, p.q_stride_h = q_sn, q_sh
+    p.k_stride_b, p.k_stride_m, p.k_stride_h = k_sb, k_sm, k_sh
+    p.v_stride_b, p.v_stride_m, p.v_stride_h = v_sb, v_sm, v_sh
     p.B, p.H, p.N, p.M, p.dqk, p.dv = B, H, N, M, dqk, dv
     p.scale = float(scale)
     p.dtype = _pcv_dtype(q.dtype)
