@@ -1024,7 +1024,7 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   p.out = a.out; p.osb = a.o_stride_b; p.osn = a.o_stride_n; p.osh = a.o_stride_h;
   p.write_partial = a.write_partial;
   {
-    static const int turns = [] { const char* e = getenv("PCV_TURNS"); return e ? atoi(e) : 1; }();
+    static const int turns = [] { const char* e = getenv("PCV_TURNS"); return e ? atoi(e) : 0; }();
     p.take_turns = turns;
     static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 0; }();
     p.poly = poly;

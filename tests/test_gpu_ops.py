@@ -172,3 +172,16 @@ def test_errors_surface_as_exceptions():
         ops.attention(q, k[:, :, :16], v, 2, 1.0)
     with pytest.raises(PcvError, match="m_total"):
         ops.attention_partial(q, k, v, 2, 1.0, m_total=8, m_offset=0)
+
+
+def test_head_major_4d_operands_by_stride():
+    """K/V stored (B, H, M, d) and passed as a permuted (B, M, H, d) view: same result, no copy."""
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, d = 2, 96, 700, 4, 64
+    q, k, v = _qkv(B, N, M, H, d, d, seed=21)
+    k_hm = k.view(B, M, H, d).permute(0, 2, 1, 3).contiguous()   # (B, H, M, d) storage
+    v_hm = v.view(B, M, H, d).permute(0, 2, 1, 3).contiguous()
+    out = ops.attention(q, k_hm.permute(0, 2, 1, 3), v_hm.permute(0, 2, 1, 3), H, d ** -0.5)
+    assert_close(out, oracle_core(q, k, v, H, d ** -0.5), REL_TC, "head-major")
+    assert torch.equal(out, ops.attention(q, k, v, H, d ** -0.5))
