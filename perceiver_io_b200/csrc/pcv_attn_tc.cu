@@ -44,10 +44,6 @@ constexpr int kThreads = 384;  // 12 warps: 8 softmax + MMA + TMA + 2 idle (fill
 constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr float kRescaleThreshold = 8.f;  // log2 units
-#ifndef PCV_POLY_PER8
-#define PCV_POLY_PER8 3
-#endif
-constexpr int kPolyPer8 = PCV_POLY_PER8;  // of every 8 column pairs, this many use the FMA-pipe exp2
 
 struct Segment {
   int b, h;
@@ -78,10 +74,8 @@ struct TcParams {
   int write_partial;
   float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
   float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
-  int take_turns;                   // softmax warpgroups alternate on the exponent phase
   int dbg;                          // developer experiments (PCV_DBG): 1 = softmax skips its math, 2 = no PV MMAs, 4 = no QK MMAs
   int optimistic;                   // 1: exponentiate against the current reference, verify the max afterwards
-  int poly;                         // 1: route part of the exponentials through the FMA pipes
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
 };
 
@@ -103,17 +97,22 @@ struct Cfg {
 
 constexpr int kTraceTiles = 48, kTraceEvents = 8, kTraceRoles = 3;
 // stamp event `ev` of role `role` for key tile `tile` (CTA 0 only, first kTraceTiles tiles, one lane per role)
+#ifdef PCV_ENABLE_TRACE  // developer build only (make TRACE=1): the stamps cost registers in the softmax loop
 #define PCV_TRACE(pp, role, tile, ev, cond)                                                             \
   do {                                                                                                  \
     if ((pp).trace != nullptr && blockIdx.x == 0 && (tile) < kTraceTiles && (cond))                       \
       (pp).trace[((role) * kTraceTiles + (tile)) * kTraceEvents + (ev)] = (unsigned long long)clock64(); \
   } while (0)
+#else
+#define PCV_TRACE(pp, role, tile, ev, cond) \
+  do {                                      \
+  } while (0)
+#endif
 
 struct Barriers {
   uint64_t q_full, q_empty;
   uint64_t kv_full[8], kv_empty[8];
   uint64_t s_full[2], p_full[2], o_full[2], o_empty[2];
-  uint64_t turn[2];  // the two softmax warpgroups take turns on the exponent (MUFU) phase
   uint32_t tmem_base;
 };
 
@@ -141,30 +140,11 @@ struct TileCtx {
   int cshift;         // key j (local) is causally masked for this row iff j > cshift
   uint4 mw;           // padding bits of the 128 keys of the tile
   bool first_tile;    // no accumulator content yet
-  bool take_turns;
-  uint32_t turn_parity;
   bool trace_on;
   int tt;
 };
 
-// 2^x for x <= ~8 on the FMA/ALU pipes (Cody-Waite split + cubic minimax on [0,1), max rel. error 7.5e-5,
-// far below the bf16 rounding of P): relieves the MUFU pipe, which is exactly co-critical with the tensor
-// pipe in this kernel (128x128 exponentials per 128x128x(128+128) MMA work).
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float magic = 12582912.f;  // 1.5 * 2^23: adding it rounds to nearest integer in the low mantissa bits
-  const float xr = x + magic;
-  const float xi = xr - magic;     // round(x)
-  const float xf = x - xi;         // in [-0.5, 0.5]
-  // Remez fit of 2^t on [-0.5, 0.5] (relative error 7.5e-5)
-  float pf = fmaf(xf, 0.0551716685f, 0.2426111251f);
-  pf = fmaf(pf, xf, 0.6932609677f);
-  pf = fmaf(pf, xf, 0.9999280572f);
-  // scale by 2^round(x): add the integer (sitting in the low bits of xr) to the exponent field
-  return __int_as_float(__float_as_int(pf) + (__float_as_int(xr) << 23));
-}
-
-template <int DV, bool BF16, bool MASKED, int POLY>
+template <int DV, bool BF16, bool MASKED>
 __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, const TileCtx& c, RowState& st) {
   uint32_t s[4][32];
   tmem_ld32(c.tS + 0, s[0]);
@@ -233,10 +213,7 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
     }
   }
 
-  // Exponent phase.  With take_turns the two warpgroups alternate strictly (WG0 first) so that they do not
-  // share the MUFU pipe at the same moment (see TcParams::take_turns).
   PCV_TRACE(p, c.wg, c.tt, 2, c.trace_on);
-  if (c.take_turns) mbar_wait(&bar.turn[c.wg], c.turn_parity, 14);
   PCV_TRACE(p, c.wg, c.tt, 3, c.trace_on);
   float2 sum2 = make_float2(0.f, 0.f);
   const float2 mul2 = make_float2(mul, mul);
@@ -250,13 +227,7 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float2 x = fma2(make_float2(__uint_as_float(s[q4][i]), __uint_as_float(s[q4][i + 1])), mul2, negm2);
-        float2 e;
-        // POLY of every 8 column pairs take the polynomial route (compile-time pattern)
-        if (!MASKED && ((i >> 1) & 7) < POLY) {
-          e = make_float2(exp2_poly(x.x), exp2_poly(x.y));
-        } else {
-          e = make_float2(ex2(x.x), ex2(x.y));
-        }
+        const float2 e = make_float2(ex2(x.x), ex2(x.y));
         sum2 = add2(sum2, e);
         pk[qq * 16 + (i >> 1)] = pack2(e.x, e.y, BF16);
       }
@@ -264,7 +235,6 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
     tmem_st32(c.tS + half * 32, pk);  // P (16-bit) over S columns [0,64)
   }
   PCV_TRACE(p, c.wg, c.tt, 4, c.trace_on);
-  if (c.take_turns) mbar_arrive(&bar.turn[c.wg ^ 1]);
   st.l += sum2.x + sum2.y;
   tmem_wait_st();
   tc_fence_before_sync();
@@ -280,7 +250,7 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
 template <int DV, bool BF16>
 __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barriers& bar, const TileCtx& c,
                                                         RowState& st) {
-  uint32_t pk[64];
+  uint32_t pk_lo[32], pk_hi[32];  // packed P for key columns [0,64) / [64,128)
   float2 sum2 = make_float2(0.f, 0.f);
   float mx0 = -INFINITY, mx1 = -INFINITY;
   const float2 mul2 = make_float2(p.scale_log2, p.scale_log2);
@@ -289,36 +259,34 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
   tmem_ld32(c.tS + 0, sa);
   tmem_wait_ld();
   PCV_TRACE(p, c.wg, c.tt, 1, c.trace_on);
-  if (c.take_turns) mbar_wait(&bar.turn[c.wg], c.turn_parity, 14);
   PCV_TRACE(p, c.wg, c.tt, 3, c.trace_on);
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    // double-buffered: chunk q4+1 streams from TMEM while chunk q4 is exponentiated
-    uint32_t(&cur)[32] = (q4 & 1) ? sb : sa;
-    uint32_t(&nxt)[32] = (q4 & 1) ? sa : sb;
-    if (q4 < 3) tmem_ld32(c.tS + (q4 + 1) * 32, nxt);
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
-      mx0 = fmaxf(mx0, s0);
-      mx1 = fmaxf(mx1, s1);
-      const float2 x = fma2(make_float2(s0, s1), mul2, negm2);
-      const float2 e = make_float2(ex2(x.x), ex2(x.y));
-      sum2 = add2(sum2, e);
-      pk[q4 * 16 + (i >> 1)] = pack2(e.x, e.y, BF16);
-    }
-    if (q4 < 3) tmem_wait_ld();
-  }
+
+  // chunk q (32 score columns) -> 16 packed words at dst[off..off+16); the next chunk streams from TMEM
+  // into the other buffer meanwhile
+#define PCV_OPT_CHUNK(cur, nxt, q, dst, off)                                                      \
+  do {                                                                                            \
+    if ((q) < 3) tmem_ld32(c.tS + ((q) + 1) * 32, nxt);                                           \
+    _Pragma("unroll") for (int i = 0; i < 32; i += 2) {                                           \
+      const float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);                \
+      mx0 = fmaxf(mx0, s0);                                                                       \
+      mx1 = fmaxf(mx1, s1);                                                                       \
+      const float2 x = fma2(make_float2(s0, s1), mul2, negm2);                                    \
+      const float2 e = make_float2(ex2(x.x), ex2(x.y));                                           \
+      sum2 = add2(sum2, e);                                                                       \
+      dst[(off) + (i >> 1)] = pack2(e.x, e.y, BF16);                                              \
+    }                                                                                             \
+    if ((q) < 3) tmem_wait_ld();                                                                  \
+  } while (0)
+  PCV_OPT_CHUNK(sa, sb, 0, pk_lo, 0);
+  PCV_OPT_CHUNK(sb, sa, 1, pk_lo, 16);
+  PCV_OPT_CHUNK(sa, sb, 2, pk_hi, 0);
+  PCV_OPT_CHUNK(sb, sa, 3, pk_hi, 16);
+#undef PCV_OPT_CHUNK
   PCV_TRACE(p, c.wg, c.tt, 4, c.trace_on);
-  if (c.take_turns) mbar_arrive(&bar.turn[c.wg ^ 1]);
   const float m_tile = fmaxf(mx0, mx1) * p.scale_log2;
   if (__any_sync(0xffffffffu, m_tile - st.m_ref > kRescaleThreshold)) return false;
-  {
-    uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[0]);
-    uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[32]);
-    tmem_st32(c.tS + 0, lo);  // P (16-bit) over S columns [0,64); all of S is in registers by now
-    tmem_st32(c.tS + 32, hi);
-  }
+  tmem_st32(c.tS + 0, pk_lo);  // P (16-bit) over S columns [0,64); all of S is in registers by now
+  tmem_st32(c.tS + 32, pk_hi);
   st.l += sum2.x + sum2.y;
   tmem_wait_st();
   tc_fence_before_sync();
@@ -333,12 +301,11 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
   const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
   const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
   const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
-  uint32_t n_s = 0, n_o = 0, n_turn = 0;
+  uint32_t n_s = 0, n_o = 0;
 
   for (int sg = seg_lo; sg < seg_hi; ++sg) {
     const Segment seg = p.segs[sg];
     if (wg == 1 && seg.ntile < 2) continue;
-    const bool take_turns = p.take_turns && seg.ntile == 2;
     const int n = seg.q0 + wg * kTileM + row;
     RowState st;
     st.m_ref = -INFINITY;
@@ -346,7 +313,6 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     TileCtx c;
     c.tS = tS; c.tO = tO; c.wg = wg; c.row = row;
     c.cshift = n + p.causal_shift;
-    c.take_turns = take_turns;
     c.trace_on = (row == 0 && sg == seg_lo);
 
     for (int t = seg.t0; t < seg.t1; ++t) {
@@ -361,10 +327,6 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       const bool masked_tile =
           __any_sync(0xffffffffu, (c.j0 + kTileN > p.M) || ((c.mw.x | c.mw.y | c.mw.z | c.mw.w) != 0u) ||
                                       (p.causal && (c.j0 + kTileN - 1 > c.cshift)));
-      if (take_turns && !(p.dbg & 1)) {
-        c.turn_parity = wg == 0 ? ((n_turn & 1) ^ 1) : (n_turn & 1);
-        ++n_turn;
-      }
       mbar_wait(&bar.s_full[wg], n_s & 1, 12);
       ++n_s;
       tc_fence_after_sync();
@@ -375,19 +337,14 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
         continue;
       }
       if (masked_tile) {
-        softmax_tile<DV, BF16, true, 0>(p, bar, c, st);
+        softmax_tile<DV, BF16, true>(p, bar, c, st);
       } else if (p.optimistic && !c.first_tile) {
         if (!softmax_tile_optimistic<DV, BF16>(p, bar, c, st)) {
-          // the reference must move: redo on the classic path.  The turn (if any) was already consumed and
-          // handed on inside the optimistic attempt, so the redo runs without one.
-          TileCtx c2 = c;
-          c2.take_turns = false;
-          softmax_tile<DV, BF16, false, 0>(p, bar, c2, st);
+          // the reference must move: nothing was stored, redo on the classic path (max first)
+          softmax_tile<DV, BF16, false>(p, bar, c, st);
         }
-      } else if (p.poly == 0) {
-        softmax_tile<DV, BF16, false, 0>(p, bar, c, st);
       } else {
-        softmax_tile<DV, BF16, false, kPolyPer8>(p, bar, c, st);
+        softmax_tile<DV, BF16, false>(p, bar, c, st);
       }
     }
     const float l = st.l, m_ref = st.m_ref;
@@ -493,7 +450,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&bar.p_full[i], kTileM);
       mbar_init(&bar.o_full[i], 1);
       mbar_init(&bar.o_empty[i], kTileM);
-      mbar_init(&bar.turn[i], kTileM);
     }
     fence_mbar_init();
   }
@@ -511,10 +467,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tc_fence_after_sync();
 
   if (warp < 8) {
-    reg_alloc<208>();  // 256*208 + 128*88 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
+    reg_alloc<216>();  // 256*216 + 128*72 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
     softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
   } else {
-    reg_dealloc<88>();
+    reg_dealloc<72>();
   }
   // The two control roles run WARP-CONVERGED (all 32 lanes execute the loops and the barrier waits; one
   // elected lane issues the TMA / tcgen05 instructions).  Keeping the warp converged lets the compiler hold
@@ -1024,10 +980,6 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   p.out = a.out; p.osb = a.o_stride_b; p.osn = a.o_stride_n; p.osh = a.o_stride_h;
   p.write_partial = a.write_partial;
   {
-    static const int turns = [] { const char* e = getenv("PCV_TURNS"); return e ? atoi(e) : 0; }();
-    p.take_turns = turns;
-    static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 0; }();
-    p.poly = poly;
     static const int opt = [] { const char* e = getenv("PCV_OPT"); return e ? atoi(e) : 1; }();
     p.optimistic = opt;
     static const int dbg = [] { const char* e = getenv("PCV_DBG"); return e ? atoi(e) : 0; }();
