@@ -223,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
             return ops.attention(q, k, v, H, scale, impl=args.kernel)
     else:
         def core_step():
-            return sharded_attention(q, k, v, H, scale, M, m0)
+            return sharded_attention(q, k, v, H, scale, M, m0, merge=args.merge, copy_out=False)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -283,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
             if world == 1:
                 o = layer(xq, xkv).last_hidden_state
             else:
-                o = cross_attention_sharded(layer, xq, xkv, M, m0).last_hidden_state
+                o = cross_attention_sharded(layer, xq, xkv, M, m0, merge=args.merge).last_hidden_state
         out_host.copy_(o, non_blocking=True)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -311,7 +311,7 @@ def run_ours(args, rank, world, local_rank):
                 "parallelism": f"m-shard x{world}" if world > 1 else "single GPU",
                 "keys_per_gpu": Mg,
                 "l2": f"no flush needed: K+V per GPU = {2 * B * Mg * d * 2 / 2**20:.0f} MiB > 126 MiB L2",
-                "kernel": args.kernel, "kv_layout": args.kv_layout,
+                "kernel": args.kernel, "kv_layout": args.kv_layout, "merge": args.merge if world > 1 else None,
             },
             "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps,
@@ -336,6 +336,8 @@ def main():
     ap.add_argument("--kernel", choices=["auto", "tcgen05", "simt"], default="auto")
     ap.add_argument("--kv-layout", choices=["token_major", "head_major"], default="token_major",
                     help="memory layout of the projected K/V: (B,M,H*dh) as nn.Linear writes it, or (B,H,M,dh)")
+    ap.add_argument("--merge", choices=["auto", "peer", "nccl"], default="auto",
+                    help="multi-GPU merge transport: symmetric-memory peer kernel or NCCL all-reduces")
     ap.add_argument("--M", type=int, default=0, help="override the key count (sweep points)")
     ap.add_argument("--B", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=10)

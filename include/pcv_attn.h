@@ -184,6 +184,29 @@ typedef struct pcv_rescale_params {
   int32_t reserved;
 } pcv_rescale_params;
 
+/*
+ * Merge of M-shard partial states held in PEER-ACCESSIBLE memory (NVLink / NVSwitch), no NCCL on the data
+ * path: rank `rank` owns rows [row_begin, row_end) of the flattened (B*H*N) row space; for each owned row it
+ * loads (part_o, part_m, part_l) of that row from all `num_peers` ranks through their mapped pointers, merges
+ * them exactly as pcv_attn_combine does, and stores the normalised row into the output buffer of EVERY rank
+ * (so all ranks end up with the full (B, N, H, dv) result after a barrier).  The caller provides the barriers
+ * (before: all partial states written; after: all outputs written) — perceiver_io_b200/dist.py uses the
+ * symmetric-memory signal pads for that.
+ */
+#define PCV_MAX_PEERS 8
+typedef struct pcv_peer_combine_params {
+  const float* part_o[PCV_MAX_PEERS]; /* per rank: (B, H, N, dv) f32 */
+  const float* part_m[PCV_MAX_PEERS]; /* per rank: (B, H, N) f32     */
+  const float* part_l[PCV_MAX_PEERS]; /* per rank: (B, H, N) f32     */
+  void* out[PCV_MAX_PEERS];           /* per rank: (B, N, H, dv) in `dtype`, strides below */
+  int64_t o_stride_b, o_stride_n, o_stride_h;
+  int64_t row_begin, row_end;
+  int32_t num_peers, rank;
+  int32_t B, H, N, dv;
+  int32_t dtype;
+  int32_t reserved;
+} pcv_peer_combine_params;
+
 /* library / device introspection */
 typedef struct pcv_device_info {
   int32_t device;
@@ -202,6 +225,7 @@ PCV_API int pcv_attn_supported_tcgen05(const pcv_attn_params* p);
 PCV_API int pcv_attn_workspace_bytes(const pcv_attn_params* p, size_t* bytes);
 PCV_API int pcv_attn_fwd(const pcv_attn_params* p, void* stream);
 PCV_API int pcv_attn_combine(const pcv_combine_params* p, void* stream);
+PCV_API int pcv_attn_combine_peers(const pcv_peer_combine_params* p, void* stream);
 PCV_API int pcv_partial_rescale(const pcv_rescale_params* p, void* stream);
 PCV_API int pcv_rotary_apply(const pcv_rotary_params* p, void* stream);
 PCV_API int pcv_kv_append(const pcv_kv_append_params* p, void* stream);

@@ -26,6 +26,7 @@ EXPORTS = (
     "pcv_attn_workspace_bytes",
     "pcv_attn_fwd",
     "pcv_attn_combine",
+    "pcv_attn_combine_peers",
     "pcv_partial_rescale",
     "pcv_rotary_apply",
     "pcv_kv_append",
@@ -69,6 +70,21 @@ class CombineParams(C.Structure):
         ("num_parts", C.c_int32),
         ("B", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("dv", C.c_int32),
         ("dtype", C.c_int32),
+    ]
+
+
+PCV_MAX_PEERS = 8
+
+
+class PeerCombineParams(C.Structure):
+    _fields_ = [
+        ("part_o", C.c_void_p * PCV_MAX_PEERS), ("part_m", C.c_void_p * PCV_MAX_PEERS),
+        ("part_l", C.c_void_p * PCV_MAX_PEERS), ("out", C.c_void_p * PCV_MAX_PEERS),
+        ("o_stride_b", C.c_int64), ("o_stride_n", C.c_int64), ("o_stride_h", C.c_int64),
+        ("row_begin", C.c_int64), ("row_end", C.c_int64),
+        ("num_peers", C.c_int32), ("rank", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("dv", C.c_int32),
+        ("dtype", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -145,6 +161,8 @@ def lib() -> C.CDLL:
         l.pcv_attn_combine.argtypes = [C.POINTER(CombineParams), C.c_void_p]
         l.pcv_rotary_apply.argtypes = [C.POINTER(RotaryParams), C.c_void_p]
         l.pcv_partial_rescale.argtypes = [C.POINTER(RescaleParams), C.c_void_p]
+        l.pcv_attn_combine_peers.argtypes = [C.POINTER(PeerCombineParams), C.c_void_p]
+        l.pcv_attn_combine_peers.restype = C.c_int
         l.pcv_profile_begin.restype = C.c_int
         l.pcv_profile_end.restype = C.c_int
         l.pcv_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32)]

@@ -69,6 +69,67 @@ int combine_t(const float* po, const float* pm, const float* pl, int nparts, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// combine over peers: one warp per owned row; every lane keeps num_peers 16-byte loads in flight (the
+// remote ones cross NVLink), then pushes the normalised row to every rank's output buffer.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) combine_peers_kernel(const pcv_peer_combine_params p) {
+  const int64_t r = p.row_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= p.row_end) return;
+  const int G = p.num_peers;
+  float mg[PCV_MAX_PEERS], w[PCV_MAX_PEERS];
+  float m = -INFINITY;
+#pragma unroll
+  for (int g = 0; g < PCV_MAX_PEERS; ++g) {
+    mg[g] = (g < G) ? p.part_m[g][r] : -INFINITY;
+    m = fmaxf(m, mg[g]);
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int g = 0; g < PCV_MAX_PEERS; ++g) {
+    w[g] = (g < G && mg[g] != -INFINITY) ? exp2f(mg[g] - m) : 0.f;
+    if (g < G) l += p.part_l[g][r] * w[g];
+  }
+  const float inv = 1.f / l;
+  const int n = (int)(r % p.N);
+  const int h = (int)((r / p.N) % p.H);
+  const int b = (int)(r / ((int64_t)p.N * p.H));
+  const int64_t o_off = (int64_t)b * p.o_stride_b + (int64_t)n * p.o_stride_n + (int64_t)h * p.o_stride_h;
+  if ((p.dv & 3) == 0) {
+    for (int c = lane * 4; c < p.dv; c += 128) {
+      float4 x[PCV_MAX_PEERS];
+#pragma unroll
+      for (int g = 0; g < PCV_MAX_PEERS; ++g)
+        if (g < G) x[g] = *reinterpret_cast<const float4*>(p.part_o[g] + r * p.dv + c);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < PCV_MAX_PEERS; ++g)
+        if (g < G) {
+          acc.x = fmaf(x[g].x, w[g], acc.x);
+          acc.y = fmaf(x[g].y, w[g], acc.y);
+          acc.z = fmaf(x[g].z, w[g], acc.z);
+          acc.w = fmaf(x[g].w, w[g], acc.w);
+        }
+      T v0 = Elem<T>::from_f(acc.x * inv), v1 = Elem<T>::from_f(acc.y * inv);
+      T v2 = Elem<T>::from_f(acc.z * inv), v3 = Elem<T>::from_f(acc.w * inv);
+      uint2 packed;
+      packed.x = (uint32_t)(*reinterpret_cast<unsigned short*>(&v0)) | ((uint32_t)(*reinterpret_cast<unsigned short*>(&v1)) << 16);
+      packed.y = (uint32_t)(*reinterpret_cast<unsigned short*>(&v2)) | ((uint32_t)(*reinterpret_cast<unsigned short*>(&v3)) << 16);
+#pragma unroll
+      for (int g = 0; g < PCV_MAX_PEERS; ++g)
+        if (g < G) *reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.out[g]) + o_off + c) = packed;
+    }
+  } else {
+    for (int c = lane; c < p.dv; c += 32) {
+      float acc = 0.f;
+      for (int g = 0; g < G; ++g) acc = fmaf(p.part_o[g][r * p.dv + c], w[g], acc);
+      for (int g = 0; g < G; ++g) reinterpret_cast<T*>(p.out[g])[o_off + c] = Elem<T>::from_f(acc * inv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // rescale: one warp per row, float4 where the row length allows.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rescale_kernel(const pcv_rescale_params p) {
@@ -205,6 +266,30 @@ int launch_combine(const pcv_combine_params& p, cudaStream_t stream) {
                                     p.o_stride_b, p.o_stride_n, p.o_stride_h, nullptr, nullptr, nullptr, stream);
   return combine_t<__half>(p.part_o, p.part_m, p.part_l, p.num_parts, p.B, p.H, p.N, p.dv, p.out, p.o_stride_b,
                            p.o_stride_n, p.o_stride_h, nullptr, nullptr, nullptr, stream);
+}
+
+int launch_combine_peers(const pcv_peer_combine_params& p, cudaStream_t stream) {
+  PCV_REQUIRE(p.num_peers >= 1 && p.num_peers <= PCV_MAX_PEERS, PCV_ERR_INVALID, "combine_peers: num_peers=%d", p.num_peers);
+  PCV_REQUIRE(p.rank >= 0 && p.rank < p.num_peers, PCV_ERR_INVALID, "combine_peers: bad rank %d", p.rank);
+  PCV_REQUIRE(p.B >= 1 && p.H >= 1 && p.N >= 1 && p.dv >= 1, PCV_ERR_INVALID, "combine_peers: bad dimension");
+  PCV_REQUIRE(p.dtype == PCV_BF16 || p.dtype == PCV_F16, PCV_ERR_INVALID, "combine_peers: unknown dtype %d", p.dtype);
+  const int64_t R = (int64_t)p.B * p.H * p.N;
+  PCV_REQUIRE(p.row_begin >= 0 && p.row_begin <= p.row_end && p.row_end <= R, PCV_ERR_INVALID, "combine_peers: bad row range");
+  for (int g = 0; g < p.num_peers; ++g)
+    PCV_REQUIRE(p.part_o[g] && p.part_m[g] && p.part_l[g] && p.out[g], PCV_ERR_INVALID, "combine_peers: null pointer for peer %d", g);
+  if ((p.dv & 3) == 0)
+    PCV_REQUIRE(((p.o_stride_b | p.o_stride_n | p.o_stride_h) & 3) == 0, PCV_ERR_INVALID, "combine_peers: output strides must be multiples of 4");
+  const int64_t rows = p.row_end - p.row_begin;
+  if (rows == 0) return PCV_OK;
+  const int warps = 8;
+  const unsigned blocks = (unsigned)((rows + warps - 1) / warps);
+  if (p.dtype == PCV_BF16)
+    combine_peers_kernel<__nv_bfloat16><<<blocks, warps * 32, 0, stream>>>(p);
+  else
+    combine_peers_kernel<__half><<<blocks, warps * 32, 0, stream>>>(p);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PCV_OK;
 }
 
 int launch_rescale(const pcv_rescale_params& p, cudaStream_t stream) {

@@ -50,6 +50,7 @@ def test_ctypes_layout_matches_header(tmp_path):
         "pcv_combine_params": _lib.CombineParams,
         "pcv_rotary_params": _lib.RotaryParams,
         "pcv_rescale_params": _lib.RescaleParams,
+        "pcv_peer_combine_params": _lib.PeerCombineParams,
         "pcv_kv_append_params": _lib.KvAppendParams,
         "pcv_device_info": _lib.DeviceInfo,
     }

@@ -27,9 +27,10 @@ for (B, N, M, H, d, causal) in [(2, 200, 5000, 4, 64, False), (2, 512, 16384, 8,
     pad[0, : M // 3] = True
     pad = pad.to(dev)
     m0, m1 = shard_bounds(M, world, rank)
-    out = sharded_attention(q, k[:, m0:m1], v[:, m0:m1], H, d ** -0.5, M, m0, pad[:, m0:m1], causal)
+    out = sharded_attention(q, k[:, m0:m1], v[:, m0:m1], H, d ** -0.5, M, m0, pad[:, m0:m1], causal, merge="peer")
+    out_nccl = sharded_attention(q, k[:, m0:m1], v[:, m0:m1], H, d ** -0.5, M, m0, pad[:, m0:m1], causal, merge="nccl")
     ref = ops.attention(q, k, v, H, d ** -0.5, pad_mask=pad, causal=causal)
-    err = (out.float() - ref.float()).abs().max().item()
+    err = max((out.float() - ref.float()).abs().max().item(), (out_nccl.float() - ref.float()).abs().max().item())
     bound = 1e-2 * ref.float().abs().max().item()
     gathered = [torch.empty_like(out) for _ in range(world)]
     dist.all_gather(gathered, out)
