@@ -74,6 +74,7 @@ struct TcParams {
   int write_partial;
   float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
   float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
+  int rows_per_unit;                // 256 (two query tiles per CTA) or 128 (wide-dv mode)
   int dbg;                          // developer experiments (PCV_DBG): 1 = softmax skips its math, 2 = no PV MMAs, 4 = no QK MMAs
   int optimistic;                   // 1: exponentiate against the current reference, verify the max afterwards
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
@@ -84,7 +85,8 @@ struct Cfg {
   static constexpr int kQBoxes = DQK / 64;
   static constexpr int kVBoxes = DV / 64;
   static constexpr int kQTileBytes = kQBoxes * kBoxBytes;
-  static constexpr int kQBytes = 2 * kQTileBytes;
+  static constexpr bool kWide = DV > 128;  // one query tile per CTA: the O accumulator takes TMEM columns [256, 256+DV)
+  static constexpr int kQBytes = (kWide ? 1 : 2) * kQTileBytes;
   static constexpr int kStageBytes = (DQK > DV ? DQK : DV) / 64 * kBoxBytes;
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kMaxSmem = 232448 - 1024;  // leave room for the 1024-byte alignment slack
@@ -92,7 +94,7 @@ struct Cfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kBarrierBytes + 1024;
   static_assert(kStages >= 3, "need at least K_j, V_j, K_(j+1) in flight");
-  static_assert(DQK % 64 == 0 && DV % 64 == 0 && DQK <= 128 && DV <= 128, "padded head dims");
+  static_assert(DQK % 64 == 0 && DV % 64 == 0 && DQK <= 128 && DV <= 256, "padded head dims");
 };
 
 constexpr int kTraceTiles = 48, kTraceEvents = 8, kTraceRoles = 3;
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(256) tc_combine_kernel(const UnitRec* __restri
   const int row = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int n = u.q0 + row;
-  if (n >= p.N) return;
+  if (n >= p.N || row >= p.rows_per_unit) return;
   float m = -INFINITY;
   for (int s = 0; s < u.slot_count; ++s) m = fmaxf(m, p.slot_m[(int64_t)(u.slot_begin + s) * kRowsPerUnit + row]);
   float l = 0.f;
@@ -713,11 +715,11 @@ struct Plan {
   UnitRec* d_units = nullptr;
 };
 
-void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms) {
-  const int QB = (N + kRowsPerUnit - 1) / kRowsPerUnit;
+void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms, int rows_per_unit) {
+  const int QB = (N + rows_per_unit - 1) / rows_per_unit;
   const int T = (M + kTileN - 1) / kTileN;
   const int BH = B * H;
-  auto ntile_of = [&](int qb) { return (N - qb * kRowsPerUnit) > kTileM ? 2 : 1; };
+  auto ntile_of = [&](int qb) { return (rows_per_unit > kTileM && (N - qb * rows_per_unit) > kTileM) ? 2 : 1; };
   std::vector<std::vector<Segment>> per_cta;
   const bool split_mode = QB <= 8 && QB <= num_sms;
   if (split_mode) {
@@ -736,7 +738,7 @@ void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms) {
         const int t1 = (int)std::min<int64_t>(T, t0 + (end - pos));
         for (int r = 0; r < QB; ++r) {
           Segment s{};
-          s.b = bh / H; s.h = bh % H; s.q0 = r * kRowsPerUnit; s.ntile = ntile_of(r); s.t0 = t0; s.t1 = t1;
+          s.b = bh / H; s.h = bh % H; s.q0 = r * rows_per_unit; s.ntile = ntile_of(r); s.t0 = t0; s.t1 = t1;
           if (t0 == 0 && t1 == T) {
             s.slot = -1;
           } else {
@@ -753,7 +755,7 @@ void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms) {
     int next = 0;
     for (auto& kv : unit_slots) {
       UnitRec u{};
-      u.b = kv.first.first / H; u.h = kv.first.first % H; u.q0 = kv.first.second * kRowsPerUnit;
+      u.b = kv.first.first / H; u.h = kv.first.first % H; u.q0 = kv.first.second * rows_per_unit;
       u.slot_begin = next; u.slot_count = (int)kv.second.size();
       for (int old : kv.second) remap[old] = next++;
       pl.units.push_back(u);
@@ -770,7 +772,7 @@ void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms) {
       for (int64_t u = U * c / nctas; u < U * (c + 1) / nctas; ++u) {
         const int bh = (int)(u / QB), qb = (int)(u % QB);
         Segment s{};
-        s.b = bh / H; s.h = bh % H; s.q0 = qb * kRowsPerUnit; s.ntile = ntile_of(qb); s.t0 = 0; s.t1 = T; s.slot = -1;
+        s.b = bh / H; s.h = bh % H; s.q0 = qb * rows_per_unit; s.ntile = ntile_of(qb); s.t0 = 0; s.t1 = T; s.slot = -1;
         per_cta[c].push_back(s);
       }
     }
@@ -804,9 +806,9 @@ int ensure_diag(int dev) {
 unsigned long long* g_trace_dev = nullptr;  // PCV_TRACE=1
 
 std::mutex g_plan_mu;
-std::map<std::tuple<int, int, int, int, int, int>, Plan*> g_plans;  // (device, B, H, N, M, sms)
+std::map<std::tuple<int, int, int, int, int, int, int>, Plan*> g_plans;  // (device, B, H, N, M, sms, rows/unit)
 
-int get_plan(int B, int H, int N, int M, Plan** out) {
+int get_plan(int B, int H, int N, int M, int rows_per_unit, Plan** out) {
   int dev = 0;
   PCV_CHECK_CUDA(cudaGetDevice(&dev));
   int sms = 0;
@@ -816,14 +818,14 @@ int get_plan(int B, int H, int N, int M, Plan** out) {
     int rc = ensure_diag(dev);
     if (rc != PCV_OK) return rc;
   }
-  auto key = std::make_tuple(dev, B, H, N, M, sms);
+  auto key = std::make_tuple(dev, B, H, N, M, sms, rows_per_unit);
   auto it = g_plans.find(key);
   if (it != g_plans.end()) {
     *out = it->second;
     return PCV_OK;
   }
   Plan* pl = new Plan();
-  build_plan(*pl, B, H, N, M, sms);
+  build_plan(*pl, B, H, N, M, sms, rows_per_unit);
   PCV_CHECK_CUDA(cudaMalloc(&pl->d_segs, sizeof(Segment) * pl->segs.size()));
   PCV_CHECK_CUDA(cudaMalloc(&pl->d_cta, sizeof(int) * pl->cta_seg_begin.size()));
   PCV_CHECK_CUDA(cudaMemcpy(pl->d_segs, pl->segs.data(), sizeof(Segment) * pl->segs.size(), cudaMemcpyHostToDevice));
@@ -924,7 +926,8 @@ bool attn_tc_supported(const pcv_attn_params& p, const char** why) {
     *why = w;
     return false;
   };
-  if (p.dqk > 128 || p.dv > 128) return fail("head dim > 128 (TMEM budget of the 2-tile kernel)");
+  if (p.dqk > 128) return fail("qk head dim > 128 (shared-memory budget of the K ring)");
+  if (p.dv > 256) return fail("v head dim > 256 (TMEM budget: O accumulator columns)");
   if ((p.dqk % 8) || (p.dv % 8)) return fail("head dims must be multiples of 8 (16-byte TMA strides)");
   if (!(p.scale > 0.f)) return fail("scale must be positive");
   auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
@@ -948,7 +951,7 @@ bool attn_tc_supported(const pcv_attn_params& p, const char** why) {
 
 int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
   Plan* pl = nullptr;
-  int rc = get_plan(p.B, p.H, p.N, p.M, &pl);
+  int rc = get_plan(p.B, p.H, p.N, p.M, pad64(p.dv) > 128 ? kTileM : kRowsPerUnit, &pl);
   if (rc != PCV_OK) return rc;
   size_t b = slots_bytes(*pl, pad64(p.dv));
   b = (b + 255) / 256 * 256;
@@ -959,9 +962,10 @@ int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
 
 int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   Plan* pl = nullptr;
-  int rc = get_plan(a.B, a.H, a.N, a.M, &pl);
-  if (rc != PCV_OK) return rc;
   const int DQK = pad64(a.dqk), DV = pad64(a.dv);
+  const int rows_per_unit = DV > 128 ? kTileM : kRowsPerUnit;
+  int rc = get_plan(a.B, a.H, a.N, a.M, rows_per_unit, &pl);
+  if (rc != PCV_OK) return rc;
   size_t need = 0;
   attn_tc_workspace_bytes(a, &need);
   PCV_REQUIRE(need == 0 || (a.workspace != nullptr && a.workspace_bytes >= need), PCV_ERR_WORKSPACE,
@@ -979,6 +983,7 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   p.q_bcast = (a.q_stride_b == 0) ? 1 : 0;
   p.out = a.out; p.osb = a.o_stride_b; p.osn = a.o_stride_n; p.osh = a.o_stride_h;
   p.write_partial = a.write_partial;
+  p.rows_per_unit = rows_per_unit;
   {
     static const int opt = [] { const char* e = getenv("PCV_OPT"); return e ? atoi(e) : 1; }();
     p.optimistic = opt;
@@ -1028,6 +1033,10 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   PCV_TC_CASE(64, 64)
   PCV_TC_CASE(64, 128)
   PCV_TC_CASE(128, 64)
+  PCV_TC_CASE(64, 192)
+  PCV_TC_CASE(64, 256)
+  PCV_TC_CASE(128, 192)
+  PCV_TC_CASE(128, 256)
 #undef PCV_TC_CASE
   set_error("tcgen05 attention: no instantiation for padded head dims (%d, %d)", DQK, DV);
   return PCV_ERR_UNSUPPORTED;

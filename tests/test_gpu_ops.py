@@ -31,6 +31,8 @@ SHAPES = [
     (1, 40, 96, 1, 322, 322),     # optical-flow encoder head dim
     (1, 70, 64, 1, 512, 512),     # optical-flow decoder head dim
     (2, 256, 512, 2, 128, 128),   # north-star head dim, small
+    (1, 300, 2048, 2, 64, 192),   # wide-dv single-tile mode, split over key ranges
+    (1, 130, 300, 2, 128, 256),   # widest v head the tcgen05 family covers
 ]
 
 

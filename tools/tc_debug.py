@@ -20,6 +20,9 @@ CASES = {
     "d64": (2, 130, 300, 4, 64, 64, 2, False, False, 1.0),
     "d32_96": (2, 64, 257, 8, 32, 96, 2, False, False, 1.0),
     "d24": (2, 1, 77, 4, 24, 24, 2, False, False, 1.0),
+    "d32_160": (2, 64, 257, 8, 32, 160, 2, False, False, 1.0),
+    "wide256": (1, 130, 300, 2, 128, 256, 1, False, False, 1.0),
+    "wide_split": (1, 300, 4096, 2, 64, 192, 1, False, True, 1.0),
     "pad": (3, 40, 300, 2, 64, 64, 1, False, True, 1.0),
     "causal": (2, 100, 300, 2, 64, 64, 2, True, True, 1.0),
     "peaked": (1, 128, 4096, 2, 128, 128, 1, False, False, 6.0),
