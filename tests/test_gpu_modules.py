@@ -206,3 +206,23 @@ def test_patch_rebinds_reference_style_modules():
     w = {k: v.cpu().double() for k, v in holder[0].state_dict().items()}
     ref, _ = O.mha(w, x.cpu().double(), kv.cpu().double(), 2)
     assert_close(out, ref, REL_1LAYER, "patched")
+
+
+def test_streamed_host_input_matches_plain_forward():
+    import perceiver_io_b200 as P
+    from perceiver_io_b200.streaming import cross_attention_from_host
+
+    torch.manual_seed(3)
+    layer = P.CrossAttention(4, 128, 96).cuda().bfloat16().eval()
+    xq = torch.randn(1, 48, 128).bfloat16().pin_memory()
+    xkv = torch.randn(3, 2500, 96).bfloat16().pin_memory()
+    pad = torch.zeros(3, 2500, dtype=torch.bool)
+    pad[1, :700] = True
+    pad[2, :] = True
+    out_host = torch.empty(3, 48, 128, dtype=torch.bfloat16).pin_memory()
+    with torch.no_grad():
+        ref = layer(xq.cuda(), xkv.cuda(), pad_mask=pad.cuda()).last_hidden_state
+        got = cross_attention_from_host(layer, xq, xkv, pad_mask=pad, chunk=600, out_host=out_host).last_hidden_state
+    torch.cuda.synchronize()
+    assert_close(got, ref.double(), 1e-2, "streamed vs plain")
+    assert torch.equal(out_host, got.cpu())
