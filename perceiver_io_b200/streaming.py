@@ -64,7 +64,10 @@ def cross_attention_from_host(module, x_q: torch.Tensor, x_kv_host: torch.Tensor
                     buf = torch.empty(B, chunk, x_kv_host.shape[2], dtype=prm.dtype, device=device)
                     staged[slot] = buf
                 view = buf[:, : b - a]
-                view.copy_(x_kv_host[:, a:b], non_blocking=True)
+                # one contiguous (rows x C) block per batch row: a strided host slice would be staged through
+                # a pageable temporary by torch and serialise the pipeline
+                for bi in range(B):
+                    view[bi].copy_(x_kv_host[bi, a:b], non_blocking=True)
                 ready[slot].record(copy)
             return view
 
