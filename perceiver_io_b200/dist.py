@@ -81,6 +81,7 @@ class PeerMerger:
     [Õ | m | l] and the output buffer, both mapped into every rank of the group."""
 
     _cache = {}
+    disabled = False  # set when symmetric memory could not be set up; "auto" then stays on NCCL
 
     def __init__(self, B, H, N, dv, dtype, device, group):
         import torch.distributed._symmetric_memory as symm_mem
@@ -139,6 +140,17 @@ class PeerMerger:
         return self.out.view(self.B, self.N, self.H * self.dv)
 
 
+_warned = set()
+
+
+def _warn_once(msg: str) -> None:
+    if msg not in _warned:
+        _warned.add(msg)
+        import warnings
+
+        warnings.warn(msg)
+
+
 def _peer_merge_possible(t: torch.Tensor, world: int) -> bool:
     if not t.is_cuda or world < 2 or world > 8:
         return False
@@ -159,8 +171,9 @@ def sharded_attention(q: torch.Tensor, k_shard: torch.Tensor, v_shard: torch.Ten
     available and no custom ``kernels`` are injected).  With the peer merge the result lives in a reused
     symmetric buffer; ``copy_out=False`` returns that buffer itself (valid until the next call)."""
     world_now = dist.get_world_size(group) if dist.is_initialized() else 1
+    merge_requested = merge
     if merge == "auto":
-        merge = "peer" if (kernels is None and _peer_merge_possible(k_shard, world_now)) else "nccl"
+        merge = "peer" if (kernels is None and not PeerMerger.disabled and _peer_merge_possible(k_shard, world_now)) else "nccl"
     if merge == "peer" and world_now > 1:
         from . import ops
 
@@ -168,7 +181,18 @@ def sharded_attention(q: torch.Tensor, k_shard: torch.Tensor, v_shard: torch.Ten
         B, N = k_shard.shape[0], q.shape[1]
         dv = (v_shard.shape[2] // H) if v_shard.dim() == 3 else v_shard.shape[3]
         cdt = q.dtype if q.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
-        pm = PeerMerger.get(B, H, N, dv, cdt, k_shard.device, group)
+        try:
+            pm = PeerMerger.get(B, H, N, dv, cdt, k_shard.device, group)
+        except Exception as exc:  # noqa: BLE001 — symmetric memory cannot be set up on this system
+            if merge_requested == "peer":
+                raise
+            _warn_once(f"perceiver_io_b200.dist: peer-memory merge unavailable ({type(exc).__name__}: {exc}); "
+                       "using the NCCL all-reduce merge")
+            PeerMerger.disabled = True
+            pm = None
+        if pm is None:
+            return sharded_attention(q, k_shard, v_shard, num_heads, scale, m_total, m_offset, pad_mask_shard, causal,
+                                     group, kernels, merge="nccl")
         ops.attention_partial(q, k_shard, v_shard, H, scale, pad_mask=pad_mask_shard, causal=causal,
                               m_total=m_total, m_offset=m_offset, out=(pm.po, pm.pm, pm.pl))
         out = pm.merge()
