@@ -74,7 +74,8 @@ struct TcParams {
   int write_partial;
   float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
   float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
-  int rows_per_unit;                // 256 (two query tiles per CTA) or 128 (wide-dv mode)
+  int rows_per_unit;                // query rows per work unit: 256 (two tiles per CTA), 128 (wide-dv), 512 (CTA pair)
+  int slot_rows;                    // row stride of the partial slots (>= rows_per_unit)
   int dbg;                          // developer experiments (PCV_DBG): 1 = softmax skips its math, 2 = no PV MMAs, 4 = no QK MMAs
   int optimistic;                   // 1: exponentiate against the current reference, verify the max afterwards
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
@@ -135,7 +136,11 @@ struct RowState {
   float l;      // running denominator relative to m_ref
 };
 
+struct TileCtx;
+__device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c);
+
 struct TileCtx {
+  uint32_t p_full_pair;  // 0: arrive locally (count 128); else shared::cluster address of the pair leader's p_full[wg] (one arrive per warp)
   uint32_t tS, tO;    // TMEM addresses (lane field included) of this thread's S / O row
   int wg, row;
   int j0;             // first key of the tile
@@ -145,6 +150,16 @@ struct TileCtx {
   bool trace_on;
   int tt;
 };
+
+// P of this thread's row is in TMEM (tcgen05.wait::st + fence done by the caller): tell the MMA issuer
+__device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c) {
+  if (c.p_full_pair == 0) {
+    mbar_arrive(&bar.p_full[c.wg]);
+  } else {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(c.p_full_pair);
+  }
+}
 
 template <int DV, bool BF16, bool MASKED>
 __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, const TileCtx& c, RowState& st) {
@@ -240,7 +255,7 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
   st.l += sum2.x + sum2.y;
   tmem_wait_st();
   tc_fence_before_sync();
-  mbar_arrive(&bar.p_full[c.wg]);
+  arrive_p_full(bar, c);
   PCV_TRACE(p, c.wg, c.tt, 5, c.trace_on);
 }
 
@@ -292,14 +307,21 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
   st.l += sum2.x + sum2.y;
   tmem_wait_st();
   tc_fence_before_sync();
-  mbar_arrive(&bar.p_full[c.wg]);
+  arrive_p_full(bar, c);
   PCV_TRACE(p, c.wg, c.tt, 5, c.trace_on);
   return true;
 }
 
 template <int DQK, int DV, bool BF16>
 __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, int wg, int row, int seg_lo,
-                                             int seg_hi) {
+                                             int seg_hi, int pair_rank = -1) {
+  // pair_rank < 0: single-CTA kernel.  Otherwise this CTA is rank `pair_rank` of a cta_group::2 pair: query tile
+  // `wg` of the pair spans 256 rows (128 per CTA) and the p_full / o_empty barriers live in the leader CTA.
+  const bool pair = pair_rank >= 0;
+  const int tile_rows = pair ? 2 * kTileM : kTileM;
+  const int row_in_unit = wg * tile_rows + (pair ? pair_rank * kTileM : 0) + row;
+  const uint32_t p_full_pair = pair ? mapa_cluster(smem_u32(&bar.p_full[wg]), 0) : 0u;
+  const uint32_t o_empty_pair = pair ? mapa_cluster(smem_u32(&bar.o_empty[wg]), 0) : 0u;
   const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
   const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
   const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
@@ -308,12 +330,13 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
   for (int sg = seg_lo; sg < seg_hi; ++sg) {
     const Segment seg = p.segs[sg];
     if (wg == 1 && seg.ntile < 2) continue;
-    const int n = seg.q0 + wg * kTileM + row;
+    const int n = seg.q0 + row_in_unit;
     RowState st;
     st.m_ref = -INFINITY;
     st.l = 0.f;
     TileCtx c;
     c.tS = tS; c.tO = tO; c.wg = wg; c.row = row;
+    c.p_full_pair = p_full_pair;
     c.cshift = n + p.causal_shift;
     c.trace_on = (row == 0 && sg == seg_lo);
 
@@ -335,7 +358,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       PCV_TRACE(p, wg, c.tt, 0, c.trace_on);
       if (p.dbg & 1) {  // timing experiment: protocol only
         tc_fence_before_sync();
-        mbar_arrive(&bar.p_full[wg]);
+        arrive_p_full(bar, c);
         continue;
       }
       if (masked_tile) {
@@ -394,7 +417,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
           p.fin_l[r] = l;
         }
       } else {
-        const int64_t r = (int64_t)seg.slot * kRowsPerUnit + wg * kTileM + row;
+        const int64_t r = (int64_t)seg.slot * p.slot_rows + row_in_unit;
         dst = p.slot_o + r * DV;
         ncols = DV;
         store = true;
@@ -417,7 +440,12 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       }
     }
     tc_fence_before_sync();
-    mbar_arrive(&bar.o_empty[wg]);
+    if (!pair) {
+      mbar_arrive(&bar.o_empty[wg]);
+    } else {
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(o_empty_pair);
+    }
   }
 }
 
@@ -638,6 +666,248 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   }
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): a cluster of two CTAs on one TPC works on 512 query rows of one (b,h).
+// Every tcgen05.mma is M = 256 (128 rows from each CTA) and each CTA supplies only HALF of the B operand —
+// keys [64r, 64r+64) of the K tile for Q K^T, channels [64r, 64r+64) of the V tile for P V — so per SM the
+// shared-memory operand traffic, the TMA fill and the L2->SM traffic of K/V are all halved relative to the
+// single-CTA kernel (whose SS-mode Q K^T sits exactly on the 128 B/clk shared-memory ceiling).
+// Rank 0 (leader) issues all MMAs; completion is multicast to both CTAs with tcgen05.commit; both CTAs' TMA
+// transactions and softmax arrivals are counted on the leader's barriers.  dv is 128 (padded) in this kernel.
+// --------------------------------------------------------------------------------------------------
+template <int DQK>
+struct PairCfg {
+  static constexpr int DV = 128;
+  static constexpr int kQBoxes = DQK / 64;
+  static constexpr int kQTileBytes = kQBoxes * kBoxBytes;        // 128 rows x DQK
+  static constexpr int kQBytes = 2 * kQTileBytes;
+  static constexpr int kKHalfBytes = kQBoxes * (kBoxBytes / 2);  // 64 keys x DQK: kQBoxes boxes of 64 rows
+  static constexpr int kVHalfBytes = kBoxBytes;                  // 128 keys x 64 channels
+  static constexpr int kStageBytes = kKHalfBytes > kVHalfBytes ? kKHalfBytes : kVHalfBytes;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kMaxSmem = 232448 - 1024;
+  static constexpr int kStagesRaw = (kMaxSmem - kQBytes - kBarrierBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kBarrierBytes + 1024;
+  static_assert(kStages >= 3, "ring too shallow");
+};
+
+template <int DQK, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
+  using C = PairCfg<DQK>;
+  constexpr int DV = C::DV;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + C::kQBytes;
+  Barriers& bar = *reinterpret_cast<Barriers*>(smem + C::kQBytes + C::kStages * C::kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair_id = blockIdx.x >> 1;
+  const int seg_lo = p.cta_seg_begin[pair_id];
+  const int seg_hi = p.cta_seg_begin[pair_id + 1];
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar.q_full, 2);    // leader: own arrive.expect_tx + the peer's remote arrive
+    mbar_init(&bar.q_empty, 1);   // multicast commit
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&bar.kv_full[i], 2);
+      mbar_init(&bar.kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar.s_full[i], 1);
+      mbar_init(&bar.p_full[i], 8);   // one arrive per softmax warp, 4 warps x 2 CTAs
+      mbar_init(&bar.o_full[i], 1);
+      mbar_init(&bar.o_empty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_pair(&bar.tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after_sync();
+
+  if (warp < 8) {
+    reg_alloc<216>();
+    softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi, (int)rank);
+  } else {
+    reg_dealloc<72>();
+  }
+
+  if (warp == kTmaWarp) {
+    // ===== TMA producer (both CTAs): own Q tiles, own half of every K / V tile; bytes counted on the leader =====
+    const bool leader_lane = elect_one();
+    const uint32_t q_full_leader = mapa_cluster(smem_u32(&bar.q_full), 0);
+    uint32_t it = 0, n_q = 0;
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const int bq = p.q_bcast ? 0 : seg.b;
+      mbar_wait(&bar.q_empty, (n_q & 1) ^ 1, 1);
+      ++n_q;
+      if (leader_lane) {
+        if (rank == 0)
+          mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(2 * seg.ntile * C::kQTileBytes));
+        else
+          mbar_arrive_cluster(q_full_leader);
+        for (int i = 0; i < seg.ntile; ++i)
+          for (int bx = 0; bx < C::kQBoxes; ++bx)
+            tma_load_4d_pair(q_smem + i * C::kQTileBytes + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64,
+                             seg.q0 + i * 2 * kTileM + (int)rank * kTileM, seg.h, bq);
+      }
+      for (int t = seg.t0; t < seg.t1; ++t) {
+        {
+          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+          mbar_wait(&bar.kv_empty[slot], par ^ 1, 2);
+          if (leader_lane) {
+            if (rank == 0)
+              mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(2 * C::kKHalfBytes));
+            else
+              mbar_arrive_cluster(mapa_cluster(smem_u32(&bar.kv_full[slot]), 0));
+#pragma unroll
+            for (int bx = 0; bx < C::kQBoxes; ++bx)  // K half: 64 keys x 64 channels per box
+              tma_load_4d_pair(kv_smem + slot * C::kStageBytes + bx * (kBoxBytes / 2), &tmap_k, &bar.kv_full[slot],
+                               bx * 64, t * kTileN + (int)rank * 64, seg.h, seg.b);
+          }
+          ++it;
+        }
+        {
+          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+          mbar_wait(&bar.kv_empty[slot], par ^ 1, 3);
+          if (leader_lane) {
+            if (rank == 0)
+              mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(2 * C::kVHalfBytes));
+            else
+              mbar_arrive_cluster(mapa_cluster(smem_u32(&bar.kv_full[slot]), 0));
+            // V half: all 128 keys, channels [64*rank, 64*rank + 64)
+            tma_load_4d_pair(kv_smem + slot * C::kStageBytes, &tmap_v, &bar.kv_full[slot], (int)rank * 64, t * kTileN,
+                             seg.h, seg.b);
+          }
+          ++it;
+        }
+      }
+    }
+  } else if (warp == kMmaWarp && rank == 0) {
+    // ===== MMA issuer (leader CTA only) =====
+    const bool leader_lane = elect_one();
+    constexpr uint32_t idesc_qk = make_idesc(2 * kTileM, kTileN, BF16, false);
+    constexpr uint32_t idesc_pv = make_idesc(2 * kTileM, DV, BF16, true);
+    const uint32_t tmem = bar.tmem_base;
+    const uint64_t dq0 = make_smem_desc(smem_u32(q_smem), 16, 1024);
+    const uint64_t dk0 = make_smem_desc(smem_u32(kv_smem), 16, 1024);
+    const uint64_t dv0 = make_smem_desc(smem_u32(kv_smem), kBoxBytes, 1024);
+    uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe0 = 0, n_oe1 = 0;
+
+    auto issue_qk = [&](int i, uint32_t k_slot) {
+      if (leader_lane && !(p.dbg & 4)) {
+        const uint64_t da = dq0 + (uint64_t)((i * C::kQTileBytes) >> 4);
+        const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < DQK / 16; ++kk) {
+          const uint64_t offa = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          const uint64_t offb = (uint64_t)(((kk >> 2) * (kBoxBytes / 2) + (kk & 3) * 32) >> 4);
+          mma_ss_pair(tmem + i * 128, da + offa, db + offb, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+      }
+    };
+    auto issue_pv = [&](int i, uint32_t v_slot, bool accumulate) {
+      if (leader_lane && !(p.dbg & 2)) {
+        const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < kTileN / 16; ++kk)
+          mma_ts_pair(tmem + 256 + i * 128, tmem + i * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+                      (accumulate || kk > 0) ? 1u : 0u);
+      }
+    };
+    auto commit = [&](uint64_t* b) {
+      if (leader_lane) tc_commit_pair(b, 3);
+    };
+
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const bool two = seg.ntile == 2;
+      const int nt = seg.t1 - seg.t0;
+      mbar_wait(&bar.q_full, n_q & 1, 4);
+      ++n_q;
+
+      uint32_t k_slot = it % C::kStages;
+      mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 5);
+      ++it;
+      tc_fence_after_sync();
+      issue_qk(0, k_slot);
+      commit(&bar.s_full[0]);
+      if (two) {
+        issue_qk(1, k_slot);
+        commit(&bar.s_full[1]);
+      }
+      commit(&bar.kv_empty[k_slot]);
+
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t v_slot = it % C::kStages;
+        mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
+        ++it;
+        if (j == 0) {
+          mbar_wait(&bar.o_empty[0], (n_oe0 & 1) ^ 1, 7);
+          ++n_oe0;
+        }
+        mbar_wait(&bar.p_full[0], n_p0 & 1, 8);
+        ++n_p0;
+        tc_fence_after_sync();
+        issue_pv(0, v_slot, j > 0);
+        const bool more = (j + 1 < nt);
+        if (more) {
+          k_slot = it % C::kStages;
+          mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
+          ++it;
+          tc_fence_after_sync();
+          issue_qk(0, k_slot);
+          commit(&bar.s_full[0]);
+        }
+        if (two) {
+          if (j == 0) {
+            mbar_wait(&bar.o_empty[1], (n_oe1 & 1) ^ 1, 10);
+            ++n_oe1;
+          }
+          mbar_wait(&bar.p_full[1], n_p1 & 1, 11);
+          ++n_p1;
+          tc_fence_after_sync();
+          issue_pv(1, v_slot, j > 0);
+        }
+        commit(&bar.kv_empty[v_slot]);
+        if (more) {
+          if (two) {
+            issue_qk(1, k_slot);
+            commit(&bar.s_full[1]);
+          }
+          commit(&bar.kv_empty[k_slot]);
+        }
+      }
+      commit(&bar.q_empty);
+      commit(&bar.o_full[0]);
+      if (two) commit(&bar.o_full[1]);
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its pair can still touch its memory / barriers
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(bar.tmem_base, 512);
+  }
+}
+
 // --------------------------------------------------------------------------------------------------
 // merge of split units (one warp per query row)
 // --------------------------------------------------------------------------------------------------
@@ -649,16 +919,16 @@ __global__ void __launch_bounds__(256) tc_combine_kernel(const UnitRec* __restri
   const int n = u.q0 + row;
   if (n >= p.N || row >= p.rows_per_unit) return;
   float m = -INFINITY;
-  for (int s = 0; s < u.slot_count; ++s) m = fmaxf(m, p.slot_m[(int64_t)(u.slot_begin + s) * kRowsPerUnit + row]);
+  for (int s = 0; s < u.slot_count; ++s) m = fmaxf(m, p.slot_m[(int64_t)(u.slot_begin + s) * p.slot_rows + row]);
   float l = 0.f;
   for (int s = 0; s < u.slot_count; ++s) {
-    const int64_t r = (int64_t)(u.slot_begin + s) * kRowsPerUnit + row;
+    const int64_t r = (int64_t)(u.slot_begin + s) * p.slot_rows + row;
     l += p.slot_l[r] * exp2f(p.slot_m[r] - m);
   }
   for (int c = lane * 4; c < DV; c += 128) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < u.slot_count; ++s) {
-      const int64_t r = (int64_t)(u.slot_begin + s) * kRowsPerUnit + row;
+      const int64_t r = (int64_t)(u.slot_begin + s) * p.slot_rows + row;
       const float w = exp2f(p.slot_m[r] - m);
       const float4 x = *reinterpret_cast<const float4*>(p.slot_o + r * DV + c);
       acc.x = fmaf(x.x, w, acc.x);
@@ -715,11 +985,12 @@ struct Plan {
   UnitRec* d_units = nullptr;
 };
 
-void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms, int rows_per_unit) {
+void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms, int rows_per_unit, int rows_per_tile) {
+  // num_sms = number of workers (CTAs, or CTA pairs for the cta_group::2 kernel)
   const int QB = (N + rows_per_unit - 1) / rows_per_unit;
   const int T = (M + kTileN - 1) / kTileN;
   const int BH = B * H;
-  auto ntile_of = [&](int qb) { return (rows_per_unit > kTileM && (N - qb * rows_per_unit) > kTileM) ? 2 : 1; };
+  auto ntile_of = [&](int qb) { return (rows_per_unit > rows_per_tile && (N - qb * rows_per_unit) > rows_per_tile) ? 2 : 1; };
   std::vector<std::vector<Segment>> per_cta;
   const bool split_mode = QB <= 8 && QB <= num_sms;
   if (split_mode) {
@@ -806,9 +1077,14 @@ int ensure_diag(int dev) {
 unsigned long long* g_trace_dev = nullptr;  // PCV_TRACE=1
 
 std::mutex g_plan_mu;
-std::map<std::tuple<int, int, int, int, int, int, int>, Plan*> g_plans;  // (device, B, H, N, M, sms, rows/unit)
+std::map<std::tuple<int, int, int, int, int, int, int, int>, Plan*> g_plans;  // (device, B, H, N, M, workers, rows/unit, rows/tile)
 
-int get_plan(int B, int H, int N, int M, int rows_per_unit, Plan** out) {
+struct Mode {
+  int rows_per_unit, rows_per_tile, slot_rows;
+  bool pair;
+};
+
+int get_plan(int B, int H, int N, int M, const Mode& mode, Plan** out) {
   int dev = 0;
   PCV_CHECK_CUDA(cudaGetDevice(&dev));
   int sms = 0;
@@ -818,14 +1094,15 @@ int get_plan(int B, int H, int N, int M, int rows_per_unit, Plan** out) {
     int rc = ensure_diag(dev);
     if (rc != PCV_OK) return rc;
   }
-  auto key = std::make_tuple(dev, B, H, N, M, sms, rows_per_unit);
+  if (mode.pair) sms /= 2;  // workers are CTA pairs
+  auto key = std::make_tuple(dev, B, H, N, M, sms, mode.rows_per_unit, mode.rows_per_tile);
   auto it = g_plans.find(key);
   if (it != g_plans.end()) {
     *out = it->second;
     return PCV_OK;
   }
   Plan* pl = new Plan();
-  build_plan(*pl, B, H, N, M, sms, rows_per_unit);
+  build_plan(*pl, B, H, N, M, sms, mode.rows_per_unit, mode.rows_per_tile);
   PCV_CHECK_CUDA(cudaMalloc(&pl->d_segs, sizeof(Segment) * pl->segs.size()));
   PCV_CHECK_CUDA(cudaMalloc(&pl->d_cta, sizeof(int) * pl->cta_seg_begin.size()));
   PCV_CHECK_CUDA(cudaMemcpy(pl->d_segs, pl->segs.data(), sizeof(Segment) * pl->segs.size(), cudaMemcpyHostToDevice));
@@ -864,13 +1141,13 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // (channels, rows, heads, batch) view of a (batch, rows, heads*channels)-style tensor; box = 64 x 128 x 1 x 1
 int make_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int rows, int heads, int batch,
-              int64_t stride_row, int64_t stride_head, int64_t stride_batch) {
+              int64_t stride_row, int64_t stride_head, int64_t stride_batch, int box_rows = kTileN) {
   auto fn = get_encode_fn();
   PCV_REQUIRE(fn != nullptr, PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)batch};
   if (stride_batch == 0) stride_batch = (int64_t)rows * stride_row;  // broadcast batch: dim is 1, stride unused
   cuuint64_t strides[3] = {(cuuint64_t)stride_row * 2, (cuuint64_t)stride_head * 2, (cuuint64_t)stride_batch * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)kTileN, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapDataType dt = dtype == PCV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = fn(tm, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -881,7 +1158,21 @@ int make_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int ro
 
 inline int pad64(int d) { return (d + 63) / 64 * 64; }
 
-size_t slots_bytes(const Plan& pl, int DV) { return sizeof(float) * (size_t)pl.num_slots * kRowsPerUnit * (DV + 2); }
+size_t slots_bytes(const Plan& pl, int DV, int slot_rows) {
+  return sizeof(float) * (size_t)pl.num_slots * slot_rows * (DV + 2);
+}
+
+Mode choose_mode(const pcv_attn_params& a) {
+  static const int pair_env = [] { const char* e = getenv("PCV_PAIR"); return e ? atoi(e) : 1; }();
+  const int DV = pad64(a.dv);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false};
+  if (pair_env && DV == 128 && a.N > kRowsPerUnit && sms >= 2 && (sms % 2) == 0)
+    return Mode{4 * kTileM, 2 * kTileM, 4 * kTileM, true};
+  return Mode{kRowsPerUnit, kTileM, kRowsPerUnit, false};
+}
 
 template <int DQK, int DV, bool BF16>
 int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk,
@@ -899,8 +1190,43 @@ int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, 
   PCV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   if (pl.num_units > 0) {
-    dim3 grid(pl.num_units, kRowsPerUnit / 8);
+    dim3 grid(pl.num_units, p.slot_rows / 8);
     tc_combine_kernel<DV, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return PCV_OK;
+}
+
+template <int DQK, bool BF16>
+int launch_pair(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk,
+                const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
+  using C = PairCfg<DQK>;
+  auto kern = attn_tc_pair_kernel<DQK, BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pl.num_ctas);  // num_ctas counts CTA pairs in this mode
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_mark_begin(stream);
+  PCV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, p));
+  prof_mark_end(stream);
+  count_launch();
+  if (pl.num_units > 0) {
+    dim3 grid(pl.num_units, p.slot_rows / 8);
+    tc_combine_kernel<128, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
     PCV_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -951,9 +1277,10 @@ bool attn_tc_supported(const pcv_attn_params& p, const char** why) {
 
 int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
   Plan* pl = nullptr;
-  int rc = get_plan(p.B, p.H, p.N, p.M, pad64(p.dv) > 128 ? kTileM : kRowsPerUnit, &pl);
+  const Mode mode = choose_mode(p);
+  int rc = get_plan(p.B, p.H, p.N, p.M, mode, &pl);
   if (rc != PCV_OK) return rc;
-  size_t b = slots_bytes(*pl, pad64(p.dv));
+  size_t b = slots_bytes(*pl, pad64(p.dv), mode.slot_rows);
   b = (b + 255) / 256 * 256;
   if (p.pad_mask != nullptr) b += sizeof(uint32_t) * (size_t)p.B * ((p.M + kTileN - 1) / kTileN * 4);
   *bytes = b;
@@ -963,8 +1290,8 @@ int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
 int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   Plan* pl = nullptr;
   const int DQK = pad64(a.dqk), DV = pad64(a.dv);
-  const int rows_per_unit = DV > 128 ? kTileM : kRowsPerUnit;
-  int rc = get_plan(a.B, a.H, a.N, a.M, rows_per_unit, &pl);
+  const Mode mode = choose_mode(a);
+  int rc = get_plan(a.B, a.H, a.N, a.M, mode, &pl);
   if (rc != PCV_OK) return rc;
   size_t need = 0;
   attn_tc_workspace_bytes(a, &need);
@@ -983,7 +1310,8 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   p.q_bcast = (a.q_stride_b == 0) ? 1 : 0;
   p.out = a.out; p.osb = a.o_stride_b; p.osn = a.o_stride_n; p.osh = a.o_stride_h;
   p.write_partial = a.write_partial;
-  p.rows_per_unit = rows_per_unit;
+  p.rows_per_unit = mode.rows_per_unit;
+  p.slot_rows = mode.slot_rows;
   {
     static const int opt = [] { const char* e = getenv("PCV_OPT"); return e ? atoi(e) : 1; }();
     p.optimistic = opt;
@@ -999,12 +1327,12 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   }
   p.fin_o = a.part_o; p.fin_m = a.part_m; p.fin_l = a.part_l;
   char* ws = reinterpret_cast<char*>(a.workspace);
-  const size_t nrows = (size_t)pl->num_slots * kRowsPerUnit;
+  const size_t nrows = (size_t)pl->num_slots * mode.slot_rows;
   p.slot_o = reinterpret_cast<float*>(ws);
   p.slot_m = p.slot_o + nrows * DV;
   p.slot_l = p.slot_m + nrows;
   if (a.pad_mask != nullptr) {
-    size_t off = (slots_bytes(*pl, DV) + 255) / 256 * 256;
+    size_t off = (slots_bytes(*pl, DV, mode.slot_rows) + 255) / 256 * 256;
     uint32_t* bits = reinterpret_cast<uint32_t*>(ws + off);
     p.pad_wpr = (a.M + kTileN - 1) / kTileN * 4;
     p.pad_bits = bits;
@@ -1019,12 +1347,18 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   const int Bq = a.q_stride_b == 0 ? 1 : a.B;
   rc = make_tmap(&tq, a.q, a.dtype, a.dqk, a.N, a.H, Bq, a.q_stride_n, a.q_stride_h, a.q_stride_b);
   if (rc != PCV_OK) return rc;
-  rc = make_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b);
+  rc = make_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b,
+                 mode.pair ? kTileN / 2 : kTileN);  // the pair kernel loads 64-key halves of every K tile
   if (rc != PCV_OK) return rc;
   rc = make_tmap(&tv, a.v, a.dtype, a.dv, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
   if (rc != PCV_OK) return rc;
 
   const bool bf = a.dtype == PCV_BF16;
+  if (mode.pair) {
+    if (DQK == 128)
+      return bf ? launch_pair<128, true>(a, *pl, tq, tk, tv, p, stream) : launch_pair<128, false>(a, *pl, tq, tk, tv, p, stream);
+    return bf ? launch_pair<64, true>(a, *pl, tq, tk, tv, p, stream) : launch_pair<64, false>(a, *pl, tq, tk, tv, p, stream);
+  }
 #define PCV_TC_CASE(DQ, DVV)                                                                          \
   if (DQK == DQ && DV == DVV)                                                                         \
     return bf ? launch_cfg<DQ, DVV, true>(a, *pl, tq, tk, tv, p, stream)                              \

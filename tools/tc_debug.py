@@ -23,6 +23,11 @@ CASES = {
     "d32_160": (2, 64, 257, 8, 32, 160, 2, False, False, 1.0),
     "wide256": (1, 130, 300, 2, 128, 256, 1, False, False, 1.0),
     "wide_split": (1, 300, 4096, 2, 64, 192, 1, False, True, 1.0),
+    "pair_1tile": (1, 512, 128, 1, 128, 128, 1, False, False, 1.0),
+    "pair_kv4": (1, 512, 512, 1, 128, 128, 1, False, False, 1.0),
+    "pair_ragged": (2, 300, 700, 2, 128, 128, 2, False, False, 1.0),
+    "pair_mask": (3, 400, 900, 2, 128, 128, 1, True, True, 1.0),
+    "pair_d64": (2, 640, 1000, 2, 64, 128, 2, False, True, 2.0),
     "pad": (3, 40, 300, 2, 64, 64, 1, False, True, 1.0),
     "causal": (2, 100, 300, 2, 64, 64, 2, True, True, 1.0),
     "peaked": (1, 128, 4096, 2, 128, 128, 1, False, False, 6.0),
