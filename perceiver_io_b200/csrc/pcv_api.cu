@@ -56,7 +56,7 @@ static int validate_attn(const pcv_attn_params* p) {
   } else {
     PCV_REQUIRE(p->out != nullptr, PCV_ERR_INVALID, "attn: out pointer is NULL");
   }
-  PCV_REQUIRE(p->impl >= PCV_IMPL_AUTO && p->impl <= PCV_IMPL_SIMT, PCV_ERR_INVALID, "attn: unknown impl %d", p->impl);
+  PCV_REQUIRE(p->impl >= PCV_IMPL_AUTO && p->impl <= PCV_IMPL_TCGEN05_PAIR, PCV_ERR_INVALID, "attn: unknown impl %d", p->impl);
   return PCV_OK;
 }
 
@@ -145,7 +145,8 @@ int pcv_attn_workspace_bytes(const pcv_attn_params* p, size_t* bytes) {
   PCV_REQUIRE(bytes != nullptr, PCV_ERR_INVALID, "attn: bytes is NULL");
   const char* why = "";
   if (use_tc(*p, &why)) return attn_tc_workspace_bytes(*p, bytes);
-  PCV_REQUIRE(p->impl != PCV_IMPL_TCGEN05, PCV_ERR_UNSUPPORTED, "attn: tcgen05 kernel requested but %s", why);
+  PCV_REQUIRE(p->impl != PCV_IMPL_TCGEN05 && p->impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
+              "attn: tcgen05 kernel requested but %s", why);
   return attn_simt_workspace_bytes(*p, bytes);
 }
 
@@ -154,7 +155,8 @@ int pcv_attn_fwd(const pcv_attn_params* p, void* stream) {
   if (rc != PCV_OK) return rc;
   const char* why = "";
   if (use_tc(*p, &why)) return launch_attn_tc(*p, reinterpret_cast<cudaStream_t>(stream));
-  PCV_REQUIRE(p->impl != PCV_IMPL_TCGEN05, PCV_ERR_UNSUPPORTED, "attn: tcgen05 kernel requested but %s", why);
+  PCV_REQUIRE(p->impl != PCV_IMPL_TCGEN05 && p->impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
+              "attn: tcgen05 kernel requested but %s", why);
   return launch_attn_simt(*p, reinterpret_cast<cudaStream_t>(stream));
 }
 

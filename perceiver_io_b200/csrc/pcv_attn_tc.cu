@@ -1163,13 +1163,16 @@ size_t slots_bytes(const Plan& pl, int DV, int slot_rows) {
 }
 
 Mode choose_mode(const pcv_attn_params& a) {
-  static const int pair_env = [] { const char* e = getenv("PCV_PAIR"); return e ? atoi(e) : 1; }();
+  // The CTA-pair kernel is opt-in (impl = PCV_IMPL_TCGEN05_PAIR, or PCV_PAIR=1 in the environment): measured at
+  // the north-star shape it is currently slower than the single-CTA kernel (0.9 vs 1.2 PFLOP/s).
+  static const int pair_env = [] { const char* e = getenv("PCV_PAIR"); return e ? atoi(e) : 0; }();
+  const bool want_pair = pair_env || a.impl == PCV_IMPL_TCGEN05_PAIR;
   const int DV = pad64(a.dv);
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false};
-  if (pair_env && DV == 128 && a.N > kRowsPerUnit && sms >= 2 && (sms % 2) == 0)
+  if (want_pair && DV == 128 && a.N > kRowsPerUnit && sms >= 2 && (sms % 2) == 0)
     return Mode{4 * kTileM, 2 * kTileM, 4 * kTileM, true};
   return Mode{kRowsPerUnit, kTileM, kRowsPerUnit, false};
 }
@@ -1291,6 +1294,8 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   Plan* pl = nullptr;
   const int DQK = pad64(a.dqk), DV = pad64(a.dv);
   const Mode mode = choose_mode(a);
+  PCV_REQUIRE(mode.pair || a.impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
+              "tcgen05 pair kernel needs N > 256, dv <= 128 (padded to 128) and an even SM count");
   int rc = get_plan(a.B, a.H, a.N, a.M, mode, &pl);
   if (rc != PCV_OK) return rc;
   size_t need = 0;

@@ -187,3 +187,23 @@ def test_head_major_4d_operands_by_stride():
     out = ops.attention(q, k_hm.permute(0, 2, 1, 3), v_hm.permute(0, 2, 1, 3), H, d ** -0.5)
     assert_close(out, oracle_core(q, k, v, H, d ** -0.5), REL_TC, "head-major")
     assert torch.equal(out, ops.attention(q, k, v, H, d ** -0.5))
+
+
+@pytest.mark.parametrize("shape", [(2, 300, 700, 2, 128, 128), (1, 512, 2048, 4, 64, 128), (3, 400, 900, 2, 96, 96)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_cta_pair_kernel_matches_oracle(shape):
+    """cta_group::2 kernel (two SMs per 256-row MMA), incl. padding + causal masks and ragged N / M."""
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, dqk, dv = shape
+    q, k, v = _qkv(B, N, M, H, dqk, dv, Bq=1 if B == 3 else None, seed=17, q_gain=2.0)
+    pad = torch.zeros(B, M, dtype=torch.bool)
+    pad[0, : M // 5] = True
+    if B > 2:
+        pad[2, :] = True
+    for causal in (False, True):
+        out = ops.attention(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="tcgen05_pair")
+        assert_close(out, oracle_core(q, k, v, H, dqk ** -0.5, pad, causal), REL_TC, f"pair causal={causal}")
+    part = ops.attention_partial(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), impl="tcgen05_pair")
+    merged = ops.combine_partials(part[0][None], part[1][None], part[2][None])
+    assert_close(merged, oracle_core(q, k, v, H, dqk ** -0.5, pad, False), REL_TC, "pair partial state")
