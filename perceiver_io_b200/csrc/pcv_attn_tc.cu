@@ -140,7 +140,7 @@ struct TileCtx;
 __device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c);
 
 struct TileCtx {
-  uint32_t p_full_pair;  // 0: arrive locally (count 128); else shared::cluster address of the pair leader's p_full[wg] (one arrive per warp)
+  uint32_t p_full_pair;  // 0: arrive on the local p_full[wg]; else shared::cluster address of the pair leader's p_full[wg]
   uint32_t tS, tO;    // TMEM addresses (lane field included) of this thread's S / O row
   int wg, row;
   int j0;             // first key of the tile
@@ -153,11 +153,14 @@ struct TileCtx {
 
 // P of this thread's row is in TMEM (tcgen05.wait::st + fence done by the caller): tell the MMA issuer
 __device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c) {
-  if (c.p_full_pair == 0) {
-    mbar_arrive(&bar.p_full[c.wg]);
-  } else {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(c.p_full_pair);
+  // one arrive per warp (every lane has executed tcgen05.wait::st + the tcgen05 fence before the warp sync):
+  // 4 arrivals per tile instead of 128 serialised updates of one shared-memory word
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    if (c.p_full_pair == 0)
+      mbar_arrive(&bar.p_full[c.wg]);
+    else
+      mbar_arrive_cluster(c.p_full_pair);
   }
 }
 
@@ -440,11 +443,12 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       }
     }
     tc_fence_before_sync();
-    if (!pair) {
-      mbar_arrive(&bar.o_empty[wg]);
-    } else {
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(o_empty_pair);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      if (!pair)
+        mbar_arrive(&bar.o_empty[wg]);
+      else
+        mbar_arrive_cluster(o_empty_pair);
     }
   }
 }
@@ -477,9 +481,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar.s_full[i], 1);
-      mbar_init(&bar.p_full[i], kTileM);
+      mbar_init(&bar.p_full[i], 4);   // one arrive per softmax warp
       mbar_init(&bar.o_full[i], 1);
-      mbar_init(&bar.o_empty[i], kTileM);
+      mbar_init(&bar.o_empty[i], 4);
     }
     fence_mbar_init();
   }
@@ -642,10 +646,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           PCV_TRACE(p, 2, j, 4, leader && sg == seg_lo);
           issue_pv(1, v_slot, j > 0);
         }
+        PCV_TRACE(p, 2, j, 6, leader && sg == seg_lo);
         commit(&bar.kv_empty[v_slot]);
         if (more) {
           if (two) {
             issue_qk(1, k_slot);
+            PCV_TRACE(p, 2, j, 7, leader && sg == seg_lo);
             commit(&bar.s_full[1]);
           }
           commit(&bar.kv_empty[k_slot]);

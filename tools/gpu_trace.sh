@@ -1,0 +1,4 @@
+#!/bin/bash
+# builds the tracing variant of the library on the GPU box and prints in-kernel timelines
+make -C perceiver_io_b200/csrc clean >/dev/null; make -C perceiver_io_b200/csrc -j8 TRACE=1 2>&1 | grep -E "error" 
+for d in ${DBGS:-0 1}; do echo "== PCV_DBG=$d"; PCV_DBG=$d PCV_TRACE=1 timeout 200 python tools/tc_trace.py 2>&1 | tail -${TAILN:-6}; done

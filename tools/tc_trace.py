@@ -40,4 +40,6 @@ for r, name in enumerate(("WG0", "WG1")):
     print(name, "avg phase durations [ld, max, turnwait, exp, st+arrive]:", [sum(s[i] for s in seg) / len(seg) for i in range(5)],
           "wait for next S:", sum(a[r][t + 1][0] - a[r][t][5] for t in range(10, 40)) / 30)
 seg = [[a[2][t][e + 1] - a[2][t][e] for e in range(5)] for t in range(10, 40)]
+m=a[2]
+print("MMA fine: [p1_ok->pv1 issued, commit kv_empty(V), qk1 issue, commit s_full1 + kv_empty(K)]:", [sum(x)/30 for x in zip(*[[m[t][6]-m[t][4], 0, m[t][7]-m[t][6], m[t][5]-m[t][7]] for t in range(10,40)])])
 print("MMA avg [wait p0, issue pv0, (wait K)+issue qk0, wait p1, issue pv1+qk1]:", [sum(s[i] for s in seg) / len(seg) for i in range(5)])
