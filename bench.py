@@ -51,7 +51,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock, power and throttle reasons sampled DURING the timed region.
+
+    The timed region is ~20 ms (20 steps of ~1 ms), far shorter than nvidia-smi's loop period, so NVML is
+    polled directly from a thread every ~1 ms; `nvidia-smi -lms` is only the fallback when pynvml is missing."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -59,12 +62,54 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _poll_nvml(self):
+        n, h = self.nvml
+        reasons = {
+            "hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+            "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:  # noqa: BLE001
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in reasons.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.001)
 
     def __enter__(self):
         try:
+            import pynvml as n
+
+            n.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            h = n.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            self.nvml = (n, h)
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -76,6 +121,9 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        self._stop.set()
+        if self.nvml is not None and self.thread is not None:
+            self.thread.join(timeout=1)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -84,6 +132,11 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        if self.nvml is not None and self.samples:
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml, 1 ms polling inside the timed region"}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -100,7 +153,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -112,7 +166,8 @@ def cpu_cross_attention_sample(steps: int, warmup: int, min_seconds: float = 0.0
     from oracle import mha_oracle as O
 
     w = WORKLOAD
-    torch.set_num_threads(os.cpu_count() or 1)
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
     g = torch.Generator().manual_seed(0)
     d = w["d"]
     weights = {}
@@ -125,6 +180,17 @@ def cpu_cross_attention_sample(steps: int, warmup: int, min_seconds: float = 0.0
     x_kv = torch.randn(1, w["M"], d, generator=g)
     times = []
     with torch.no_grad():
+        # give the reference its best thread count on this host (all cores is not always fastest for torch CPU)
+        best = (None, float("inf"))
+        for nt in sorted({ncpu, max(1, ncpu // 2), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
+            torch.set_num_threads(nt)
+            O.cross_attention(weights, x_q, x_kv, w["H"])
+            t0 = time.perf_counter()
+            O.cross_attention(weights, x_q, x_kv, w["H"])
+            dt = time.perf_counter() - t0
+            if dt < best[1]:
+                best = (nt, dt)
+        torch.set_num_threads(best[0])
         for _ in range(warmup):
             O.cross_attention(weights, x_q, x_kv, w["H"])
         t_all = time.perf_counter()
@@ -142,7 +208,7 @@ def cpu_cross_attention_sample(steps: int, warmup: int, min_seconds: float = 0.0
         tflops=flops / mean_s / 1e12, seconds=mean_s, steps=len(times), cores=torch.get_num_threads(),
         sample=(f"1 of {w['B']} batch rows of the workload (B=1, M={w['M']}, N={w['N']}, d={d}, H={w['H']}), fp32, "
                 f"oracle port of CrossAttention.forward (LayerNorm + q/k/v/o projections + attention), "
-                f"{len(times)} timed passes"),
+                f"{len(times)} timed passes, fastest of several torch thread counts on {ncpu} host cores"),
     )
 
 
