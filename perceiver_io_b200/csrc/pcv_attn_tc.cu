@@ -1119,6 +1119,7 @@ int get_plan(int B, int H, int N, int M, const Mode& mode, Plan** out) {
     PCV_CHECK_CUDA(cudaMemcpy(pl->d_units, pl->units.data(), sizeof(UnitRec) * pl->units.size(), cudaMemcpyHostToDevice));
   }
   if (g_plans.size() > 256) {  // bounded cache: drop everything (plans are cheap to rebuild)
+    cudaDeviceSynchronize();   // kernels in flight may still read the tables about to be freed
     for (auto& kv : g_plans) {
       cudaFree(kv.second->d_segs);
       cudaFree(kv.second->d_cta);
@@ -1188,10 +1189,12 @@ int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, 
                const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
   using C = Cfg<DQK, DV>;
   auto kern = attn_tc_kernel<DQK, DV, BF16>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per instantiation and device
+  int dev = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   prof_mark_begin(stream);
   kern<<<pl.num_ctas, kThreads, C::kSmemBytes, stream>>>(tq, tk, tv, p);
@@ -1212,10 +1215,12 @@ int launch_pair(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq,
                 const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
   using C = PairCfg<DQK>;
   auto kern = attn_tc_pair_kernel<DQK, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pl.num_ctas);  // num_ctas counts CTA pairs in this mode
