@@ -77,6 +77,7 @@ struct TcParams {
   int rows_per_unit;                // query rows per work unit: 256 (two tiles per CTA), 128 (wide-dv), 512 (CTA pair)
   int slot_rows;                    // row stride of the partial slots (>= rows_per_unit)
   int dbg;                          // developer experiments (PCV_DBG): 1 = softmax skips its math, 2 = no PV MMAs, 4 = no QK MMAs
+  int poly;                         // 1: every 4th column pair uses the FMA-pipe exp2 (optimistic tiles only)
   int optimistic;                   // 1: exponentiate against the current reference, verify the max afterwards
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
 };
@@ -267,7 +268,7 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
 // turns out to exceed the reference by more than the rescale threshold, nothing has been stored yet: the warp
 // returns false and the caller redoes the tile on the classic path (max first).  After the first few tiles of
 // a row the reference hardly ever moves, so the redo is rare.
-template <int DV, bool BF16>
+template <int DV, bool BF16, int POLY4>
 __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barriers& bar, const TileCtx& c,
                                                         RowState& st) {
   uint32_t pk_lo[32], pk_hi[32];  // packed P for key columns [0,64) / [64,128)
@@ -291,7 +292,8 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
       mx0 = fmaxf(mx0, s0);                                                                       \
       mx1 = fmaxf(mx1, s1);                                                                       \
       const float2 x = fma2(make_float2(s0, s1), mul2, negm2);                                    \
-      const float2 e = make_float2(ex2(x.x), ex2(x.y));                                           \
+      /* POLY4 of every 4 column pairs go through the FMA-pipe exp2 (compile-time pattern) */     \
+      const float2 e = (((i >> 1) & 3) < POLY4) ? exp2_poly2(x) : make_float2(ex2(x.x), ex2(x.y)); \
       sum2 = add2(sum2, e);                                                                       \
       dst[(off) + (i >> 1)] = pack2(e.x, e.y, BF16);                                              \
     }                                                                                             \
@@ -367,7 +369,9 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       if (masked_tile) {
         softmax_tile<DV, BF16, true>(p, bar, c, st);
       } else if (p.optimistic && !c.first_tile) {
-        if (!softmax_tile_optimistic<DV, BF16>(p, bar, c, st)) {
+        const bool ok = p.poly ? softmax_tile_optimistic<DV, BF16, 1>(p, bar, c, st)
+                               : softmax_tile_optimistic<DV, BF16, 0>(p, bar, c, st);
+        if (!ok) {
           // the reference must move: nothing was stored, redo on the classic path (max first)
           softmax_tile<DV, BF16, false>(p, bar, c, st);
         }
@@ -1331,6 +1335,8 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   {
     static const int opt = [] { const char* e = getenv("PCV_OPT"); return e ? atoi(e) : 1; }();
     p.optimistic = opt;
+    static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 0; }();
+    p.poly = poly;
     static const int dbg = [] { const char* e = getenv("PCV_DBG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
     static const int trace = [] { const char* e = getenv("PCV_TRACE"); return e ? atoi(e) : 0; }();

@@ -310,6 +310,35 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   return d;
 }
 
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+// 2^x for two lanes on the FMA/ALU pipes instead of the MUFU pipe (x <= ~100): round-to-nearest split
+// x = n + f, |f| <= 0.5 (adding 1.5*2^23 leaves n in the low mantissa bits), cubic Remez fit of 2^f (relative
+// error 7.5e-5, far below the bf16 rounding of P), then n is added to the exponent field.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 xr = add2(x, magic);
+  const float2 xi = sub2(xr, magic);
+  const float2 xf = sub2(x, xi);
+  float2 pf = fma2(xf, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  pf = fma2(pf, xf, make_float2(0.6932609677f, 0.6932609677f));
+  pf = fma2(pf, xf, make_float2(0.9999280572f, 0.9999280572f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pf.x) + (__float_as_int(xr.x) << 23));
+  r.y = __int_as_float(__float_as_int(pf.y) + (__float_as_int(xr.y) << 23));
+  return r;
+}
+
 // plain 2-input max the compiler cannot re-fuse into FMNMX3
 __device__ __forceinline__ float max2(float a, float b) {
   float d;

@@ -1,0 +1,92 @@
+"""-m gpu: parity at BASELINE.json's FULL north-star size (B=8, M=65536, N=512, d=1024, H=8), where the CPU
+oracle is too slow, through size-independent properties of softmax attention plus an oracle spot check of a
+few (batch, head) slices."""
+import pytest
+import torch
+
+from gpu_util import assert_close, oracle_core
+
+pytestmark = pytest.mark.gpu
+
+B, M, N, D, H = 8, 65536, 512, 1024, 8
+DH = D // H
+SCALE = DH ** -0.5
+
+
+@pytest.fixture(scope="module")
+def qkv():
+    g = torch.Generator(device="cuda").manual_seed(123)
+    q = (torch.randn(B, N, D, device="cuda", generator=g) * 1.5).bfloat16()
+    k = torch.randn(B, M, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, M, D, device="cuda", generator=g).bfloat16()
+    return q, k, v
+
+
+def test_zero_queries_give_the_mean_of_all_values(qkv):
+    """q = 0 -> uniform softmax over 65536 keys -> output = mean(V): closed form at full size (stresses the
+    65k-term denominator and the split-M merge)."""
+    from perceiver_io_b200 import ops
+
+    _, k, v = qkv
+    out = ops.attention(torch.zeros(B, N, D, device="cuda", dtype=torch.bfloat16), k, v, H, SCALE)
+    mean_v = v.float().mean(dim=1, keepdim=True).expand(B, N, D)
+    assert_close(out, mean_v, 2e-2, "uniform softmax")   # |mean| ~ 1/sqrt(M): bf16 output rounding dominates
+
+
+def test_key_shards_merge_to_the_full_result(qkv):
+    """softmax over M decomposes exactly: 3 uneven key shards -> partial states -> pcv_attn_combine == one pass."""
+    from perceiver_io_b200 import ops
+
+    q, k, v = qkv
+    full = ops.attention(q, k, v, H, SCALE)
+    cuts = [0, 20000 // 128 * 128, 50048, M]
+    parts = [ops.attention_partial(q, k[:, a:b], v[:, a:b], H, SCALE, m_total=M, m_offset=a) for a, b in zip(cuts[:-1], cuts[1:])]
+    merged = ops.combine_partials(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]),
+                                  torch.stack([p[2] for p in parts]))
+    assert_close(merged, full.double(), 8e-3, "3 shards vs 1 pass")
+
+
+def test_linear_in_the_values(qkv):
+    """attn(q, k, a*v1 + b*v2) == a*attn(q,k,v1) + b*attn(q,k,v2) (the softmax weights do not depend on V)."""
+    from perceiver_io_b200 import ops
+
+    q, k, v = qkv
+    v2 = torch.roll(v, shifts=7, dims=1)
+    lhs = ops.attention(q, k, (0.5 * v.float() + 0.25 * v2.float()).bfloat16(), H, SCALE)
+    rhs = 0.5 * ops.attention(q, k, v, H, SCALE).float() + 0.25 * ops.attention(q, k, v2, H, SCALE).float()
+    assert_close(lhs, rhs, 2.5e-2, "linearity in V")
+
+
+def test_key_permutation_invariance(qkv):
+    from perceiver_io_b200 import ops
+
+    q, k, v = qkv
+    perm = torch.randperm(M, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    a = ops.attention(q, k, v, H, SCALE)
+    b = ops.attention(q, k[:, perm], v[:, perm], H, SCALE)
+    assert_close(b, a.double(), 8e-3, "key permutation")
+
+
+def test_padding_everything_but_a_window_equals_attention_on_the_window(qkv):
+    """pad mask that leaves only keys [30000, 30512) visible == attention over that 512-key slice."""
+    from perceiver_io_b200 import ops
+
+    q, k, v = qkv
+    pad = torch.ones(B, M, dtype=torch.bool, device="cuda")
+    pad[:, 30000:30512] = False
+    a = ops.attention(q, k, v, H, SCALE, pad_mask=pad)
+    b = ops.attention(q, k[:, 30000:30512], v[:, 30000:30512], H, SCALE)
+    assert_close(a, b.double(), 8e-3, "window")
+
+
+def test_oracle_spot_check_of_two_slices(qkv):
+    """fp64 oracle on (b=0,h=0) and (b=7,h=5) with the first 8192 keys of the full-size tensors (strided views:
+    exercises the same TMA descriptors as the full run)."""
+    from perceiver_io_b200 import ops
+
+    q, k, v = qkv
+    for b, h in ((0, 0), (7, 5)):
+        sl = slice(h * DH, (h + 1) * DH)
+        qs, ks, vs = q[b:b + 1, :, sl], k[b:b + 1, :8192, sl], v[b:b + 1, :8192, sl]
+        out = ops.attention(qs, ks, vs, 1, SCALE)
+        assert_close(out, oracle_core(qs, ks, vs, 1, SCALE), 1.2e-2, f"slice {(b, h)}")
