@@ -64,6 +64,9 @@ struct TcParams {
   const Segment* segs;
   const int* cta_seg_begin;
   int B, H, N, M, dv;
+  int dv_off, dv_pass;              // this launch writes output channels [dv_off, dv_off + dv_pass)
+  int nc;                           // big-head kernel: number of 128-channel chunks of the qk head dim
+  int v_boxes;                      // big-head kernel: 64-channel boxes of V in this pass (PV MMA N = 64 * v_boxes)
   float scale_log2;
   int causal, causal_shift;  // key j (local) masked for query n iff j > n + causal_shift
   const uint32_t* pad_bits;  // (B, pad_wpr) bit set = padding key; nullptr if no mask
@@ -142,6 +145,8 @@ __device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c);
 
 struct TileCtx {
   uint32_t p_full_pair;  // 0: arrive on the local p_full[wg]; else shared::cluster address of the pair leader's p_full[wg]
+  uint64_t* pv_bar;      // non-null: barrier (and parity) to wait on before rescaling O — kernels whose S(j) does not imply PV(j-1) done
+  uint32_t pv_parity;
   uint32_t tS, tO;    // TMEM addresses (lane field included) of this thread's S / O row
   int wg, row;
   int j0;             // first key of the tile
@@ -223,6 +228,10 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
     moved = !c.first_tile;
   }
   if (__any_sync(0xffffffffu, moved)) {
+    if (c.pv_bar != nullptr) {
+      mbar_wait(c.pv_bar, c.pv_parity, 15);
+      tc_fence_after_sync();
+    }
 #pragma unroll
     for (int ch = 0; ch < DV / 32; ++ch) {
       uint32_t o[32];
@@ -317,6 +326,75 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
   return true;
 }
 
+// O row of this thread (TMEM, `DV` accumulator columns starting at tO) -> global memory: the normalised output,
+// the caller's partial state, or a split-M slot.  Channels [0, dv_pass) of the accumulator map to output channels
+// [dv_off, dv_off + dv_pass) (dv_off > 0 only in the second pass of the big-head kernel).
+template <int DV, bool BF16>
+__device__ __forceinline__ void epilogue_row(const TcParams& p, const Segment& seg, uint32_t tO, int n,
+                                             int row_in_unit, float l, float m_ref) {
+  const bool valid = n < p.N;
+  if (seg.slot < 0 && !p.write_partial) {
+    const float inv = 1.f / l;
+    char* orow = reinterpret_cast<char*>(p.out) +
+                 2 * ((int64_t)seg.b * p.osb + (int64_t)n * p.osn + (int64_t)seg.h * p.osh);
+#pragma unroll
+    for (int ch = 0; ch < DV / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(tO + ch * 32, o);
+      tmem_wait_ld();
+      if (valid) {
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const int col = ch * 32 + c8 * 8;
+          if (col < p.dv) {
+            uint4 w;
+            w.x = pack2(__uint_as_float(o[c8 * 8 + 0]) * inv, __uint_as_float(o[c8 * 8 + 1]) * inv, BF16);
+            w.y = pack2(__uint_as_float(o[c8 * 8 + 2]) * inv, __uint_as_float(o[c8 * 8 + 3]) * inv, BF16);
+            w.z = pack2(__uint_as_float(o[c8 * 8 + 4]) * inv, __uint_as_float(o[c8 * 8 + 5]) * inv, BF16);
+            w.w = pack2(__uint_as_float(o[c8 * 8 + 6]) * inv, __uint_as_float(o[c8 * 8 + 7]) * inv, BF16);
+            *reinterpret_cast<uint4*>(orow + 2 * (p.dv_off + col)) = w;
+          }
+        }
+      }
+    }
+  } else {
+    float* dst;
+    int ncols;
+    bool store;
+    if (seg.slot < 0) {  // whole key range, caller wants the un-normalised state
+      const int64_t r = ((int64_t)seg.b * p.H + seg.h) * p.N + n;
+      dst = p.fin_o + r * p.dv + p.dv_off;
+      ncols = p.dv_pass;
+      store = valid;
+      if (valid) {
+        p.fin_m[r] = m_ref;
+        p.fin_l[r] = l;
+      }
+    } else {
+      const int64_t r = (int64_t)seg.slot * p.slot_rows + row_in_unit;
+      dst = p.slot_o + r * DV;
+      ncols = DV;
+      store = true;
+      p.slot_m[r] = m_ref;
+      p.slot_l[r] = l;
+    }
+#pragma unroll
+    for (int ch = 0; ch < DV / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(tO + ch * 32, o);
+      tmem_wait_ld();
+      if (store) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const int col = ch * 32 + c4 * 4;
+          if (col < ncols)
+            *reinterpret_cast<uint4*>(dst + col) = make_uint4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
+        }
+      }
+    }
+  }
+}
+
 template <int DQK, int DV, bool BF16>
 __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, int wg, int row, int seg_lo,
                                              int seg_hi, int pair_rank = -1) {
@@ -342,6 +420,8 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     TileCtx c;
     c.tS = tS; c.tO = tO; c.wg = wg; c.row = row;
     c.p_full_pair = p_full_pair;
+    c.pv_bar = nullptr;
+    c.pv_parity = 0;
     c.cshift = n + p.causal_shift;
     c.trace_on = (row == 0 && sg == seg_lo);
 
@@ -385,67 +465,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     mbar_wait(&bar.o_full[wg], n_o & 1, 13);
     ++n_o;
     tc_fence_after_sync();
-    const bool valid = n < p.N;
-    if (seg.slot < 0 && !p.write_partial) {
-      const float inv = 1.f / l;
-      char* orow = reinterpret_cast<char*>(p.out) +
-                   2 * ((int64_t)seg.b * p.osb + (int64_t)n * p.osn + (int64_t)seg.h * p.osh);
-#pragma unroll
-      for (int ch = 0; ch < DV / 32; ++ch) {
-        uint32_t o[32];
-        tmem_ld32(tO + ch * 32, o);
-        tmem_wait_ld();
-        if (valid) {
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const int col = ch * 32 + c8 * 8;
-            if (col < p.dv) {
-              uint4 w;
-              w.x = pack2(__uint_as_float(o[c8 * 8 + 0]) * inv, __uint_as_float(o[c8 * 8 + 1]) * inv, BF16);
-              w.y = pack2(__uint_as_float(o[c8 * 8 + 2]) * inv, __uint_as_float(o[c8 * 8 + 3]) * inv, BF16);
-              w.z = pack2(__uint_as_float(o[c8 * 8 + 4]) * inv, __uint_as_float(o[c8 * 8 + 5]) * inv, BF16);
-              w.w = pack2(__uint_as_float(o[c8 * 8 + 6]) * inv, __uint_as_float(o[c8 * 8 + 7]) * inv, BF16);
-              *reinterpret_cast<uint4*>(orow + 2 * col) = w;
-            }
-          }
-        }
-      }
-    } else {
-      float* dst;
-      int ncols;
-      bool store;
-      if (seg.slot < 0) {  // whole key range, caller wants the un-normalised state
-        const int64_t r = ((int64_t)seg.b * p.H + seg.h) * p.N + n;
-        dst = p.fin_o + r * p.dv;
-        ncols = p.dv;
-        store = valid;
-        if (valid) {
-          p.fin_m[r] = m_ref;
-          p.fin_l[r] = l;
-        }
-      } else {
-        const int64_t r = (int64_t)seg.slot * p.slot_rows + row_in_unit;
-        dst = p.slot_o + r * DV;
-        ncols = DV;
-        store = true;
-        p.slot_m[r] = m_ref;
-        p.slot_l[r] = l;
-      }
-#pragma unroll
-      for (int ch = 0; ch < DV / 32; ++ch) {
-        uint32_t o[32];
-        tmem_ld32(tO + ch * 32, o);
-        tmem_wait_ld();
-        if (store) {
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const int col = ch * 32 + c4 * 4;
-            if (col < ncols)
-              *reinterpret_cast<uint4*>(dst + col) = make_uint4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
-          }
-        }
-      }
-    }
+    epilogue_row<DV, BF16>(p, seg, tO, n, row_in_unit, l, m_ref);
     tc_fence_before_sync();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
@@ -918,6 +938,227 @@ attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// Big-head kernel: qk head dims up to 512 and v head dims up to 256 per pass (the optical-flow encoder /
+// decoder geometry, 322 and 512 channels per head).  One query tile (128 rows) per CTA.  Q and K stream through
+// shared memory in 128-channel chunks (Q is re-streamed from L2 for every key tile) and S accumulates over the
+// chunks in TMEM; S is double-buffered (columns [0,128) / [128,256)) so Q K^T of tile j+1 overlaps the softmax
+// of tile j; O occupies columns [256, 256 + 64*v_boxes).  A v head dim above 256 is covered by launching the
+// kernel once per 256-channel slice of V (the scores are recomputed).  256 threads: warps 0-3 softmax (one
+// thread per row), warp 4 MMA issuer, warp 5 TMA producer.
+// --------------------------------------------------------------------------------------------------
+constexpr int kBigThreads = 256;
+constexpr int kBigItems = 3;
+constexpr int kBigItemBytes = 4 * kBoxBytes;  // 64 KB: [Q chunk 32 KB | K chunk 32 KB] or a V tile of <= 256 channels
+constexpr int kBigSmemBytes = kBigItems * kBigItemBytes + 1024 + 1024;
+
+struct BigBarriers {
+  uint64_t item_full[kBigItems], item_empty[kBigItems];
+  uint64_t s_full, p_full, pv_done, o_full, o_empty;
+  uint32_t tmem_base;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(kBigThreads, 1)
+attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  BigBarriers& bb = *reinterpret_cast<BigBarriers*>(smem + kBigItems * kBigItemBytes);
+  // the shared softmax helpers address barriers through the common struct; alias the fields they touch
+  Barriers& bar = *reinterpret_cast<Barriers*>(smem + kBigItems * kBigItemBytes + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seg_lo = p.cta_seg_begin[blockIdx.x];
+  const int seg_hi = p.cta_seg_begin[blockIdx.x + 1];
+  constexpr int kMma = 4, kTma = 5;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBigItems; ++i) {
+      mbar_init(&bb.item_full[i], 1);
+      mbar_init(&bb.item_empty[i], 1);
+    }
+    mbar_init(&bb.s_full, 1);
+    mbar_init(&bar.p_full[0], 4);  // arrive_p_full() targets bar.p_full[wg = 0]
+    mbar_init(&bb.pv_done, 1);
+    mbar_init(&bb.o_full, 1);
+    mbar_init(&bb.o_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == kMma) {
+    tmem_alloc(&bb.tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == kTma && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bb.tmem_base;
+
+  if (warp < 4) {
+    // ===== softmax + epilogue: thread = query row =====
+    const int row = threadIdx.x;
+    const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
+    const uint32_t tO = tmem + lane_field + 256u;
+    uint32_t n_s = 0, n_o = 0, n_pv = 0;
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const int n = seg.q0 + row;
+      RowState st;
+      st.m_ref = -INFINITY;
+      st.l = 0.f;
+      TileCtx c;
+      c.tO = tO; c.wg = 0; c.row = row;
+      c.p_full_pair = 0;
+      c.pv_bar = &bb.pv_done;
+      c.cshift = n + p.causal_shift;
+      c.trace_on = false;
+      for (int t = seg.t0; t < seg.t1; ++t) {
+        const int j = t - seg.t0;
+        c.tS = tmem + lane_field + (uint32_t)((j & 1) * 128);
+        c.j0 = t * kTileN;
+        c.tt = j;
+        c.first_tile = (j == 0);
+        c.pv_parity = (n_pv + 1) & 1;  // phase of PV(j-1): n_pv counts the PVs of earlier tiles (all segments)
+        c.mw = make_uint4(0, 0, 0, 0);
+        if (p.pad_bits != nullptr)
+          c.mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
+        const bool masked_tile =
+            __any_sync(0xffffffffu, (c.j0 + kTileN > p.M) || ((c.mw.x | c.mw.y | c.mw.z | c.mw.w) != 0u) ||
+                                        (p.causal && (c.j0 + kTileN - 1 > c.cshift)));
+        mbar_wait(&bb.s_full, n_s & 1, 12);
+        ++n_s;
+        tc_fence_after_sync();
+        if (masked_tile) {
+          softmax_tile<256, BF16, true>(p, bar, c, st);
+        } else if (p.optimistic && !c.first_tile) {
+          if (!softmax_tile_optimistic<256, BF16, 0>(p, bar, c, st)) softmax_tile<256, BF16, false>(p, bar, c, st);
+        } else {
+          softmax_tile<256, BF16, false>(p, bar, c, st);
+        }
+        ++n_pv;
+      }
+      mbar_wait(&bb.o_full, n_o & 1, 13);
+      ++n_o;
+      tc_fence_after_sync();
+      epilogue_row<256, BF16>(p, seg, tO, n, row, st.l, st.m_ref);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bb.o_empty);
+    }
+  } else if (warp == kTma) {
+    // ===== TMA producer; item order = consumption order: QK(0), QK(1), V(0), QK(2), V(1), ... =====
+    const bool leader = elect_one();
+    uint32_t it = 0;
+    auto load_qk = [&](const Segment& seg, int t) {
+      const int bq = p.q_bcast ? 0 : seg.b;
+      for (int ch = 0; ch < p.nc; ++ch) {
+        const uint32_t slot = it % kBigItems, par = (it / kBigItems) & 1;
+        mbar_wait(&bb.item_empty[slot], par ^ 1, 2);
+        if (leader) {
+          uint8_t* base = smem + slot * kBigItemBytes;
+          mbar_arrive_expect_tx(&bb.item_full[slot], (uint32_t)kBigItemBytes);
+          tma_load_4d(base, &tmap_q, &bb.item_full[slot], ch * 128, seg.q0, seg.h, bq);
+          tma_load_4d(base + kBoxBytes, &tmap_q, &bb.item_full[slot], ch * 128 + 64, seg.q0, seg.h, bq);
+          tma_load_4d(base + 2 * kBoxBytes, &tmap_k, &bb.item_full[slot], ch * 128, t * kTileN, seg.h, seg.b);
+          tma_load_4d(base + 3 * kBoxBytes, &tmap_k, &bb.item_full[slot], ch * 128 + 64, t * kTileN, seg.h, seg.b);
+        }
+        ++it;
+      }
+    };
+    auto load_v = [&](const Segment& seg, int t) {
+      const uint32_t slot = it % kBigItems, par = (it / kBigItems) & 1;
+      mbar_wait(&bb.item_empty[slot], par ^ 1, 3);
+      if (leader) {
+        uint8_t* base = smem + slot * kBigItemBytes;
+        mbar_arrive_expect_tx(&bb.item_full[slot], (uint32_t)(p.v_boxes * kBoxBytes));
+        for (int bx = 0; bx < p.v_boxes; ++bx)
+          tma_load_4d(base + bx * kBoxBytes, &tmap_v, &bb.item_full[slot], bx * 64, t * kTileN, seg.h, seg.b);
+      }
+      ++it;
+    };
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      load_qk(seg, seg.t0);
+      for (int t = seg.t0; t < seg.t1; ++t) {
+        if (t + 1 < seg.t1) load_qk(seg, t + 1);
+        load_v(seg, t);
+      }
+    }
+  } else if (warp == kMma) {
+    // ===== MMA issuer =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_qk = make_idesc(kTileM, kTileN, BF16, false);
+    const uint32_t idesc_pv = make_idesc(kTileM, 64 * p.v_boxes, BF16, true);
+    const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);          // K-major operands (Q / K chunks)
+    const uint64_t dv0 = make_smem_desc(smem_u32(smem), kBoxBytes, 1024);  // MN-major V tile
+    uint32_t it = 0, n_p = 0, n_oe = 0;
+    auto commit = [&](uint64_t* b) {
+      if (leader) tc_commit(b);
+    };
+    auto issue_qk = [&](int j) {  // S[j & 1] = Q K_j^T, accumulated over the channel chunks
+      for (int ch = 0; ch < p.nc; ++ch) {
+        const uint32_t slot = it % kBigItems;
+        mbar_wait(&bb.item_full[slot], (it / kBigItems) & 1, 5);
+        ++it;
+        tc_fence_after_sync();
+        if (leader && !(p.dbg & 4)) {
+          const uint64_t da = d0 + (uint64_t)((slot * kBigItemBytes) >> 4);
+          const uint64_t db = da + (uint64_t)((2 * kBoxBytes) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+            mma_ss(tmem + (j & 1) * 128, da + off, db + off, idesc_qk, (ch > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        commit(&bb.item_empty[slot]);
+      }
+      commit(&bb.s_full);
+    };
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const int nt = seg.t1 - seg.t0;
+      issue_qk(0);
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) issue_qk(j + 1);
+        const uint32_t slot = it % kBigItems;
+        mbar_wait(&bb.item_full[slot], (it / kBigItems) & 1, 6);
+        ++it;
+        if (j == 0) {
+          mbar_wait(&bb.o_empty, (n_oe & 1) ^ 1, 7);
+          ++n_oe;
+        }
+        mbar_wait(&bar.p_full[0], n_p & 1, 8);
+        ++n_p;
+        tc_fence_after_sync();
+        if (leader && !(p.dbg & 2)) {
+          const uint64_t db = dv0 + (uint64_t)((slot * kBigItemBytes) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < kTileN / 16; ++kk)
+            mma_ts(tmem + 256, tmem + (j & 1) * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+                   (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        commit(&bb.item_empty[slot]);
+        commit(&bb.pv_done);
+      }
+      commit(&bb.o_full);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMma) {
+    tc_fence_after_sync();
+    tmem_dealloc(bb.tmem_base, 512);
+  }
+}
+
 // --------------------------------------------------------------------------------------------------
 // merge of split units (one warp per query row)
 // --------------------------------------------------------------------------------------------------
@@ -946,17 +1187,17 @@ __global__ void __launch_bounds__(256) tc_combine_kernel(const UnitRec* __restri
       acc.z = fmaf(x.z, w, acc.z);
       acc.w = fmaf(x.w, w, acc.w);
     }
-    if (c >= p.dv) continue;
+    if (c >= p.dv_pass) continue;
     if (!p.write_partial) {
       const float inv = 1.f / l;
       uint2 w2;
       w2.x = pack2(acc.x * inv, acc.y * inv, BF16);
       w2.y = pack2(acc.z * inv, acc.w * inv, BF16);
       char* orow = reinterpret_cast<char*>(p.out) + 2 * ((int64_t)u.b * p.osb + (int64_t)n * p.osn + (int64_t)u.h * p.osh);
-      *reinterpret_cast<uint2*>(orow + 2 * c) = w2;
+      *reinterpret_cast<uint2*>(orow + 2 * (p.dv_off + c)) = w2;
     } else {
       const int64_t r = ((int64_t)u.b * p.H + u.h) * p.N + n;
-      *reinterpret_cast<float4*>(p.fin_o + r * p.dv + c) = acc;
+      *reinterpret_cast<float4*>(p.fin_o + r * p.dv + p.dv_off + c) = acc;
     }
   }
   if (p.write_partial && lane == 0) {
@@ -1002,7 +1243,7 @@ void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms, int rows_per_
   const int BH = B * H;
   auto ntile_of = [&](int qb) { return (rows_per_unit > rows_per_tile && (N - qb * rows_per_unit) > rows_per_tile) ? 2 : 1; };
   std::vector<std::vector<Segment>> per_cta;
-  const bool split_mode = QB <= 8 && QB <= num_sms;
+  const bool split_mode = QB * 2 <= num_sms;  // groups of QB workers share their K/V stream; else whole units per worker
   if (split_mode) {
     // groups of QB CTAs walk the flattened (b*h, key tile) space together, one query block each, so that
     // the members of a group stream the same K/V tiles at the same time (they meet in L2)
@@ -1092,6 +1333,7 @@ std::map<std::tuple<int, int, int, int, int, int, int, int>, Plan*> g_plans;  //
 struct Mode {
   int rows_per_unit, rows_per_tile, slot_rows;
   bool pair;
+  bool big;  // big-head kernel (qk head dim > 128 or v head dim > 256)
 };
 
 int get_plan(int B, int H, int N, int M, const Mode& mode, Plan** out) {
@@ -1182,10 +1424,11 @@ Mode choose_mode(const pcv_attn_params& a) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false};
+  if (pad64(a.dqk) > 128 || DV > 256) return Mode{kTileM, kTileM, kTileM, false, true};
+  if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false, false};
   if (want_pair && DV == 128 && a.N > kRowsPerUnit && sms >= 2 && (sms % 2) == 0)
-    return Mode{4 * kTileM, 2 * kTileM, 4 * kTileM, true};
-  return Mode{kRowsPerUnit, kTileM, kRowsPerUnit, false};
+    return Mode{4 * kTileM, 2 * kTileM, 4 * kTileM, true, false};
+  return Mode{kRowsPerUnit, kTileM, kRowsPerUnit, false, false};
 }
 
 template <int DQK, int DV, bool BF16>
@@ -1251,6 +1494,31 @@ int launch_pair(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq,
   return PCV_OK;
 }
 
+template <bool BF16>
+int launch_big(const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, TcParams& p,
+               cudaStream_t stream) {
+  auto kern = attn_tc_big_kernel<BF16>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigSmemBytes));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  prof_mark_begin(stream);
+  kern<<<pl.num_ctas, kBigThreads, kBigSmemBytes, stream>>>(tq, tk, tv, p);
+  prof_mark_end(stream);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  if (pl.num_units > 0) {
+    dim3 grid(pl.num_units, p.slot_rows / 8);
+    tc_combine_kernel<256, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return PCV_OK;
+}
+
 }  // namespace
 
 int debug_trace_read(unsigned long long* out, int n) {
@@ -1270,8 +1538,8 @@ bool attn_tc_supported(const pcv_attn_params& p, const char** why) {
     *why = w;
     return false;
   };
-  if (p.dqk > 128) return fail("qk head dim > 128 (shared-memory budget of the K ring)");
-  if (p.dv > 256) return fail("v head dim > 256 (TMEM budget: O accumulator columns)");
+  if (p.dqk > 512) return fail("qk head dim > 512");
+  if (p.dv > 512) return fail("v head dim > 512");
   if ((p.dqk % 8) || (p.dv % 8)) return fail("head dims must be multiples of 8 (16-byte TMA strides)");
   if (!(p.scale > 0.f)) return fail("scale must be positive");
   auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
@@ -1298,7 +1566,7 @@ int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
   const Mode mode = choose_mode(p);
   int rc = get_plan(p.B, p.H, p.N, p.M, mode, &pl);
   if (rc != PCV_OK) return rc;
-  size_t b = slots_bytes(*pl, pad64(p.dv), mode.slot_rows);
+  size_t b = slots_bytes(*pl, mode.big ? 256 : pad64(p.dv), mode.slot_rows);
   b = (b + 255) / 256 * 256;
   if (p.pad_mask != nullptr) b += sizeof(uint32_t) * (size_t)p.B * ((p.M + kTileN - 1) / kTileN * 4);
   *bytes = b;
@@ -1324,6 +1592,8 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   p.segs = pl->d_segs;
   p.cta_seg_begin = pl->d_cta;
   p.B = a.B; p.H = a.H; p.N = a.N; p.M = a.M; p.dv = a.dv;
+  p.dv_off = 0;
+  p.dv_pass = a.dv;
   p.scale_log2 = a.scale * kLog2e;
   p.causal = a.causal;
   p.causal_shift = (a.m_total - a.N) - a.m_offset;
@@ -1350,11 +1620,12 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   p.fin_o = a.part_o; p.fin_m = a.part_m; p.fin_l = a.part_l;
   char* ws = reinterpret_cast<char*>(a.workspace);
   const size_t nrows = (size_t)pl->num_slots * mode.slot_rows;
+  const int slot_dv = mode.big ? 256 : DV;
   p.slot_o = reinterpret_cast<float*>(ws);
-  p.slot_m = p.slot_o + nrows * DV;
+  p.slot_m = p.slot_o + nrows * slot_dv;
   p.slot_l = p.slot_m + nrows;
   if (a.pad_mask != nullptr) {
-    size_t off = (slots_bytes(*pl, DV, mode.slot_rows) + 255) / 256 * 256;
+    size_t off = (slots_bytes(*pl, slot_dv, mode.slot_rows) + 255) / 256 * 256;
     uint32_t* bits = reinterpret_cast<uint32_t*>(ws + off);
     p.pad_wpr = (a.M + kTileN - 1) / kTileN * 4;
     p.pad_bits = bits;
@@ -1376,6 +1647,21 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   if (rc != PCV_OK) return rc;
 
   const bool bf = a.dtype == PCV_BF16;
+  if (mode.big) {
+    // one launch per 256-channel slice of V (the scores are recomputed for every slice)
+    p.nc = (a.dqk + 127) / 128;
+    for (int off = 0; off < a.dv; off += 256) {
+      p.dv_off = off;
+      p.dv_pass = std::min(256, a.dv - off);
+      p.v_boxes = (p.dv_pass + 63) / 64;
+      const char* vbase = reinterpret_cast<const char*>(a.v) + 2 * (size_t)off;
+      rc = make_tmap(&tv, vbase, a.dtype, p.dv_pass, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
+      if (rc != PCV_OK) return rc;
+      rc = bf ? launch_big<true>(*pl, tq, tk, tv, p, stream) : launch_big<false>(*pl, tq, tk, tv, p, stream);
+      if (rc != PCV_OK) return rc;
+    }
+    return PCV_OK;
+  }
   if (mode.pair) {
     if (DQK == 128)
       return bf ? launch_pair<128, true>(a, *pl, tq, tk, tv, p, stream) : launch_pair<128, false>(a, *pl, tq, tk, tv, p, stream);

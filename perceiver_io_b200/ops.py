@@ -137,10 +137,29 @@ def _prep(q, k, v):
     return q, k, v, out_dtype
 
 
+def _pad_heads_to8(t: torch.Tensor, num_heads: int) -> torch.Tensor:
+    """(B, L, H*d) or (B, L, H, d) with d % 8 != 0 -> zero-padded (B, L, H, d8) copy, d8 = next multiple of 8.
+
+    TMA needs 16-byte strides; zero channels change neither q.k nor the first d channels of P.V (the MNIST
+    encoder has d = 131, the optical-flow encoder d = 322)."""
+    if t.dim() == 3:
+        t = t.reshape(t.shape[0], t.shape[1], num_heads, t.shape[2] // num_heads)
+    d = t.shape[3]
+    return torch.nn.functional.pad(t, (0, (-d) % 8))
+
+
+def _head_dim(t: torch.Tensor, num_heads: int) -> int:
+    return t.shape[2] // num_heads if t.dim() == 3 else t.shape[3]
+
+
 def _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl):
     q, k, v, out_dtype = _prep(q, k, v)
     if pad_mask is not None:
         _require_cuda(pad_mask)
+    dv_true = _head_dim(v, num_heads)
+    if impl != "simt" and (_head_dim(q, num_heads) % 8 or dv_true % 8):
+        # odd head dims: pad to a multiple of 8 so that the tensor-core kernels (TMA) can take them
+        q, k, v = _pad_heads_to8(q, num_heads), _pad_heads_to8(k, num_heads), _pad_heads_to8(v, num_heads)
     with torch.cuda.device(k.device):
         p, keep = _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, None, 0, impl)
         out = torch.empty(p.B, p.N, p.H * p.dv, dtype=q.dtype, device=k.device)
@@ -148,6 +167,8 @@ def _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl):
         p.o_stride_b, p.o_stride_n, p.o_stride_h = out.stride(0), out.stride(1), p.dv
         _run_attn(p, k.device)
     del keep
+    if p.dv != dv_true:
+        out = out.view(p.B, p.N, p.H, p.dv)[..., :dv_true].reshape(p.B, p.N, p.H * dv_true)
     return out if out.dtype == out_dtype else out.to(out_dtype)
 
 

@@ -28,6 +28,12 @@ CASES = {
     "pair_ragged": (2, 300, 700, 2, 128, 128, 2, False, False, 1.0),
     "pair_mask": (3, 400, 900, 2, 128, 128, 1, True, True, 1.0),
     "pair_d64": (2, 640, 1000, 2, 64, 128, 2, False, True, 2.0),
+    "big_192": (1, 128, 256, 1, 192, 64, 1, False, False, 1.0),
+    "big_322": (1, 300, 1000, 1, 322, 322, 1, False, False, 1.0),
+    "big_512": (2, 200, 700, 2, 512, 512, 2, False, True, 1.0),
+    "big_131": (2, 32, 784, 1, 131, 131, 1, False, False, 1.0),
+    "big_causal": (2, 260, 900, 2, 256, 160, 2, True, True, 1.0),
+    "big_long": (1, 2048, 20000, 1, 328, 328, 1, False, False, 1.0),
     "pad": (3, 40, 300, 2, 64, 64, 1, False, True, 1.0),
     "causal": (2, 100, 300, 2, 64, 64, 2, True, True, 1.0),
     "peaked": (1, 128, 4096, 2, 128, 128, 1, False, False, 6.0),
