@@ -955,7 +955,7 @@ constexpr int kBigSmemBytes = kBigItems * kBigItemBytes + 1024 + 1024;
 
 struct BigBarriers {
   uint64_t item_full[kBigItems], item_empty[kBigItems];
-  uint64_t s_full, p_full, pv_done, o_full, o_empty;
+  uint64_t s_full[2], pv_done, o_full, o_empty;  // s_full per S buffer: a barrier must never run a full phase ahead of its waiter
   uint32_t tmem_base;
 };
 
@@ -980,8 +980,10 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       mbar_init(&bb.item_full[i], 1);
       mbar_init(&bb.item_empty[i], 1);
     }
-    mbar_init(&bb.s_full, 1);
-    mbar_init(&bar.p_full[0], 4);  // arrive_p_full() targets bar.p_full[wg = 0]
+    mbar_init(&bb.s_full[0], 1);
+    mbar_init(&bb.s_full[1], 1);
+    mbar_init(&bar.p_full[0], 4);  // arrive_p_full() targets bar.p_full[c.wg]; c.wg = S buffer index here
+    mbar_init(&bar.p_full[1], 4);
     mbar_init(&bb.pv_done, 1);
     mbar_init(&bb.o_full, 1);
     mbar_init(&bb.o_empty, 4);
@@ -1006,7 +1008,7 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int row = threadIdx.x;
     const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
     const uint32_t tO = tmem + lane_field + 256u;
-    uint32_t n_s = 0, n_o = 0, n_pv = 0;
+    uint32_t n_tile = 0, n_o = 0;  // n_tile: key tiles processed by this CTA so far (all segments)
     for (int sg = seg_lo; sg < seg_hi; ++sg) {
       const Segment seg = p.segs[sg];
       const int n = seg.q0 + row;
@@ -1014,26 +1016,27 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       st.m_ref = -INFINITY;
       st.l = 0.f;
       TileCtx c;
-      c.tO = tO; c.wg = 0; c.row = row;
+      c.tO = tO; c.row = row;
       c.p_full_pair = 0;
       c.pv_bar = &bb.pv_done;
       c.cshift = n + p.causal_shift;
       c.trace_on = false;
       for (int t = seg.t0; t < seg.t1; ++t) {
         const int j = t - seg.t0;
-        c.tS = tmem + lane_field + (uint32_t)((j & 1) * 128);
+        const uint32_t buf = n_tile & 1;  // S buffer (and its barriers) alternate over ALL tiles of the CTA
+        c.wg = (int)buf;
+        c.tS = tmem + lane_field + buf * 128u;
         c.j0 = t * kTileN;
         c.tt = j;
         c.first_tile = (j == 0);
-        c.pv_parity = (n_pv + 1) & 1;  // phase of PV(j-1): n_pv counts the PVs of earlier tiles (all segments)
+        c.pv_parity = (n_tile + 1) & 1;  // phase of the previous tile's PV on pv_done
         c.mw = make_uint4(0, 0, 0, 0);
         if (p.pad_bits != nullptr)
           c.mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
         const bool masked_tile =
             __any_sync(0xffffffffu, (c.j0 + kTileN > p.M) || ((c.mw.x | c.mw.y | c.mw.z | c.mw.w) != 0u) ||
                                         (p.causal && (c.j0 + kTileN - 1 > c.cshift)));
-        mbar_wait(&bb.s_full, n_s & 1, 12);
-        ++n_s;
+        mbar_wait(&bb.s_full[buf], (n_tile >> 1) & 1, 12);
         tc_fence_after_sync();
         if (masked_tile) {
           softmax_tile<256, BF16, true>(p, bar, c, st);
@@ -1042,7 +1045,7 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         } else {
           softmax_tile<256, BF16, false>(p, bar, c, st);
         }
-        ++n_pv;
+        ++n_tile;
       }
       mbar_wait(&bb.o_full, n_o & 1, 13);
       ++n_o;
@@ -1098,11 +1101,12 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t idesc_pv = make_idesc(kTileM, 64 * p.v_boxes, BF16, true);
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);          // K-major operands (Q / K chunks)
     const uint64_t dv0 = make_smem_desc(smem_u32(smem), kBoxBytes, 1024);  // MN-major V tile
-    uint32_t it = 0, n_p = 0, n_oe = 0;
+    uint32_t it = 0, n_qk = 0, n_pvi = 0, n_oe = 0;  // n_qk / n_pvi: tiles whose QK^T / PV have been issued (all segments)
     auto commit = [&](uint64_t* b) {
       if (leader) tc_commit(b);
     };
-    auto issue_qk = [&](int j) {  // S[j & 1] = Q K_j^T, accumulated over the channel chunks
+    auto issue_qk = [&]() {  // S[n_qk & 1] = Q K^T of the next tile, accumulated over the channel chunks
+      const uint32_t buf = n_qk & 1;
       for (int ch = 0; ch < p.nc; ++ch) {
         const uint32_t slot = it % kBigItems;
         mbar_wait(&bb.item_full[slot], (it / kBigItems) & 1, 5);
@@ -1114,19 +1118,21 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-            mma_ss(tmem + (j & 1) * 128, da + off, db + off, idesc_qk, (ch > 0 || kk > 0) ? 1u : 0u);
+            mma_ss(tmem + buf * 128, da + off, db + off, idesc_qk, (ch > 0 || kk > 0) ? 1u : 0u);
           }
         }
         commit(&bb.item_empty[slot]);
       }
-      commit(&bb.s_full);
+      commit(&bb.s_full[buf]);
+      ++n_qk;
     };
     for (int sg = seg_lo; sg < seg_hi; ++sg) {
       const Segment seg = p.segs[sg];
       const int nt = seg.t1 - seg.t0;
-      issue_qk(0);
+      issue_qk();
       for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) issue_qk(j + 1);
+        if (j + 1 < nt) issue_qk();
+        const uint32_t buf = n_pvi & 1;
         const uint32_t slot = it % kBigItems;
         mbar_wait(&bb.item_full[slot], (it / kBigItems) & 1, 6);
         ++it;
@@ -1134,18 +1140,18 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           mbar_wait(&bb.o_empty, (n_oe & 1) ^ 1, 7);
           ++n_oe;
         }
-        mbar_wait(&bar.p_full[0], n_p & 1, 8);
-        ++n_p;
+        mbar_wait(&bar.p_full[buf], (n_pvi >> 1) & 1, 8);
         tc_fence_after_sync();
         if (leader && !(p.dbg & 2)) {
           const uint64_t db = dv0 + (uint64_t)((slot * kBigItemBytes) >> 4);
 #pragma unroll
           for (int kk = 0; kk < kTileN / 16; ++kk)
-            mma_ts(tmem + 256, tmem + (j & 1) * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+            mma_ts(tmem + 256, tmem + buf * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
                    (j > 0 || kk > 0) ? 1u : 0u);
         }
         commit(&bb.item_empty[slot]);
         commit(&bb.pv_done);
+        ++n_pvi;
       }
       commit(&bb.o_full);
     }

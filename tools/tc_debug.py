@@ -33,6 +33,7 @@ CASES = {
     "big_512": (2, 200, 700, 2, 512, 512, 2, False, True, 1.0),
     "big_131": (2, 32, 784, 1, 131, 131, 1, False, False, 1.0),
     "big_causal": (2, 260, 900, 2, 256, 160, 2, True, True, 1.0),
+    "big_multi": (1, 128, 51200, 1, 192, 64, 1, False, False, 1.0),
     "big_long": (1, 2048, 20000, 1, 328, 328, 1, False, False, 1.0),
     "pad": (3, 40, 300, 2, 64, 64, 1, False, True, 1.0),
     "causal": (2, 100, 300, 2, 64, 64, 2, True, True, 1.0),
