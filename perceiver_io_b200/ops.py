@@ -355,8 +355,10 @@ def kv_append(k_cache: torch.Tensor, v_cache: torch.Tensor, k_new: torch.Tensor,
 def tcgen05_supported(q, k, v, num_heads: int, pad_mask=None, causal: bool = False) -> bool:
     """True when pcv_attn_fwd would pick the tcgen05 kernel for these operands."""
     q, k, v, _ = _prep(q, k, v)
+    if _head_dim(q, num_heads) % 8 or _head_dim(v, num_heads) % 8:  # same padding rule as the forward
+        q, k, v = _pad_heads_to8(q, num_heads), _pad_heads_to8(k, num_heads), _pad_heads_to8(v, num_heads)
     p, keep = _fill_attn_params(q, k, v, num_heads, 1.0, pad_mask, causal, None, 0, "auto")
-    dummy = torch.empty(1, device=k.device)
+    dummy = torch.empty(16, device=k.device)
     p.out = dummy.data_ptr()
     ok = bool(_lib.lib().pcv_attn_supported_tcgen05(C.byref(p)))
     del keep

@@ -207,3 +207,24 @@ def test_cta_pair_kernel_matches_oracle(shape):
     part = ops.attention_partial(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), impl="tcgen05_pair")
     merged = ops.combine_partials(part[0][None], part[1][None], part[2][None])
     assert_close(merged, oracle_core(q, k, v, H, dqk ** -0.5, pad, False), REL_TC, "pair partial state")
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 3000, 2, 192, 320), (2, 130, 1500, 1, 322, 322), (1, 300, 2000, 1, 512, 512)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_big_head_kernel_multi_tile_with_masks(shape):
+    """qk head dims > 128 / v head dims > 256 (optical-flow geometry): chunked Q K^T, double-buffered S, two V
+    passes; several key tiles per CTA, padding + causal masks, partial-state output."""
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, dqk, dv = shape
+    q, k, v = _qkv(B, N, M, H, dqk, dv, seed=23, q_gain=2.0)
+    assert ops.tcgen05_supported(q, k, v, H)
+    pad = torch.zeros(B, M, dtype=torch.bool)
+    pad[0, 100:900] = True
+    for causal in (False, True):
+        out = ops.attention(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="tcgen05")
+        assert_close(out, oracle_core(q, k, v, H, dqk ** -0.5, pad, causal), REL_TC, f"big-head causal={causal}")
+    if dqk % 8 == 0 and dv % 8 == 0:
+        part = ops.attention_partial(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), impl="tcgen05")
+        merged = ops.combine_partials(part[0][None], part[1][None], part[2][None])
+        assert_close(merged, oracle_core(q, k, v, H, dqk ** -0.5, pad, False), REL_TC, "big-head partial state")
