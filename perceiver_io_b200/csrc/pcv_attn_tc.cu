@@ -346,7 +346,7 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const Segment& s
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           const int col = ch * 32 + c8 * 8;
-          if (col < p.dv) {
+          if (col < p.dv_pass) {
             uint4 w;
             w.x = pack2(__uint_as_float(o[c8 * 8 + 0]) * inv, __uint_as_float(o[c8 * 8 + 1]) * inv, BF16);
             w.y = pack2(__uint_as_float(o[c8 * 8 + 2]) * inv, __uint_as_float(o[c8 * 8 + 3]) * inv, BF16);

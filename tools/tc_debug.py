@@ -33,6 +33,10 @@ CASES = {
     "big_512": (2, 200, 700, 2, 512, 512, 2, False, True, 1.0),
     "big_131": (2, 32, 784, 1, 131, 131, 1, False, False, 1.0),
     "big_causal": (2, 260, 900, 2, 256, 160, 2, True, True, 1.0),
+    "big_small": (1, 40, 96, 1, 322, 322, 1, False, False, 1.0),
+    "big_small2": (1, 40, 96, 1, 328, 328, 1, False, False, 1.0),
+    "big_small3": (1, 40, 96, 1, 328, 256, 1, False, False, 1.0),
+    "big_small4": (1, 40, 200, 1, 328, 328, 1, False, False, 1.0),
     "big_multi": (1, 128, 51200, 1, 192, 64, 1, False, False, 1.0),
     "big_long": (1, 2048, 20000, 1, 328, 328, 1, False, False, 1.0),
     "pad": (3, 40, 300, 2, 64, 64, 1, False, True, 1.0),
@@ -87,6 +91,18 @@ def run_case(name):
         res["bad_rows_per_batch"] = rows_bad.sum(-1).tolist()
         cols_bad = bad.any(1).any(0)
         res["bad_cols"] = int(cols_bad.sum())
+        idx = cols_bad.nonzero().flatten().tolist()
+        runs, start = [], None
+        for a, b2 in zip(idx, idx[1:] + [None]):
+            if start is None:
+                start = a
+            if b2 is None or b2 != a + 1:
+                runs.append((start, a))
+                start = None
+        res["bad_col_runs"] = runs[:12]
+        r1 = 1 if out.shape[1] > 1 else 0
+        res["row1_out"] = [round(float(x), 3) for x in out[0, r1, :6]] + [round(float(x), 3) for x in out[0, r1, 250:262]]
+        res["row1_ref"] = [round(float(x), 3) for x in ref_simt[0, r1, :6]] + [round(float(x), 3) for x in ref_simt[0, r1, 250:262]]
     print("RESULT " + json.dumps(res), flush=True)
 
 
