@@ -78,39 +78,46 @@ __global__ void __launch_bounds__(256) combine_peers_kernel(const pcv_peer_combi
   const int lane = threadIdx.x & 31;
   if (r >= p.row_end) return;
   const int G = p.num_peers;
-  float mg[PCV_MAX_PEERS], w[PCV_MAX_PEERS];
-  float m = -INFINITY;
-#pragma unroll
-  for (int g = 0; g < PCV_MAX_PEERS; ++g) {
-    mg[g] = (g < G) ? p.part_m[g][r] : -INFINITY;
-    m = fmaxf(m, mg[g]);
-  }
-  float l = 0.f;
-#pragma unroll
-  for (int g = 0; g < PCV_MAX_PEERS; ++g) {
-    w[g] = (g < G && mg[g] != -INFINITY) ? exp2f(mg[g] - m) : 0.f;
-    if (g < G) l += p.part_l[g][r] * w[g];
-  }
-  const float inv = 1.f / l;
   const int n = (int)(r % p.N);
   const int h = (int)((r / p.N) % p.H);
   const int b = (int)(r / ((int64_t)p.N * p.H));
   const int64_t o_off = (int64_t)b * p.o_stride_b + (int64_t)n * p.o_stride_n + (int64_t)h * p.o_stride_h;
-  if ((p.dv & 3) == 0) {
-    for (int c = lane * 4; c < p.dv; c += 128) {
-      float4 x[PCV_MAX_PEERS];
+
+  if ((p.dv & 3) == 0 && p.dv <= 128) {
+    // fast path (dv <= 128): every remote load of the row — row max, denominator and this lane's 16 bytes of the
+    // numerator from every peer — is issued BEFORE anything is consumed, so the warp pays one NVLink round trip
+    float mg[PCV_MAX_PEERS], lg[PCV_MAX_PEERS];
+    float4 x[PCV_MAX_PEERS];
+    const int c = lane * 4;
+    const bool active = c < p.dv;
 #pragma unroll
-      for (int g = 0; g < PCV_MAX_PEERS; ++g)
-        if (g < G) x[g] = *reinterpret_cast<const float4*>(p.part_o[g] + r * p.dv + c);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < PCV_MAX_PEERS; ++g) {
+      if (g < G) {
+        mg[g] = __ldg(p.part_m[g] + r);
+        lg[g] = __ldg(p.part_l[g] + r);
+        x[g] = active ? __ldg(reinterpret_cast<const float4*>(p.part_o[g] + r * p.dv + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        mg[g] = -INFINITY;
+        lg[g] = 0.f;
+        x[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float m = -INFINITY;
 #pragma unroll
-      for (int g = 0; g < PCV_MAX_PEERS; ++g)
-        if (g < G) {
-          acc.x = fmaf(x[g].x, w[g], acc.x);
-          acc.y = fmaf(x[g].y, w[g], acc.y);
-          acc.z = fmaf(x[g].z, w[g], acc.z);
-          acc.w = fmaf(x[g].w, w[g], acc.w);
-        }
+    for (int g = 0; g < PCV_MAX_PEERS; ++g) m = fmaxf(m, mg[g]);
+    float l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < PCV_MAX_PEERS; ++g) {
+      const float w = (mg[g] != -INFINITY) ? exp2f(mg[g] - m) : 0.f;
+      l = fmaf(lg[g], w, l);
+      acc.x = fmaf(x[g].x, w, acc.x);
+      acc.y = fmaf(x[g].y, w, acc.y);
+      acc.z = fmaf(x[g].z, w, acc.z);
+      acc.w = fmaf(x[g].w, w, acc.w);
+    }
+    if (active) {
+      const float inv = 1.f / l;
       T v0 = Elem<T>::from_f(acc.x * inv), v1 = Elem<T>::from_f(acc.y * inv);
       T v2 = Elem<T>::from_f(acc.z * inv), v3 = Elem<T>::from_f(acc.w * inv);
       uint2 packed;
@@ -120,12 +127,26 @@ __global__ void __launch_bounds__(256) combine_peers_kernel(const pcv_peer_combi
       for (int g = 0; g < PCV_MAX_PEERS; ++g)
         if (g < G) *reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.out[g]) + o_off + c) = packed;
     }
-  } else {
-    for (int c = lane; c < p.dv; c += 32) {
-      float acc = 0.f;
-      for (int g = 0; g < G; ++g) acc = fmaf(p.part_o[g][r * p.dv + c], w[g], acc);
-      for (int g = 0; g < G; ++g) reinterpret_cast<T*>(p.out[g])[o_off + c] = Elem<T>::from_f(acc * inv);
-    }
+    return;
+  }
+
+  // general path
+  float w[PCV_MAX_PEERS];
+  float m = -INFINITY;
+  for (int g = 0; g < G; ++g) {
+    w[g] = p.part_m[g][r];
+    m = fmaxf(m, w[g]);
+  }
+  float l = 0.f;
+  for (int g = 0; g < G; ++g) {
+    w[g] = (w[g] != -INFINITY) ? exp2f(w[g] - m) : 0.f;
+    l += p.part_l[g][r] * w[g];
+  }
+  const float inv = 1.f / l;
+  for (int c = lane; c < p.dv; c += 32) {
+    float acc = 0.f;
+    for (int g = 0; g < G; ++g) acc = fmaf(p.part_o[g][r * p.dv + c], w[g], acc);
+    for (int g = 0; g < G; ++g) reinterpret_cast<T*>(p.out[g])[o_off + c] = Elem<T>::from_f(acc * inv);
   }
 }
 
