@@ -170,6 +170,8 @@ __device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c) {
   }
 }
 
+// Classic tile (max pass first): first tile of a segment, masked tiles, redo after an optimistic miss.  (Making it
+// __noinline__ to relieve register pressure in the tile loop was measured: -12 %, the context then lives on the stack.)
 template <int DV, bool BF16, bool MASKED>
 __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, const TileCtx& c, RowState& st) {
   uint32_t s[4][32];
