@@ -1432,7 +1432,8 @@ Mode choose_mode(const pcv_attn_params& a) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (pad64(a.dqk) > 128 || DV > 256) return Mode{kTileM, kTileM, kTileM, false, true};
+  static const int force_big = [] { const char* e = getenv("PCV_FORCE_BIG"); return e ? atoi(e) : 0; }();  // experiment
+  if (pad64(a.dqk) > 128 || DV > 256 || force_big) return Mode{kTileM, kTileM, kTileM, false, true};
   if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false, false};
   if (want_pair && DV == 128 && a.N > kRowsPerUnit && sms >= 2 && (sms % 2) == 0)
     return Mode{4 * kTileM, 2 * kTileM, 4 * kTileM, true, false};
