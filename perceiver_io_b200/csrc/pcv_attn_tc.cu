@@ -274,17 +274,27 @@ __device__ __forceinline__ void softmax_tile(const TcParams& p, Barriers& bar, c
   PCV_TRACE(p, c.wg, c.tt, 5, c.trace_on);
 }
 
-// Optimistic tile: exponentiate against the CURRENT reference maximum while the scores stream in from TMEM
-// (no separate max pass on the critical path) and track the tile maximum on the side.  If any row of the warp
-// turns out to exceed the reference by more than the rescale threshold, nothing has been stored yet: the warp
-// returns false and the caller redoes the tile on the classic path (max first).  After the first few tiles of
-// a row the reference hardly ever moves, so the redo is rare.
+// Largest tile sum of exponentials (relative to the current reference) the optimistic path accepts.  Every P
+// entry is <= the tile sum, so the bound keeps P representable (fp16: 2^15 < 65504) and leaves the fp32
+// denominator / accumulator ~2^80 of headroom (bf16 shares fp32's exponent range, so its bound is only about
+// overflow).  The classic path moves the reference whenever the row maximum leads it by more than
+// kRescaleThreshold, i.e. whenever a tile sum could exceed 128 * 2^8 = 2^15, so a redo always makes progress.
+template <bool BF16>
+__device__ __forceinline__ constexpr float optimistic_limit() {
+  return BF16 ? 1.099511627776e12f /* 2^40 */ : 32768.f /* 2^15 */;
+}
+
+// Optimistic tile: exponentiate against the CURRENT reference maximum while the scores stream in from TMEM —
+// no max pass at all (the fused 3-input max the compiler emits for a side-tracked maximum costs more issue
+// time than the packed adds of the row sum).  The row sum doubles as the range check: if any row of the warp
+// exceeds optimistic_limit(), nothing has been stored yet, the warp returns false and the caller redoes the
+// tile on the classic path (max first, reference moves, accumulator rescaled).  After the first tile of a row
+// that is rare.
 template <int DV, bool BF16, int POLY4>
 __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barriers& bar, const TileCtx& c,
                                                         RowState& st) {
   uint32_t pk_lo[32], pk_hi[32];  // packed P for key columns [0,64) / [64,128)
   float2 sum2 = make_float2(0.f, 0.f);
-  float mx0 = -INFINITY, mx1 = -INFINITY;
   const float2 mul2 = make_float2(p.scale_log2, p.scale_log2);
   const float2 negm2 = make_float2(-st.m_ref, -st.m_ref);
   uint32_t sa[32], sb[32];
@@ -300,8 +310,6 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
     if ((q) < 3) tmem_ld32(c.tS + ((q) + 1) * 32, nxt);                                           \
     _Pragma("unroll") for (int i = 0; i < 32; i += 2) {                                           \
       const float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);                \
-      mx0 = fmaxf(mx0, s0);                                                                       \
-      mx1 = fmaxf(mx1, s1);                                                                       \
       const float2 x = fma2(make_float2(s0, s1), mul2, negm2);                                    \
       /* POLY4 of every 4 column pairs go through the FMA-pipe exp2 (compile-time pattern) */     \
       const float2 e = (((i >> 1) & 3) < POLY4) ? exp2_poly2(x) : make_float2(ex2(x.x), ex2(x.y)); \
@@ -316,11 +324,11 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
   PCV_OPT_CHUNK(sb, sa, 3, pk_hi, 16);
 #undef PCV_OPT_CHUNK
   PCV_TRACE(p, c.wg, c.tt, 4, c.trace_on);
-  const float m_tile = fmaxf(mx0, mx1) * p.scale_log2;
-  if (__any_sync(0xffffffffu, m_tile - st.m_ref > kRescaleThreshold)) return false;
+  const float tsum = sum2.x + sum2.y;
+  if (__any_sync(0xffffffffu, !(tsum <= optimistic_limit<BF16>()))) return false;
   tmem_st32(c.tS + 0, pk_lo);  // P (16-bit) over S columns [0,64); all of S is in registers by now
   tmem_st32(c.tS + 32, pk_hi);
-  st.l += sum2.x + sum2.y;
+  st.l += tsum;
   tmem_wait_st();
   tc_fence_before_sync();
   arrive_p_full(bar, c);
@@ -698,6 +706,455 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   }
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// Split-tile kernel (default for head dims <= 128).  Same roles, shared-memory ring and TMEM map as
+// attn_tc_kernel, but every 128-key score tile is produced and consumed as two 64-key HALVES:
+//   * Q K^T is issued as two N = 64 MMAs groups (S columns [0,64) and [64,128)), each with its own barrier;
+//   * the softmax row thread turns half A into P_A (16-bit, S columns [0,32)) and hands it over, then works on
+//     half B while the tensor pipe already runs P_A V_A and the NEXT tile's Q K_A^T into the freed columns;
+//   * each query tile has its own MMA issuing warp, so one tile's issuer never waits behind the other tile's P.
+// In attn_tc_kernel the chain  S ready -> softmax -> P ready -> P V + next Q K^T -> S ready  is serial per query
+// tile (the tensor pipe idles ~40 % of the time); here the tensor work of one half hides behind the softmax
+// of the other half, and both softmax warpgroups stay busy.
+// Accumulator rescales (rare: lazy reference) need every P V issued so far to be complete.  No extra commits
+// are spent on that: the next completion of the OTHER half's s_full barrier implies it (tcgen05.commit covers
+// all earlier MMAs of the issuing thread, which issues  PV_A(j), QK_A(j+1), PV_B(j), QK_B(j+1)  in this order),
+// so the rare path just peeks at that barrier.  After the last tile the issuer commits s_full[.][0] once more
+// (an empty phase the softmax consumes before it hands over the last P_B) so that the rule also holds at the
+// segment end.
+// --------------------------------------------------------------------------------------------------
+struct SplitBarriers {
+  uint64_t q_full, q_empty;
+  uint64_t kv_full[8], kv_empty[8];
+  uint64_t s_full[2][2], p_full[2][2], o_full[2], o_empty[2];
+  uint32_t tmem_base;
+};
+
+constexpr int kHalfN = kTileN / 2;
+constexpr int kMmaWarp1 = 10;  // issuer of query tile 1 (query tile 0: kMmaWarp)
+
+struct HalfCtx {
+  uint64_t* p_bar;       // p_full[wg][half]
+  uint64_t* pv_bar;      // barrier whose phase `pv_parity` implies that every P V handed over so far has completed
+  uint32_t pv_parity;
+  uint32_t tS, tO;       // TMEM addresses (lane field included): first S column of this half / O row
+  int j0;                // first key of the half
+  int cshift;            // key j (local) is causally masked for this row iff j > cshift
+  uint32_t mw0, mw1;     // padding bits of the 64 keys of the half
+  bool first;            // first half of the segment: no accumulator content yet
+};
+
+__device__ __forceinline__ void arrive_warp(uint64_t* b) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(b);
+}
+
+// classic half (max pass first): first half of a segment, masked halves, redo after an optimistic miss
+template <int DV, bool BF16, bool MASKED>
+__device__ __forceinline__ void softmax_half(const TcParams& p, const HalfCtx& c, RowState& st) {
+  uint32_t s[2][32];
+  tmem_ld32(c.tS + 0, s[0]);
+  tmem_ld32(c.tS + 32, s[1]);
+  tmem_wait_ld();
+
+  float m_tile;
+  float mul = p.scale_log2;
+  if (!MASKED) {
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      mx0 = max2(mx0, __uint_as_float(s[0][i]));
+      mx1 = max2(mx1, __uint_as_float(s[0][i + 1]));
+      mx2 = max2(mx2, __uint_as_float(s[1][i]));
+      mx3 = max2(mx3, __uint_as_float(s[1][i + 1]));
+    }
+    m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+  } else {
+    const int oob_from = p.M - c.j0;
+    const int cmax = p.causal ? (c.cshift - c.j0) : 0x7fffffff;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t word = q == 0 ? c.mw0 : c.mw1;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = q * 32 + i;
+        float tv = __uint_as_float(s[q][i]) * p.scale_log2;
+        if (((word >> i) & 1u) || col > cmax) tv = kMaskedScore;
+        if (col >= oob_from) tv = -INFINITY;
+        mx = fmaxf(mx, tv);
+        s[q][i] = __float_as_uint(tv);
+      }
+    }
+    m_tile = mx;
+    mul = 1.f;
+  }
+
+  const float m_new = fmaxf(st.m_ref, m_tile);
+  float alpha = 1.f;
+  bool moved = false;
+  if (m_new - st.m_ref > kRescaleThreshold) {
+    alpha = ex2(st.m_ref - m_new);
+    st.l *= alpha;
+    st.m_ref = m_new;
+    moved = !c.first;
+  }
+  if (__any_sync(0xffffffffu, moved)) {
+    if (c.pv_bar != nullptr) mbar_wait(c.pv_bar, c.pv_parity, 15);  // peek: consumed later by the normal wait
+    tc_fence_after_sync();
+#pragma unroll
+    for (int ch = 0; ch < DV / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(c.tO + ch * 32, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st32(c.tO + ch * 32, o);
+    }
+  }
+
+  float2 sum2 = make_float2(0.f, 0.f);
+  const float2 mul2 = make_float2(mul, mul);
+  const float2 negm2 = make_float2(-st.m_ref, -st.m_ref);
+  uint32_t pk[32];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float2 x = fma2(make_float2(__uint_as_float(s[q][i]), __uint_as_float(s[q][i + 1])), mul2, negm2);
+      const float2 e = make_float2(ex2(x.x), ex2(x.y));
+      sum2 = add2(sum2, e);
+      pk[q * 16 + (i >> 1)] = pack2(e.x, e.y, BF16);
+    }
+  }
+  tmem_st32(c.tS, pk);  // P (16-bit) of the 64 keys over the first 32 columns of the half
+  st.l += sum2.x + sum2.y;
+  tmem_wait_st();
+  tc_fence_before_sync();
+  arrive_warp(c.p_bar);
+}
+
+// optimistic half: exponentiate against the current reference while the scores stream in; false = the
+// reference has to move (nothing stored), the caller redoes the half on the classic path
+template <int DV, bool BF16>
+__device__ __forceinline__ bool softmax_half_optimistic(const TcParams& p, const HalfCtx& c, RowState& st) {
+  uint32_t pk[32];
+  float2 sum2 = make_float2(0.f, 0.f);
+  const float2 mul2 = make_float2(p.scale_log2, p.scale_log2);
+  const float2 negm2 = make_float2(-st.m_ref, -st.m_ref);
+  uint32_t sa[32], sb[32];
+  tmem_ld32(c.tS + 0, sa);
+  tmem_wait_ld();
+  tmem_ld32(c.tS + 32, sb);
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float s0 = __uint_as_float(sa[i]), s1 = __uint_as_float(sa[i + 1]);
+    const float2 x = fma2(make_float2(s0, s1), mul2, negm2);
+    const float2 e = make_float2(ex2(x.x), ex2(x.y));
+    sum2 = add2(sum2, e);
+    pk[i >> 1] = pack2(e.x, e.y, BF16);
+  }
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float s0 = __uint_as_float(sb[i]), s1 = __uint_as_float(sb[i + 1]);
+    const float2 x = fma2(make_float2(s0, s1), mul2, negm2);
+    const float2 e = make_float2(ex2(x.x), ex2(x.y));
+    sum2 = add2(sum2, e);
+    pk[16 + (i >> 1)] = pack2(e.x, e.y, BF16);
+  }
+  const float tsum = sum2.x + sum2.y;
+  if (__any_sync(0xffffffffu, !(tsum <= optimistic_limit<BF16>()))) return false;
+  tmem_st32(c.tS, pk);
+  st.l += tsum;
+  tmem_wait_st();
+  tc_fence_before_sync();
+  arrive_warp(c.p_bar);
+  return true;
+}
+
+template <int DQK, int DV, bool BF16>
+__device__ __forceinline__ void softmax_role_split(const TcParams& p, SplitBarriers& bar, int wg, int row,
+                                                   int seg_lo, int seg_hi) {
+  const int row_in_unit = wg * kTileM + row;
+  const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
+  const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
+  const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
+  uint32_t n_s0 = 0, n_s1 = 0, n_o = 0;  // consumed phases of s_full[wg][0], s_full[wg][1], o_full[wg]
+
+  for (int sg = seg_lo; sg < seg_hi; ++sg) {
+    const Segment seg = p.segs[sg];
+    if (wg == 1 && seg.ntile < 2) continue;
+    const int n = seg.q0 + row_in_unit;
+    RowState st;
+    st.m_ref = -INFINITY;
+    st.l = 0.f;
+    HalfCtx c;
+    c.tO = tO;
+    c.cshift = n + p.causal_shift;
+
+    for (int t = seg.t0; t < seg.t1; ++t) {
+      uint4 mw = make_uint4(0, 0, 0, 0);
+      if (p.pad_bits != nullptr)
+        mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        c.j0 = t * kTileN + h * kHalfN;
+        c.tS = tS + (uint32_t)(h * kHalfN);
+        c.p_bar = &bar.p_full[wg][h];
+        c.first = (t == seg.t0) && (h == 0);
+        c.mw0 = h ? mw.z : mw.x;
+        c.mw1 = h ? mw.w : mw.y;
+        // warp-uniform on purpose (tcgen05.ld/st are .sync.aligned)
+        const bool masked = __any_sync(0xffffffffu, (c.j0 + kHalfN > p.M) || ((c.mw0 | c.mw1) != 0u) ||
+                                                        (p.causal && (c.j0 + kHalfN - 1 > c.cshift)));
+        if (h == 0) {
+          mbar_wait(&bar.s_full[wg][0], n_s0 & 1, 12);
+          ++n_s0;
+          c.pv_bar = &bar.s_full[wg][1];  // S_B(t) complete => P V_B(t-1) (and everything before) complete
+          c.pv_parity = n_s1 & 1;
+        } else {
+          mbar_wait(&bar.s_full[wg][1], n_s1 & 1, 14);
+          ++n_s1;
+          if (t + 1 < seg.t1) {
+            c.pv_bar = &bar.s_full[wg][0];  // S_A(t+1) complete => P V_A(t) complete
+            c.pv_parity = n_s0 & 1;
+          } else {
+            // last tile: consume the issuer's end-of-segment phase of s_full[wg][0] (= P V_A(t) complete) BEFORE
+            // handing over P_B — the issuer commits that barrier's next phase only after it has seen P_B, so the
+            // barrier can never run a full phase ahead of this wait
+            mbar_wait(&bar.s_full[wg][0], n_s0 & 1, 16);
+            ++n_s0;
+            c.pv_bar = nullptr;
+          }
+        }
+        tc_fence_after_sync();
+        PCV_TRACE(p, wg, t - seg.t0, h * 4 + 0, row == 0 && sg == seg_lo);
+        if (p.dbg & 1) {  // timing experiment: protocol only
+          tc_fence_before_sync();
+          arrive_warp(c.p_bar);
+          continue;
+        }
+        if (masked) {
+          softmax_half<DV, BF16, true>(p, c, st);
+        } else if (p.optimistic && !c.first) {
+          if (!softmax_half_optimistic<DV, BF16>(p, c, st)) softmax_half<DV, BF16, false>(p, c, st);
+        } else {
+          softmax_half<DV, BF16, false>(p, c, st);
+        }
+        PCV_TRACE(p, wg, t - seg.t0, h * 4 + 1, row == 0 && sg == seg_lo);
+      }
+    }
+    const float l = st.l, m_ref = st.m_ref;
+
+    mbar_wait(&bar.o_full[wg], n_o & 1, 13);
+    ++n_o;
+    tc_fence_after_sync();
+    epilogue_row<DV, BF16>(p, seg, tO, n, row_in_unit, l, m_ref);
+    tc_fence_before_sync();
+    arrive_warp(&bar.o_empty[wg]);
+  }
+}
+
+template <int DQK, int DV, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
+  using C = Cfg<DQK, DV>;
+  static_assert(!C::kWide, "two query tiles per CTA");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + C::kQBytes;
+  SplitBarriers& bar = *reinterpret_cast<SplitBarriers*>(smem + C::kQBytes + C::kStages * C::kStageBytes);
+  static_assert(sizeof(SplitBarriers) <= C::kBarrierBytes, "barrier block");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seg_lo = p.cta_seg_begin[blockIdx.x];
+  const int seg_hi = p.cta_seg_begin[blockIdx.x + 1];
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar.q_full, 1);
+    mbar_init(&bar.q_empty, 2);  // both issuers
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&bar.kv_full[i], 1);
+      mbar_init(&bar.kv_empty[i], 2);  // both issuers
+    }
+    for (int i = 0; i < 2; ++i) {
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(&bar.s_full[i][h], 1);
+        mbar_init(&bar.p_full[i][h], 4);  // one arrive per softmax warp
+      }
+      mbar_init(&bar.o_full[i], 1);
+      mbar_init(&bar.o_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(&bar.tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  if (warp < 8) {
+    reg_alloc<216>();
+    softmax_role_split<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
+  } else {
+    reg_dealloc<72>();
+  }
+  if (warp == kTmaWarp) {
+    // ===== TMA producer (as in attn_tc_kernel): Q once per segment, then K_j, V_j through the ring =====
+    const bool leader = elect_one();
+    uint32_t it = 0, n_q = 0;
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const int bq = p.q_bcast ? 0 : seg.b;
+      mbar_wait(&bar.q_empty, (n_q & 1) ^ 1, 1);
+      ++n_q;
+      if (leader) {
+        mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(seg.ntile * C::kQTileBytes));
+        for (int i = 0; i < seg.ntile; ++i)
+          for (int bx = 0; bx < C::kQBoxes; ++bx)
+            tma_load_4d(q_smem + i * C::kQTileBytes + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64,
+                        seg.q0 + i * kTileM, seg.h, bq);
+      }
+      for (int t = seg.t0; t < seg.t1; ++t) {
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {
+          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+          mbar_wait(&bar.kv_empty[slot], par ^ 1, 2 + kv);
+          if (leader) {
+            const int boxes = kv == 0 ? C::kQBoxes : C::kVBoxes;
+            mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(boxes * kBoxBytes));
+            for (int bx = 0; bx < boxes; ++bx)
+              tma_load_4d(kv_smem + slot * C::kStageBytes + bx * kBoxBytes, kv == 0 ? &tmap_k : &tmap_v,
+                          &bar.kv_full[slot], bx * 64, t * kTileN, seg.h, seg.b);
+          }
+          ++it;
+        }
+      }
+    }
+  } else if (warp == kMmaWarp || warp == kMmaWarp1) {
+    // ===== MMA issuer of query tile i (warp-converged, one elected lane issues) =====
+    const int i = warp == kMmaWarp ? 0 : 1;
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_qk = make_idesc(kTileM, kHalfN, BF16, false);
+    constexpr uint32_t idesc_pv = make_idesc(kTileM, DV, BF16, true);
+    const uint32_t tS = bar.tmem_base + (uint32_t)(i * 128);
+    const uint32_t tO = bar.tmem_base + 256u + (uint32_t)(i * 128);
+    const uint64_t dq = make_smem_desc(smem_u32(q_smem + i * C::kQTileBytes), 16, 1024);
+    const uint64_t dk0 = make_smem_desc(smem_u32(kv_smem), 16, 1024);
+    const uint64_t dv0 = make_smem_desc(smem_u32(kv_smem), kBoxBytes, 1024);
+    uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe = 0;
+
+    // S columns [64h, 64h+64) = Q_i (128 x DQK) . K[64h .. 64h+64)^T
+    auto issue_qk = [&](int h, uint32_t k_slot) {
+      if (leader && !(p.dbg & 4)) {
+        const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes + h * (kHalfN * 128)) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < DQK / 16; ++kk) {
+          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          mma_ss(tS + h * kHalfN, dq + off, db + off, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+      }
+    };
+    // O_i += P_h (128 x 64 keys, TMEM columns [64h, 64h+32)) . V[64h .. 64h+64)
+    auto issue_pv = [&](int h, uint32_t v_slot, bool accumulate) {
+      if (leader && !(p.dbg & 2)) {
+        const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes + h * (kHalfN * 128)) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < kHalfN / 16; ++kk)
+          mma_ts(tO, tS + h * kHalfN + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+                 (accumulate || kk > 0) ? 1u : 0u);
+      }
+    };
+    auto commit = [&](uint64_t* b) {
+      if (leader) tc_commit(b);
+    };
+
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const bool active = i < seg.ntile;  // an idle issuer still walks the ring: every kv_empty / q_empty needs both
+      const int nt = seg.t1 - seg.t0;
+      mbar_wait(&bar.q_full, n_q & 1, 4);
+      ++n_q;
+
+      uint32_t k_slot = it % C::kStages;
+      mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 5);
+      ++it;
+      tc_fence_after_sync();
+      if (active) {
+        issue_qk(0, k_slot);
+        commit(&bar.s_full[i][0]);
+        issue_qk(1, k_slot);
+        commit(&bar.s_full[i][1]);
+      }
+      commit(&bar.kv_empty[k_slot]);
+
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t v_slot = it % C::kStages;
+        mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
+        ++it;
+        const bool more = (j + 1 < nt);
+        if (active) {
+          if (j == 0) {
+            mbar_wait(&bar.o_empty[i], (n_oe & 1) ^ 1, 7);
+            ++n_oe;
+          }
+          PCV_TRACE(p, 2 + 0, j, 0, leader && sg == seg_lo && i == 0);
+          mbar_wait(&bar.p_full[i][0], n_p0 & 1, 8);
+          ++n_p0;
+          tc_fence_after_sync();
+          PCV_TRACE(p, 2 + 0, j, 1, leader && sg == seg_lo && i == 0);
+          issue_pv(0, v_slot, j > 0);
+        }
+        if (more) {
+          k_slot = it % C::kStages;
+          mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
+          ++it;
+          tc_fence_after_sync();
+        }
+        if (active) {
+          if (more) issue_qk(0, k_slot);
+          commit(&bar.s_full[i][0]);  // S_A(j+1); after the last tile: the end-of-segment phase
+          PCV_TRACE(p, 2 + 0, j, 2, leader && sg == seg_lo && i == 0);
+          mbar_wait(&bar.p_full[i][1], n_p1 & 1, 11);
+          ++n_p1;
+          tc_fence_after_sync();
+          PCV_TRACE(p, 2 + 0, j, 3, leader && sg == seg_lo && i == 0);
+          issue_pv(1, v_slot, true);
+        }
+        commit(&bar.kv_empty[v_slot]);
+        if (more) {
+          if (active) {
+            issue_qk(1, k_slot);
+            commit(&bar.s_full[i][1]);
+          }
+          commit(&bar.kv_empty[k_slot]);
+        }
+        PCV_TRACE(p, 2 + 0, j, 4, leader && sg == seg_lo && i == 0);
+      }
+      commit(&bar.q_empty);
+      if (active) commit(&bar.o_full[i]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(bar.tmem_base, 512);
+  }
+}
 
 // --------------------------------------------------------------------------------------------------
 // CTA-pair kernel (cta_group::2): a cluster of two CTAs on one TPC works on 512 query rows of one (b,h).
@@ -1444,7 +1901,12 @@ template <int DQK, int DV, bool BF16>
 int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk,
                const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
   using C = Cfg<DQK, DV>;
+  // two query tiles per CTA (head dims <= 128): the split-tile kernel; PCV_SPLIT=0 selects the whole-tile kernel
+  static const int split_env = [] { const char* e = getenv("PCV_SPLIT"); return e ? atoi(e) : 0; }();
   auto kern = attn_tc_kernel<DQK, DV, BF16>;
+  if constexpr (!C::kWide) {
+    if (split_env) kern = attn_tc_split_kernel<DQK, DV, BF16>;
+  }
   static bool attr_set[64] = {};  // per instantiation and device
   int dev = 0;
   PCV_CHECK_CUDA(cudaGetDevice(&dev));

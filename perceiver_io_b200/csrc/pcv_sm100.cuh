@@ -324,8 +324,8 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
 // x = n + f, |f| <= 0.5 (adding 1.5*2^23 leaves n in the low mantissa bits), cubic Remez fit of 2^f (relative
 // error 7.5e-5, far below the bf16 rounding of P), then n is added to the exponent field.
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -125.f);
-  x.y = fmaxf(x.y, -125.f);
+  x.x = fminf(fmaxf(x.x, -125.f), 126.f);  // upper clamp: an overflowing exponent must fail the caller's range check, not wrap
+  x.y = fminf(fmaxf(x.y, -125.f), 126.f);
   const float2 magic = make_float2(12582912.f, 12582912.f);
   const float2 xr = add2(x, magic);
   const float2 xi = sub2(xr, magic);

@@ -43,6 +43,11 @@ CASES = {
     "causal": (2, 100, 300, 2, 64, 64, 2, True, True, 1.0),
     "peaked": (1, 128, 4096, 2, 128, 128, 1, False, False, 6.0),
     "long": (1, 512, 16384, 8, 128, 128, 1, False, False, 1.0),
+    # scores rise steadily with the key index: the exponent reference moves (accumulator rescale) at every half tile
+    "ramp": (1, 256, 2048, 2, 128, 128, 1, False, False, 1.0),
+    "ramp_1tile_segments": (2, 256, 640, 2, 64, 64, 2, False, False, 1.0),
+    "ramp_causal": (2, 300, 1500, 2, 128, 128, 2, True, True, 1.0),
+    "seg_many": (4, 256, 384, 8, 128, 128, 4, False, False, 1.0),
 }
 
 
@@ -56,6 +61,16 @@ def run_case(name):
     q = (torch.randn(Bq, N, H * dqk, generator=g) * gain).bfloat16().cuda()
     k = torch.randn(B, M, H * dqk, generator=g).bfloat16().cuda()
     v = torch.randn(B, M, H * dv, generator=g).bfloat16().cuda()
+    if name.startswith("ramp"):
+        # k_j = (j * step) * u, q_n = u * |u|^-2 * sqrt(dqk)  =>  scaled score = j * step (+ noise): +12 log2 units per 64 keys
+        u = torch.randn(H * dqk, generator=g)
+        qn = torch.randn(Bq, N, H * dqk, generator=g) * 0.05
+        kn = torch.randn(B, M, H * dqk, generator=g) * 0.05
+        ramp = torch.arange(M, dtype=torch.float32)[None, :, None] * (12.0 * 0.6931 / 64.0)
+        uh = u.view(H, dqk)
+        uq = (uh / (uh * uh).sum(-1, keepdim=True) * dqk ** 0.5).reshape(1, 1, H * dqk)
+        q = (qn + uq).bfloat16().cuda()
+        k = (kn + ramp * u.view(1, 1, -1)).bfloat16().cuda()
     pm = None
     if pad:
         pm = torch.zeros(B, M, dtype=torch.bool)
