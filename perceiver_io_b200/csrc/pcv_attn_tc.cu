@@ -708,27 +708,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
 
 // --------------------------------------------------------------------------------------------------
-// Split-tile kernel (default for head dims <= 128).  Same roles, shared-memory ring and TMEM map as
-// attn_tc_kernel, but every 128-key score tile is produced and consumed as two 64-key HALVES:
-//   * Q K^T is issued as two N = 64 MMAs groups (S columns [0,64) and [64,128)), each with its own barrier;
-//   * the softmax row thread turns half A into P_A (16-bit, S columns [0,32)) and hands it over, then works on
-//     half B while the tensor pipe already runs P_A V_A and the NEXT tile's Q K_A^T into the freed columns;
-//   * each query tile has its own MMA issuing warp, so one tile's issuer never waits behind the other tile's P.
-// In attn_tc_kernel the chain  S ready -> softmax -> P ready -> P V + next Q K^T -> S ready  is serial per query
-// tile (the tensor pipe idles ~40 % of the time); here the tensor work of one half hides behind the softmax
-// of the other half, and both softmax warpgroups stay busy.
-// Accumulator rescales (rare: lazy reference) need every P V issued so far to be complete.  No extra commits
-// are spent on that: the next completion of the OTHER half's s_full barrier implies it (tcgen05.commit covers
-// all earlier MMAs of the issuing thread, which issues  PV_A(j), QK_A(j+1), PV_B(j), QK_B(j+1)  in this order),
-// so the rare path just peeks at that barrier.  After the last tile the issuer commits s_full[.][0] once more
-// (an empty phase the softmax consumes before it hands over the last P_B) so that the rule also holds at the
-// segment end.
+// Split hand-off kernel (head dims <= 128).  Same roles, shared-memory ring and TMEM map as attn_tc_kernel;
+// what changes is the hand-over of P and who issues the MMAs:
+//   * the softmax row thread turns key columns [0,64) of the score tile into P_lo, hands it over, and works on
+//     columns [64,128) while the tensor pipe already runs P_lo V[0:64); after P_hi only half of P V and the next
+//     Q K^T remain on the chain  S ready -> softmax -> P ready -> P V + next Q K^T -> S ready;
+//   * each query tile has its own MMA issuing warp, so one tile's issuer never sits in a blocking tcgen05.mma of
+//     the other tile when its P arrives.
+// Accumulator rescales (rare: lazy reference) need every P V issued so far to be complete.  In the first half
+// that is implied by S(j) being ready (tcgen05.commit covers all earlier MMAs of the issuing thread, and
+// Q K^T(j) is issued after P V(j-1)); for the second half the issuer commits pv_lo[i] after P_lo V of every
+// tile (off the critical path: it would be waiting for P_hi anyway) and the rare path waits on that.
+// (Measured dead end, removed: also splitting Q K^T into two N = 64 halves so that the next tile's first half
+// overlaps the softmax of the second.  SS-mode MMAs re-read the 128 x 16 A slice from shared memory per
+// instruction, so N = 64 costs 6 KB per 32 tensor cycles — shared-memory bound, 1.11 PF)
 // --------------------------------------------------------------------------------------------------
 struct SplitBarriers {
   uint64_t q_full, q_empty;
   uint64_t kv_full[8], kv_empty[8];
-  uint64_t s_full[2][2], p_full[2][2], o_full[2], o_empty[2];
+  uint64_t s_full[2], p_full[2][2], pv_lo[2], o_full[2], o_empty[2];
   uint32_t tmem_base;
+  uint32_t issue_lock;  // held while an issuer queues its [P_hi V, next Q K^T] group (see the issuer loop)
 };
 
 constexpr int kHalfN = kTileN / 2;
@@ -738,7 +738,7 @@ struct HalfCtx {
   uint64_t* p_bar;       // p_full[wg][half]
   uint64_t* pv_bar;      // barrier whose phase `pv_parity` implies that every P V handed over so far has completed
   uint32_t pv_parity;
-  uint32_t tS, tO;       // TMEM addresses (lane field included): first S column of this half / O row
+  uint32_t tS, tP, tO;   // TMEM addresses (lane field included): first S column of this half / first P column / O row
   int j0;                // first key of the half
   int cshift;            // key j (local) is causally masked for this row iff j > cshift
   uint32_t mw0, mw1;     // padding bits of the 64 keys of the half
@@ -828,7 +828,7 @@ __device__ __forceinline__ void softmax_half(const TcParams& p, const HalfCtx& c
       pk[q * 16 + (i >> 1)] = pack2(e.x, e.y, BF16);
     }
   }
-  tmem_st32(c.tS, pk);  // P (16-bit) of the 64 keys over the first 32 columns of the half
+  tmem_st32(c.tP, pk);  // P (16-bit) of the 64 keys: 32 columns
   st.l += sum2.x + sum2.y;
   tmem_wait_st();
   tc_fence_before_sync();
@@ -866,7 +866,7 @@ __device__ __forceinline__ bool softmax_half_optimistic(const TcParams& p, const
   }
   const float tsum = sum2.x + sum2.y;
   if (__any_sync(0xffffffffu, !(tsum <= optimistic_limit<BF16>()))) return false;
-  tmem_st32(c.tS, pk);
+  tmem_st32(c.tP, pk);
   st.l += tsum;
   tmem_wait_st();
   tc_fence_before_sync();
@@ -881,7 +881,7 @@ __device__ __forceinline__ void softmax_role_split(const TcParams& p, SplitBarri
   const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
   const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
   const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
-  uint32_t n_s0 = 0, n_s1 = 0, n_o = 0;  // consumed phases of s_full[wg][0], s_full[wg][1], o_full[wg]
+  uint32_t n_s = 0, n_o = 0, n_t = 0;  // consumed phases of s_full[wg] / o_full[wg]; tiles done (pv_lo[wg] parity)
 
   for (int sg = seg_lo; sg < seg_hi; ++sg) {
     const Segment seg = p.segs[sg];
@@ -898,39 +898,25 @@ __device__ __forceinline__ void softmax_role_split(const TcParams& p, SplitBarri
       uint4 mw = make_uint4(0, 0, 0, 0);
       if (p.pad_bits != nullptr)
         mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
+      mbar_wait(&bar.s_full[wg], n_s & 1, 12);
+      ++n_s;
+      tc_fence_after_sync();
+      PCV_TRACE(p, wg, t - seg.t0, 0, row == 0 && sg == seg_lo);
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         c.j0 = t * kTileN + h * kHalfN;
-        c.tS = tS + (uint32_t)(h * kHalfN);
+        c.tS = tS + (uint32_t)(h * kHalfN);      // scores of keys [64h, 64h+64)
+        c.tP = tS + (uint32_t)(h * kHalfN / 2);  // P over S columns [0,64), consumed by the time it is written
         c.p_bar = &bar.p_full[wg][h];
         c.first = (t == seg.t0) && (h == 0);
         c.mw0 = h ? mw.z : mw.x;
         c.mw1 = h ? mw.w : mw.y;
+        // S(t) ready => every P V up to tile t-1 complete; the second half also needs P_lo V of this tile
+        c.pv_bar = h ? &bar.pv_lo[wg] : nullptr;
+        c.pv_parity = n_t & 1;
         // warp-uniform on purpose (tcgen05.ld/st are .sync.aligned)
         const bool masked = __any_sync(0xffffffffu, (c.j0 + kHalfN > p.M) || ((c.mw0 | c.mw1) != 0u) ||
                                                         (p.causal && (c.j0 + kHalfN - 1 > c.cshift)));
-        if (h == 0) {
-          mbar_wait(&bar.s_full[wg][0], n_s0 & 1, 12);
-          ++n_s0;
-          c.pv_bar = &bar.s_full[wg][1];  // S_B(t) complete => P V_B(t-1) (and everything before) complete
-          c.pv_parity = n_s1 & 1;
-        } else {
-          mbar_wait(&bar.s_full[wg][1], n_s1 & 1, 14);
-          ++n_s1;
-          if (t + 1 < seg.t1) {
-            c.pv_bar = &bar.s_full[wg][0];  // S_A(t+1) complete => P V_A(t) complete
-            c.pv_parity = n_s0 & 1;
-          } else {
-            // last tile: consume the issuer's end-of-segment phase of s_full[wg][0] (= P V_A(t) complete) BEFORE
-            // handing over P_B — the issuer commits that barrier's next phase only after it has seen P_B, so the
-            // barrier can never run a full phase ahead of this wait
-            mbar_wait(&bar.s_full[wg][0], n_s0 & 1, 16);
-            ++n_s0;
-            c.pv_bar = nullptr;
-          }
-        }
-        tc_fence_after_sync();
-        PCV_TRACE(p, wg, t - seg.t0, h * 4 + 0, row == 0 && sg == seg_lo);
         if (p.dbg & 1) {  // timing experiment: protocol only
           tc_fence_before_sync();
           arrive_warp(c.p_bar);
@@ -945,6 +931,7 @@ __device__ __forceinline__ void softmax_role_split(const TcParams& p, SplitBarri
         }
         PCV_TRACE(p, wg, t - seg.t0, h * 4 + 1, row == 0 && sg == seg_lo);
       }
+      ++n_t;
     }
     const float l = st.l, m_ref = st.m_ref;
 
@@ -983,13 +970,13 @@ attn_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_init(&bar.kv_empty[i], 2);  // both issuers
     }
     for (int i = 0; i < 2; ++i) {
-      for (int h = 0; h < 2; ++h) {
-        mbar_init(&bar.s_full[i][h], 1);
-        mbar_init(&bar.p_full[i][h], 4);  // one arrive per softmax warp
-      }
+      mbar_init(&bar.s_full[i], 1);
+      mbar_init(&bar.pv_lo[i], 1);
+      for (int h = 0; h < 2; ++h) mbar_init(&bar.p_full[i][h], 4);  // one arrive per softmax warp
       mbar_init(&bar.o_full[i], 1);
       mbar_init(&bar.o_empty[i], 4);
     }
+    bar.issue_lock = 0u;
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -1047,7 +1034,7 @@ attn_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // ===== MMA issuer of query tile i (warp-converged, one elected lane issues) =====
     const int i = warp == kMmaWarp ? 0 : 1;
     const bool leader = elect_one();
-    constexpr uint32_t idesc_qk = make_idesc(kTileM, kHalfN, BF16, false);
+    constexpr uint32_t idesc_qk = make_idesc(kTileM, kTileN, BF16, false);
     constexpr uint32_t idesc_pv = make_idesc(kTileM, DV, BF16, true);
     const uint32_t tS = bar.tmem_base + (uint32_t)(i * 128);
     const uint32_t tO = bar.tmem_base + 256u + (uint32_t)(i * 128);
@@ -1056,24 +1043,23 @@ attn_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint64_t dv0 = make_smem_desc(smem_u32(kv_smem), kBoxBytes, 1024);
     uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe = 0;
 
-    // S columns [64h, 64h+64) = Q_i (128 x DQK) . K[64h .. 64h+64)^T
-    auto issue_qk = [&](int h, uint32_t k_slot) {
+    auto issue_qk = [&](uint32_t k_slot) {
       if (leader && !(p.dbg & 4)) {
-        const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes + h * (kHalfN * 128)) >> 4);
+        const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes) >> 4);
 #pragma unroll
         for (int kk = 0; kk < DQK / 16; ++kk) {
           const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          mma_ss(tS + h * kHalfN, dq + off, db + off, idesc_qk, kk > 0 ? 1u : 0u);
+          mma_ss(tS, dq + off, db + off, idesc_qk, kk > 0 ? 1u : 0u);
         }
       }
     };
-    // O_i += P_h (128 x 64 keys, TMEM columns [64h, 64h+32)) . V[64h .. 64h+64)
+    // O_i += P_h (128 x 64 keys, TMEM columns [32h, 32h+32) of the S tile) . V[64h .. 64h+64)
     auto issue_pv = [&](int h, uint32_t v_slot, bool accumulate) {
       if (leader && !(p.dbg & 2)) {
         const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes + h * (kHalfN * 128)) >> 4);
 #pragma unroll
         for (int kk = 0; kk < kHalfN / 16; ++kk)
-          mma_ts(tO, tS + h * kHalfN + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+          mma_ts(tO, tS + h * (kHalfN / 2) + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
                  (accumulate || kk > 0) ? 1u : 0u);
       }
     };
@@ -1093,10 +1079,8 @@ attn_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ++it;
       tc_fence_after_sync();
       if (active) {
-        issue_qk(0, k_slot);
-        commit(&bar.s_full[i][0]);
-        issue_qk(1, k_slot);
-        commit(&bar.s_full[i][1]);
+        issue_qk(k_slot);
+        commit(&bar.s_full[i]);
       }
       commit(&bar.kv_empty[k_slot]);
 
@@ -1110,38 +1094,49 @@ attn_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_wait(&bar.o_empty[i], (n_oe & 1) ^ 1, 7);
             ++n_oe;
           }
-          PCV_TRACE(p, 2 + 0, j, 0, leader && sg == seg_lo && i == 0);
+          PCV_TRACE(p, 2, j, 0, leader && sg == seg_lo && i == 0);
           mbar_wait(&bar.p_full[i][0], n_p0 & 1, 8);
           ++n_p0;
           tc_fence_after_sync();
-          PCV_TRACE(p, 2 + 0, j, 1, leader && sg == seg_lo && i == 0);
+          PCV_TRACE(p, 2, j, 1, leader && sg == seg_lo && i == 0);
           issue_pv(0, v_slot, j > 0);
+          commit(&bar.pv_lo[i]);
+          PCV_TRACE(p, 2, j, 2, leader && sg == seg_lo && i == 0);
         }
         if (more) {
           k_slot = it % C::kStages;
           mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
           ++it;
-          tc_fence_after_sync();
         }
         if (active) {
-          if (more) issue_qk(0, k_slot);
-          commit(&bar.s_full[i][0]);  // S_A(j+1); after the last tile: the end-of-segment phase
-          PCV_TRACE(p, 2 + 0, j, 2, leader && sg == seg_lo && i == 0);
           mbar_wait(&bar.p_full[i][1], n_p1 & 1, 11);
           ++n_p1;
+          // The two issuers must not interleave their [P_hi V, next Q K^T] groups MMA by MMA: both score tiles
+          // would then complete together, the two softmax warpgroups would run in lock-step and the tensor pipe
+          // and the exponent pipe would take turns idling (measured: 0.98 PF).  Queueing each group as a unit
+          // keeps the tiles at least one group apart.
+          if (leader) {
+            while (atomicCAS(&bar.issue_lock, 0u, 1u) != 0u) {
+            }
+          }
+          __syncwarp();
           tc_fence_after_sync();
-          PCV_TRACE(p, 2 + 0, j, 3, leader && sg == seg_lo && i == 0);
+          PCV_TRACE(p, 2, j, 3, leader && sg == seg_lo && i == 0);
           issue_pv(1, v_slot, true);
         }
         commit(&bar.kv_empty[v_slot]);
         if (more) {
           if (active) {
-            issue_qk(1, k_slot);
-            commit(&bar.s_full[i][1]);
+            issue_qk(k_slot);
+            commit(&bar.s_full[i]);
           }
           commit(&bar.kv_empty[k_slot]);
         }
-        PCV_TRACE(p, 2 + 0, j, 4, leader && sg == seg_lo && i == 0);
+        if (active) {
+          if (leader) atomicExch(&bar.issue_lock, 0u);
+          __syncwarp();
+        }
+        PCV_TRACE(p, 2, j, 4, leader && sg == seg_lo && i == 0);
       }
       commit(&bar.q_empty);
       if (active) commit(&bar.o_full[i]);
@@ -1901,7 +1896,7 @@ template <int DQK, int DV, bool BF16>
 int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk,
                const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
   using C = Cfg<DQK, DV>;
-  // two query tiles per CTA (head dims <= 128): the split-tile kernel; PCV_SPLIT=0 selects the whole-tile kernel
+  // two query tiles per CTA (head dims <= 128): PCV_SPLIT=1 selects the split hand-off kernel
   static const int split_env = [] { const char* e = getenv("PCV_SPLIT"); return e ? atoi(e) : 0; }();
   auto kern = attn_tc_kernel<DQK, DV, BF16>;
   if constexpr (!C::kWide) {
