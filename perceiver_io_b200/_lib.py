@@ -12,7 +12,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpcv_attn.so")
+# PCV_LIB_PATH: developer override (A/B-testing two builds of the library on one GPU box)
+LIB_PATH = os.environ.get("PCV_LIB_PATH") or os.path.join(_HERE, "lib", "libpcv_attn.so")
 
 PCV_BF16, PCV_F16, PCV_F32 = 0, 1, 2
 PCV_IMPL_AUTO, PCV_IMPL_TCGEN05, PCV_IMPL_SIMT, PCV_IMPL_TCGEN05_PAIR = 0, 1, 2, 3

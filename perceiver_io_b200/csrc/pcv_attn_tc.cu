@@ -81,7 +81,8 @@ struct TcParams {
   int slot_rows;                    // row stride of the partial slots (>= rows_per_unit)
   int dbg;                          // developer experiments (PCV_DBG): 1 = softmax skips its math, 2 = no PV MMAs, 4 = no QK MMAs
   int poly;                         // 1: every 4th column pair uses the FMA-pipe exp2 (optimistic tiles only)
-  int optimistic;                   // 1: exponentiate against the current reference, verify the max afterwards
+  int optimistic;                   // 1: exponentiate against the current reference, verify the range afterwards
+  int mmaopt;                       // attn_tc_kernel issuer: 1 = overlapped barrier probes + deferred kv_empty commits
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
 };
 
@@ -155,6 +156,7 @@ struct TileCtx {
   bool first_tile;    // no accumulator content yet
   bool trace_on;
   int tt;
+  float scale_log2;   // p.scale_log2, kept in a register (a constant-bank load right after the S barrier is latency on the chain)
 };
 
 // P of this thread's row is in TMEM (tcgen05.wait::st + fence done by the caller): tell the MMA issuer
@@ -295,7 +297,7 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
                                                         RowState& st) {
   uint32_t pk_lo[32], pk_hi[32];  // packed P for key columns [0,64) / [64,128)
   float2 sum2 = make_float2(0.f, 0.f);
-  const float2 mul2 = make_float2(p.scale_log2, p.scale_log2);
+  const float2 mul2 = make_float2(c.scale_log2, c.scale_log2);
   const float2 negm2 = make_float2(-st.m_ref, -st.m_ref);
   uint32_t sa[32], sb[32];
   tmem_ld32(c.tS + 0, sa);
@@ -419,6 +421,9 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
   const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
   const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
   uint32_t n_s = 0, n_o = 0;
+  // loop-invariant dispatch, decided before the first barrier wait: 0 classic, 1 optimistic, 2 optimistic + FMA-pipe
+  // exp2 on a quarter of the columns, 3 protocol only (timing experiment)
+  const int mode = (p.dbg & 1) ? 3 : (p.optimistic ? (p.poly ? 2 : 1) : 0);
 
   for (int sg = seg_lo; sg < seg_hi; ++sg) {
     const Segment seg = p.segs[sg];
@@ -434,6 +439,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     c.pv_parity = 0;
     c.cshift = n + p.causal_shift;
     c.trace_on = (row == 0 && sg == seg_lo);
+    c.scale_log2 = p.scale_log2;
 
     for (int t = seg.t0; t < seg.t1; ++t) {
       c.j0 = t * kTileN;
@@ -451,16 +457,16 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       ++n_s;
       tc_fence_after_sync();
       PCV_TRACE(p, wg, c.tt, 0, c.trace_on);
-      if (p.dbg & 1) {  // timing experiment: protocol only
+      if (mode == 3) {  // timing experiment: protocol only
         tc_fence_before_sync();
         arrive_p_full(bar, c);
         continue;
       }
       if (masked_tile) {
         softmax_tile<DV, BF16, true>(p, bar, c, st);
-      } else if (p.optimistic && !c.first_tile) {
-        const bool ok = p.poly ? softmax_tile_optimistic<DV, BF16, 1>(p, bar, c, st)
-                               : softmax_tile_optimistic<DV, BF16, 0>(p, bar, c, st);
+      } else if (mode != 0 && !c.first_tile) {
+        const bool ok = mode == 2 ? softmax_tile_optimistic<DV, BF16, 1>(p, bar, c, st)
+                                  : softmax_tile_optimistic<DV, BF16, 0>(p, bar, c, st);
         if (!ok) {
           // the reference must move: nothing was stored, redo on the classic path (max first)
           softmax_tile<DV, BF16, false>(p, bar, c, st);
@@ -535,10 +541,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tc_fence_after_sync();
 
   if (warp < 8) {
-    reg_alloc<216>();  // 256*216 + 128*72 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
+    reg_alloc<208>();  // 256*208 + 128*88 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
     softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
   } else {
-    reg_dealloc<72>();
+    reg_dealloc<88>();
   }
   // The two control roles run WARP-CONVERGED (all 32 lanes execute the loops and the barrier waits; one
   // elected lane issues the TMA / tcgen05 instructions).  Keeping the warp converged lets the compiler hold
@@ -625,6 +631,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (leader) tc_commit(b);
     };
 
+    // Serial-path trimming (p.mmaopt): this one thread is the pacemaker of the CTA — whenever it sits in a barrier
+    // wait or a tcgen05.commit with the MMA queue empty, the tensor pipe idles.  (1) The waits whose barriers are
+    // normally long complete by the time they are reached (V_j, K_(j+1)) are probed together with the P_0 wait, so
+    // their latencies overlap instead of adding up; (2) the kv_empty commits (only the TMA producer waits for them,
+    // several stages ahead) are deferred until the next P_0 V MMAs are queued, when the thread would be blocked on
+    // the full queue anyway.  Deferral needs the 5-stage ring (with 3 stages the producer needs the slot at once).
+    const bool defer = p.mmaopt && C::kStages >= 5;
+    int pend0 = -1, pend1 = -1;  // ring slots whose kv_empty commit is still owed
+    auto flush_pending = [&]() {
+      if (pend0 >= 0) commit(&bar.kv_empty[pend0]);
+      if (pend1 >= 0) commit(&bar.kv_empty[pend1]);
+      pend0 = pend1 = -1;
+    };
+    auto release = [&](uint32_t slot) {
+      if (!defer) {
+        commit(&bar.kv_empty[slot]);
+      } else if (pend0 < 0) {
+        pend0 = (int)slot;
+      } else {
+        pend1 = (int)slot;
+      }
+    };
+
     for (int sg = seg_lo; sg < seg_hi; ++sg) {
       const Segment seg = p.segs[sg];
       const bool two = seg.ntile == 2;
@@ -645,25 +674,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       commit(&bar.kv_empty[k_slot]);
 
       for (int j = 0; j < nt; ++j) {
-        const uint32_t v_slot = it % C::kStages;
-        mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
+        const uint32_t v_slot = it % C::kStages, v_par = (it / C::kStages) & 1;
         ++it;
+        const bool more = (j + 1 < nt);
+        uint32_t k_par = 0;
+        if (more) {
+          k_slot = it % C::kStages;
+          k_par = (it / C::kStages) & 1;
+          ++it;
+        }
+        bool ok_v = false, ok_p = false, ok_k = false;
+        if (p.mmaopt) {  // independent probes: their latencies overlap
+          ok_v = mbar_try_wait(&bar.kv_full[v_slot], v_par);
+          ok_p = mbar_try_wait(&bar.p_full[0], n_p0 & 1);
+          ok_k = more ? mbar_try_wait(&bar.kv_full[k_slot], k_par) : true;
+        }
+        if (!ok_v) mbar_wait(&bar.kv_full[v_slot], v_par, 6);
         if (j == 0) {
           mbar_wait(&bar.o_empty[0], (n_oe0 & 1) ^ 1, 7);
           ++n_oe0;
         }
         PCV_TRACE(p, 2, j, 0, leader && sg == seg_lo);
-        mbar_wait(&bar.p_full[0], n_p0 & 1, 8);
+        if (!ok_p) mbar_wait(&bar.p_full[0], n_p0 & 1, 8);
         ++n_p0;
         tc_fence_after_sync();
         PCV_TRACE(p, 2, j, 1, leader && sg == seg_lo);
         issue_pv(0, v_slot, j > 0);
+        flush_pending();
         PCV_TRACE(p, 2, j, 2, leader && sg == seg_lo);
-        const bool more = (j + 1 < nt);
         if (more) {
-          k_slot = it % C::kStages;
-          mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
-          ++it;
+          if (!ok_k) mbar_wait(&bar.kv_full[k_slot], k_par, 9);
           tc_fence_after_sync();
           issue_qk(0, k_slot);
           commit(&bar.s_full[0]);
@@ -681,17 +721,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           issue_pv(1, v_slot, j > 0);
         }
         PCV_TRACE(p, 2, j, 6, leader && sg == seg_lo);
-        commit(&bar.kv_empty[v_slot]);
+        release(v_slot);
         if (more) {
           if (two) {
             issue_qk(1, k_slot);
             PCV_TRACE(p, 2, j, 7, leader && sg == seg_lo);
             commit(&bar.s_full[1]);
           }
-          commit(&bar.kv_empty[k_slot]);
+          release(k_slot);
         }
         PCV_TRACE(p, 2, j, 5, leader && sg == seg_lo);
       }
+      flush_pending();
       commit(&bar.q_empty);
       commit(&bar.o_full[0]);
       if (two) commit(&bar.o_full[1]);
@@ -1475,6 +1516,7 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       c.pv_bar = &bb.pv_done;
       c.cshift = n + p.causal_shift;
       c.trace_on = false;
+      c.scale_log2 = p.scale_log2;
       for (int t = seg.t0; t < seg.t1; ++t) {
         const int j = t - seg.t0;
         const uint32_t buf = n_tile & 1;  // S buffer (and its barriers) alternate over ALL tiles of the CTA
@@ -2073,6 +2115,8 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
     p.optimistic = opt;
     static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 0; }();
     p.poly = poly;
+    static const int mmaopt = [] { const char* e = getenv("PCV_MMAOPT"); return e ? atoi(e) : 1; }();
+    p.mmaopt = mmaopt;
     static const int dbg = [] { const char* e = getenv("PCV_DBG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
     static const int trace = [] { const char* e = getenv("PCV_TRACE"); return e ? atoi(e) : 0; }();
