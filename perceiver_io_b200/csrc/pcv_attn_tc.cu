@@ -104,6 +104,8 @@ struct Cfg {
 };
 
 constexpr int kTraceTiles = 48, kTraceEvents = 8, kTraceRoles = 3;
+constexpr int kTraceStamps = kTraceRoles * kTraceTiles * kTraceEvents;
+constexpr int kTraceMaxCtas = 1024;  // after the stamps: [cta][8] = globaltimer start, end, SM id, key tiles, clock64 start, end
 // stamp event `ev` of role `role` for key tile `tile` (CTA 0 only, first kTraceTiles tiles, one lane per role)
 #ifdef PCV_ENABLE_TRACE  // developer build only (make TRACE=1): the stamps cost registers in the softmax loop
 #define PCV_TRACE(pp, role, tile, ev, cond)                                                             \
@@ -111,9 +113,19 @@ constexpr int kTraceTiles = 48, kTraceEvents = 8, kTraceRoles = 3;
     if ((pp).trace != nullptr && blockIdx.x == 0 && (tile) < kTraceTiles && (cond))                       \
       (pp).trace[((role) * kTraceTiles + (tile)) * kTraceEvents + (ev)] = (unsigned long long)clock64(); \
   } while (0)
+// whole-CTA record (thread 0): slot 0 = start, 1 = end (ns, globaltimer), 2 = SM id, 3 = key tiles of the CTA,
+// 4 / 5 = clock64 at start / end (cycles / ns = the SM clock the kernel really ran at)
+#define PCV_TRACE_CTA(pp, slot, value)                                                                 \
+  do {                                                                                                 \
+    if ((pp).trace != nullptr && threadIdx.x == 0 && blockIdx.x < kTraceMaxCtas)                        \
+      (pp).trace[kTraceStamps + blockIdx.x * 8 + (slot)] = (unsigned long long)(value);                 \
+  } while (0)
 #else
 #define PCV_TRACE(pp, role, tile, ev, cond) \
   do {                                      \
+  } while (0)
+#define PCV_TRACE_CTA(pp, slot, value) \
+  do {                                 \
   } while (0)
 #endif
 
@@ -511,6 +523,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int seg_lo = p.cta_seg_begin[blockIdx.x];
   const int seg_hi = p.cta_seg_begin[blockIdx.x + 1];
+#ifdef PCV_ENABLE_TRACE
+  {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    int tiles = 0;
+    for (int sg = seg_lo; sg < seg_hi; ++sg) tiles += p.segs[sg].t1 - p.segs[sg].t0;
+    PCV_TRACE_CTA(p, 0, globaltimer_ns());
+    PCV_TRACE_CTA(p, 4, clock64());
+    PCV_TRACE_CTA(p, 2, smid);
+    PCV_TRACE_CTA(p, 3, tiles);
+  }
+#endif
 
   if (threadIdx.x == 0) {
     mbar_init(&bar.q_full, 1);
@@ -741,6 +765,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
   tc_fence_before_sync();
   __syncthreads();
+  PCV_TRACE_CTA(p, 1, globaltimer_ns());
+  PCV_TRACE_CTA(p, 5, clock64());
   if (warp == kMmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc(bar.tmem_base, 512);
@@ -2030,8 +2056,10 @@ int launch_big(const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk, con
 }  // namespace
 
 int debug_trace_read(unsigned long long* out, int n) {
-  const int total = kTraceRoles * kTraceTiles * kTraceEvents;
-  if (g_trace_dev == nullptr || n < total) return PCV_ERR_INVALID;
+  // n >= 3*48*8: the clock stamps; n >= that + 8*1024: also the per-CTA records
+  const int full = kTraceStamps + 8 * kTraceMaxCtas;
+  if (g_trace_dev == nullptr || n < kTraceStamps) return PCV_ERR_INVALID;
+  const int total = n >= full ? full : kTraceStamps;
   PCV_CHECK_CUDA(cudaMemcpy(out, g_trace_dev, sizeof(unsigned long long) * total, cudaMemcpyDeviceToHost));
   return PCV_OK;
 }
@@ -2121,7 +2149,7 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
     p.dbg = dbg;
     static const int trace = [] { const char* e = getenv("PCV_TRACE"); return e ? atoi(e) : 0; }();
     if (trace) {
-      const size_t bytes = sizeof(unsigned long long) * kTraceRoles * kTraceTiles * kTraceEvents;
+      const size_t bytes = sizeof(unsigned long long) * (kTraceStamps + 8 * kTraceMaxCtas);
       if (g_trace_dev == nullptr) PCV_CHECK_CUDA(cudaMalloc(&g_trace_dev, bytes));
       PCV_CHECK_CUDA(cudaMemsetAsync(g_trace_dev, 0, bytes, stream));
       p.trace = g_trace_dev;
