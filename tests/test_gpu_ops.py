@@ -228,3 +228,61 @@ def test_big_head_kernel_multi_tile_with_masks(shape):
         part = ops.attention_partial(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), impl="tcgen05")
         merged = ops.combine_partials(part[0][None], part[1][None], part[2][None])
         assert_close(merged, oracle_core(q, k, v, H, dqk ** -0.5, pad, False), REL_TC, "big-head partial state")
+
+
+def _ramp_qk(B, N, M, H, dqk, step_log2, dtype, seed=5):
+    """Scores that RISE with the key index by `step_log2` (log2 units of the softmax exponent) per 64 keys: the
+    exponent reference has to move again and again (accumulator rescale in TMEM) and, with a small step, the
+    optimistic tiles run far from the reference before their row-sum range check fires."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(H, dqk, generator=g)
+    uq = (u / (u * u).sum(-1, keepdim=True) * dqk ** 0.5).reshape(1, 1, H * dqk)
+    q = uq + torch.randn(B, N, H * dqk, generator=g) * 0.05
+    ramp = torch.arange(M, dtype=torch.float32)[None, :, None] * (step_log2 * 0.6931 / 64.0)
+    k = ramp * u.reshape(1, 1, H * dqk) + torch.randn(B, M, H * dqk, generator=g) * 0.05
+    return q.to(dtype).cuda(), k.to(dtype).cuda()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("step", [12.0, 1.5, -3.0], ids=["steep", "gentle", "falling"])
+def test_moving_reference_rescale_paths(dtype, step):
+    """steep: the reference moves at every half tile; gentle: optimistic tiles drift up to the fp16 (2^15) /
+    bf16 (2^40) row-sum bound before one is redone; falling: the first tile holds the maximum for good."""
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, d = 2, 300, 2304, 2, 128
+    q, k = _ramp_qk(B, N, M, H, d, step, dtype)
+    v = torch.randn(B, M, H * d, generator=torch.Generator().manual_seed(9)).to(dtype).cuda()
+    pad = torch.zeros(B, M, dtype=torch.bool)
+    pad[1, 1000:1100] = True
+    for causal, pm in ((False, None), (True, pad)):
+        out = ops.attention(q, k, v, H, d ** -0.5, pad_mask=None if pm is None else pm.cuda(), causal=causal, impl="tcgen05")
+        ref = oracle_core(q, k, v, H, d ** -0.5, pm, causal)
+        assert_close(out, ref, REL_TC if dtype == torch.bfloat16 else 5e-3, f"ramp {step} {dtype} causal={causal}")
+
+
+def test_split_handoff_kernel_subprocess():
+    """The opt-in split hand-off kernel (PCV_SPLIT=1 is read once per process) against the CUDA-core kernel."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import torch
+from perceiver_io_b200 import ops
+for (B, N, M, H, d, causal) in ((2, 256, 512, 2, 128, False), (2, 200, 333, 2, 64, True), (1, 512, 4096, 4, 128, False)):
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(B, N, H * d, generator=g).bfloat16().cuda()
+    k = torch.randn(B, M, H * d, generator=g).bfloat16().cuda()
+    v = torch.randn(B, M, H * d, generator=g).bfloat16().cuda()
+    pad = torch.zeros(B, M, dtype=torch.bool); pad[0, :37] = True
+    a = ops.attention(q, k, v, H, d ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="tcgen05").float()
+    b = ops.attention(q, k, v, H, d ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="simt").float()
+    err = (a - b).abs().max().item(); ref = b.abs().max().item()
+    assert torch.isfinite(a).all() and err <= 1.2e-2 * ref, (B, N, M, H, d, causal, err, ref)
+print("SPLIT_OK")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PCV_SPLIT="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0 and "SPLIT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
