@@ -82,7 +82,7 @@ struct TcParams {
   int dbg;                          // developer experiments (PCV_DBG): 1 = softmax skips its math, 2 = no PV MMAs, 4 = no QK MMAs
   int poly;                         // 1: every 4th column pair uses the FMA-pipe exp2 (optimistic tiles only)
   int optimistic;                   // 1: exponentiate against the current reference, verify the range afterwards
-  int mmaopt;                       // attn_tc_kernel issuer: 1 = overlapped barrier probes + deferred kv_empty commits
+  int mmaopt;                       // attn_tc_kernel issuer: bit 0 = overlapped barrier probes, bit 1 = deferred kv_empty commits
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
 };
 
@@ -661,7 +661,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // their latencies overlap instead of adding up; (2) the kv_empty commits (only the TMA producer waits for them,
     // several stages ahead) are deferred until the next P_0 V MMAs are queued, when the thread would be blocked on
     // the full queue anyway.  Deferral needs the 5-stage ring (with 3 stages the producer needs the slot at once).
-    const bool defer = p.mmaopt && C::kStages >= 5;
+    const bool defer = (p.mmaopt & 2) && C::kStages >= 5;
     int pend0 = -1, pend1 = -1;  // ring slots whose kv_empty commit is still owed
     auto flush_pending = [&]() {
       if (pend0 >= 0) commit(&bar.kv_empty[pend0]);
@@ -708,7 +708,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           ++it;
         }
         bool ok_v = false, ok_p = false, ok_k = false;
-        if (p.mmaopt) {  // independent probes: their latencies overlap
+        if (p.mmaopt & 1) {  // independent probes: their latencies overlap
           ok_v = mbar_try_wait(&bar.kv_full[v_slot], v_par);
           ok_p = mbar_try_wait(&bar.p_full[0], n_p0 & 1);
           ok_k = more ? mbar_try_wait(&bar.kv_full[k_slot], k_par) : true;
@@ -2143,7 +2143,7 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
     p.optimistic = opt;
     static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 0; }();
     p.poly = poly;
-    static const int mmaopt = [] { const char* e = getenv("PCV_MMAOPT"); return e ? atoi(e) : 1; }();
+    static const int mmaopt = [] { const char* e = getenv("PCV_MMAOPT"); return e ? atoi(e) : 3; }();
     p.mmaopt = mmaopt;
     static const int dbg = [] { const char* e = getenv("PCV_DBG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
