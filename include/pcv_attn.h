@@ -254,6 +254,17 @@ PCV_API int pcv_debug_read(uint32_t* out, int32_t n);
  * pipeline points; copies the 3 x 48 x 8 stamps (roles: softmax0, softmax1, mma; tile; event) of the last launch. */
 PCV_API int pcv_debug_trace_read(uint64_t* out, int32_t n);
 
+/*
+ * Host-only developer aid (no CUDA call, usable without a GPU): the stream-K work plan the tcgen05 kernels would
+ * use for (B, H, N, M) on `workers` CTAs with `rows_per_unit` query rows per work unit (256: two 128-row tiles
+ * per CTA; 128: wide-v / big-head kernels; 512: CTA pairs).  Writes counts = {segments, ctas, partial slots,
+ * split units} and, if max_segs is large enough (else PCV_ERR_WORKSPACE with counts filled), one record of
+ * 8 ints per segment: {cta, b, h, q0, active query tiles, first key tile, end key tile, slot (-1 = whole key
+ * range, writes the final output)}.  Key tiles are 128 keys.
+ */
+PCV_API int pcv_debug_plan(int32_t B, int32_t H, int32_t N, int32_t M, int32_t workers, int32_t rows_per_unit,
+                           int32_t rows_per_tile, int32_t* segs, int32_t max_segs, int32_t* counts);
+
 /* number of kernel launches issued by this library in the calling process (for bench.py's
  * gpu_launches claim) */
 PCV_API uint64_t pcv_launch_count(void);

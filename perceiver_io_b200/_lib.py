@@ -33,6 +33,7 @@ EXPORTS = (
     "pcv_rotary_apply",
     "pcv_kv_append",
     "pcv_launch_count",
+    "pcv_debug_plan",
     "pcv_profile_begin",
     "pcv_profile_end",
     "pcv_debug_read",
@@ -169,6 +170,8 @@ def lib() -> C.CDLL:
         l.pcv_profile_end.restype = C.c_int
         l.pcv_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         l.pcv_kv_append.argtypes = [C.POINTER(KvAppendParams), C.c_void_p]
+        l.pcv_debug_plan.argtypes = [C.c_int32] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
+        l.pcv_debug_plan.restype = C.c_int
         for name in ("pcv_get_device_info", "pcv_attn_supported_tcgen05", "pcv_attn_workspace_bytes",
                      "pcv_attn_fwd", "pcv_attn_combine", "pcv_rotary_apply", "pcv_kv_append",
                      "pcv_partial_rescale"):
@@ -204,6 +207,17 @@ def debug_read():
     l.pcv_debug_read.argtypes = [C.POINTER(C.c_uint32), C.c_int32]
     l.pcv_debug_read(buf, 16)
     return list(buf)
+
+
+def debug_plan(B, H, N, M, workers=148, rows_per_unit=256):
+    """Host-only: the tcgen05 work plan as (counts dict, list of (cta, b, h, q0, ntile, t0, t1, slot))."""
+    counts = (C.c_int32 * 4)()
+    lib().pcv_debug_plan(B, H, N, M, workers, rows_per_unit, 128, None, 0, counts)  # sizes only
+    n = counts[0]
+    segs = (C.c_int32 * (8 * max(n, 1)))()
+    check(lib().pcv_debug_plan(B, H, N, M, workers, rows_per_unit, 128, segs, n, counts), "pcv_debug_plan")
+    recs = [tuple(segs[8 * i + j] for j in range(8)) for i in range(n)]
+    return {"segments": counts[0], "ctas": counts[1], "slots": counts[2], "units": counts[3]}, recs
 
 
 def launch_count() -> int:

@@ -114,6 +114,15 @@ int pcv_debug_trace_read(uint64_t* out, int32_t n) {
   return debug_trace_read(reinterpret_cast<unsigned long long*>(out), n);
 }
 
+int pcv_debug_plan(int32_t B, int32_t H, int32_t N, int32_t M, int32_t workers, int32_t rows_per_unit,
+                   int32_t rows_per_tile, int32_t* segs, int32_t max_segs, int32_t* counts) {
+  PCV_REQUIRE(B > 0 && H > 0 && N > 0 && M > 0 && workers > 0, PCV_ERR_INVALID, "debug_plan: sizes must be positive");
+  PCV_REQUIRE(rows_per_tile == 128 && (rows_per_unit == 128 || rows_per_unit == 256 || rows_per_unit == 512),
+              PCV_ERR_INVALID, "debug_plan: rows_per_tile must be 128 and rows_per_unit 128, 256 or 512");
+  PCV_REQUIRE(counts != nullptr && (segs != nullptr || max_segs == 0), PCV_ERR_INVALID, "debug_plan: NULL argument");
+  return debug_plan(B, H, N, M, workers, rows_per_unit, rows_per_tile, segs, max_segs, counts);
+}
+
 uint64_t pcv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int pcv_get_device_info(pcv_device_info* info) {

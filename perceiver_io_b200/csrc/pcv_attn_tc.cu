@@ -2064,6 +2064,26 @@ int debug_trace_read(unsigned long long* out, int n) {
   return PCV_OK;
 }
 
+// Host-only (no CUDA call): the work plan of the tcgen05 kernels for a problem, one record of 8 ints per segment
+// {cta, b, h, q0, ntile, t0, t1, slot}; tests/test_plan_cpu.py checks its invariants on the CPU.
+int debug_plan(int B, int H, int N, int M, int workers, int rows_per_unit, int rows_per_tile, int32_t* segs,
+               int max_segs, int32_t* counts) {
+  Plan pl;
+  build_plan(pl, B, H, N, M, workers, rows_per_unit, rows_per_tile);
+  counts[0] = (int32_t)pl.segs.size();
+  counts[1] = pl.num_ctas;
+  counts[2] = pl.num_slots;
+  counts[3] = pl.num_units;
+  if ((int)pl.segs.size() > max_segs) return PCV_ERR_WORKSPACE;
+  for (int c = 0; c < pl.num_ctas; ++c)
+    for (int s = pl.cta_seg_begin[c]; s < pl.cta_seg_begin[c + 1]; ++s) {
+      const Segment& g = pl.segs[s];
+      int32_t* r = segs + 8 * s;
+      r[0] = c; r[1] = g.b; r[2] = g.h; r[3] = g.q0; r[4] = g.ntile; r[5] = g.t0; r[6] = g.t1; r[7] = g.slot;
+    }
+  return PCV_OK;
+}
+
 int debug_read(uint32_t* out, int n) {
   for (int i = 0; i < n; ++i) out[i] = (g_diag_host != nullptr && i < 16) ? g_diag_host[i] : 0u;
   return PCV_OK;

@@ -78,6 +78,8 @@ bool attn_tc_supported(const pcv_attn_params& p, const char** why);
 int launch_attn_tc(const pcv_attn_params& p, cudaStream_t stream);
 int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
 int debug_read(uint32_t* out, int n);
+int debug_plan(int B, int H, int N, int M, int workers, int rows_per_unit, int rows_per_tile, int32_t* segs,
+               int max_segs, int32_t* counts);  // host-only dump of the tcgen05 work plan
 int debug_trace_read(unsigned long long* out, int n);  // PCV_TRACE=1 clock stamps (3 x 48 x 8)  // watchdog record of the tcgen05 kernel (16 words)
 
 int launch_combine(const pcv_combine_params& p, cudaStream_t stream);
