@@ -318,37 +318,109 @@ def rotary(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: b
     return y if cdt == out_dtype else y.to(out_dtype)
 
 
-def kv_append(k_cache: torch.Tensor, v_cache: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor):
-    """Functional KV-cache concat along dim 1 in one launch (reference modules.py:117-121).
+class _KvArena:
+    """Backing buffer ``(B, capacity, C)`` of a growing KV cache plus the first unused row."""
 
-    Returns freshly allocated ``(B, L_old+n, C)`` tensors, as ``torch.cat`` does, so the
-    🤗-side cache consumers may slice / ``index_select`` them freely (SURVEY.md §8(b) ownership)."""
-    _require_cuda(k_cache, v_cache, k_new, v_new)
+    __slots__ = ("buf", "used")
+
+    def __init__(self, buf: torch.Tensor):
+        self.buf = buf
+        self.used = 0
+
+
+_ARENA_ATTR = "_pcv_kv_arena"
+#: Arena policy of :func:`kv_append` (``enabled=False`` restores plain concat into exact-size tensors).
+kv_arena_config = {"enabled": True, "growth": 1.5, "min_rows": 64}
+
+
+def _arena_of(t: torch.Tensor):
+    """``(arena, first_row)`` if ``t`` is a row range of an arena this module allocated, else ``None``.
+
+    Views keep ``._base`` pointing at the root buffer through any chain of slices, so a cache the caller
+    truncated (``k[:, -m:]``, core/huggingface.py:146-156) is still recognised; ``index_select`` (beam
+    reordering, :140-144) yields a fresh tensor and is not."""
+    root = t._base if t._base is not None else t
+    arena = getattr(root, _ARENA_ATTR, None)
+    if arena is None or arena.buf is not root or t.dim() != 3 or t.dtype != root.dtype:
+        return None
+    B, cap, C = root.shape
+    if t.shape[0] != B or t.shape[2] != C or t.shape[1] == 0:
+        return None
+    if t.stride(2) != 1 or t.stride(1) != C or (B > 1 and t.stride(0) != cap * C):
+        return None
+    off = t.storage_offset() - root.storage_offset()
+    if off < 0 or off % C or off // C + t.shape[1] > cap:
+        return None
+    return arena, off // C
+
+
+def _arena_target(cache: torch.Tensor, n: int):
+    """Where the appended cache lives: ``(dst_view (B, L+n, C), in_place)``.
+
+    In place only when the cache is the row range that ends at the arena's frontier and ``n`` more rows
+    fit: rows a caller may still hold are never overwritten, so the functional semantics of the
+    reference's ``torch.cat`` (modules.py:117-121; two different continuations of one cache stay
+    independent) are preserved.  Otherwise a new arena with head-room is allocated and the kernel copies
+    the old rows once — amortised O(new rows) per decode step instead of O(cache)."""
+    B, L, C = cache.shape
+    hit = _arena_of(cache) if kv_arena_config["enabled"] else None
+    if hit is not None:
+        arena, start = hit
+        if start + L == arena.used and arena.used + n <= arena.buf.shape[1]:
+            arena.used += n
+            return arena.buf[:, start:start + L + n], True
+    if not kv_arena_config["enabled"]:
+        return torch.empty(B, L + n, C, dtype=cache.dtype, device=cache.device), False
+    cap = max(int((L + n) * kv_arena_config["growth"]) + 1, kv_arena_config["min_rows"], L + n)
+    cap = (cap + 63) // 64 * 64
+    buf = torch.empty(B, cap, C, dtype=cache.dtype, device=cache.device)
+    arena = _KvArena(buf)
+    arena.used = L + n
+    setattr(buf, _ARENA_ATTR, arena)
+    return buf[:, :L + n], False
+
+
+def _launch_kv_append(k_cache, v_cache, k_new, v_new, k_dst, v_dst, k_in_place, v_in_place) -> None:
+    """One launch: dst[:, :L] = cache (skipped for a half appended in place), dst[:, L:] = new rows."""
     dt = k_new.dtype
     codes = {torch.bfloat16: _lib.PCV_BF16, torch.float16: _lib.PCV_F16, torch.float32: _lib.PCV_F32}
-    if dt not in codes or any(t.dtype != dt for t in (k_cache, v_cache, v_new)):
-        raise RuntimeError(f"kv_append expects matching bf16/fp16/fp32 tensors, got {k_cache.dtype}/{k_new.dtype}")
-    k_cache, v_cache, k_new, v_new = (_rows_contiguous(t) for t in (k_cache, v_cache, k_new, v_new))
     B, L_old, Ck = k_cache.shape
-    n = k_new.shape[1]
-    Cv = v_new.shape[2]
-    k_dst = torch.empty(B, L_old + n, Ck, dtype=dt, device=k_new.device)
-    v_dst = torch.empty(B, L_old + n, Cv, dtype=dt, device=k_new.device)
-    if L_old + n == 0:
-        return k_dst, v_dst
     p = KvAppendParams()
-    p.k_cache, p.v_cache = (k_cache.data_ptr(), v_cache.data_ptr()) if L_old else (None, None)
+    # an in-place half passes its own destination as the cache pointer: the library skips that copy
+    kc = k_dst if k_in_place else k_cache
+    vc = v_dst if v_in_place else v_cache
+    p.k_cache, p.v_cache = (kc.data_ptr(), vc.data_ptr()) if L_old else (None, None)
     p.k_new, p.v_new, p.k_dst, p.v_dst = k_new.data_ptr(), v_new.data_ptr(), k_dst.data_ptr(), v_dst.data_ptr()
-    p.kc_stride_b, p.kc_stride_l = k_cache.stride(0), k_cache.stride(1)
-    p.vc_stride_b, p.vc_stride_l = v_cache.stride(0), v_cache.stride(1)
+    p.kc_stride_b, p.kc_stride_l = kc.stride(0), kc.stride(1)
+    p.vc_stride_b, p.vc_stride_l = vc.stride(0), vc.stride(1)
     p.kn_stride_b, p.kn_stride_l = k_new.stride(0), k_new.stride(1)
     p.vn_stride_b, p.vn_stride_l = v_new.stride(0), v_new.stride(1)
     p.kd_stride_b, p.kd_stride_l = k_dst.stride(0), k_dst.stride(1)
     p.vd_stride_b, p.vd_stride_l = v_dst.stride(0), v_dst.stride(1)
-    p.B, p.L_old, p.n, p.Ck, p.Cv = B, L_old, n, Ck, Cv
+    p.B, p.L_old, p.n, p.Ck, p.Cv = B, L_old, k_new.shape[1], Ck, v_new.shape[2]
     p.dtype = codes[dt]
     with torch.cuda.device(k_new.device):
         check(_lib.lib().pcv_kv_append(C.byref(p), _stream()), "pcv_kv_append")
+
+
+def kv_append(k_cache: torch.Tensor, v_cache: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor):
+    """Functional KV-cache concat along dim 1 in one launch (reference modules.py:117-121).
+
+    Returns ``(B, L_old+n, C)`` tensors that the 🤗-side cache consumers may slice / ``index_select`` freely
+    (SURVEY.md §8(b) ownership) and that never alias rows of the inputs a caller could observe changing.
+    They are row ranges of arenas with head-room (see :func:`_arena_target`): a decode loop that feeds the
+    returned cache back in appends its new row in place instead of re-copying the whole cache every step."""
+    _require_cuda(k_cache, v_cache, k_new, v_new)
+    dt = k_new.dtype
+    if dt not in (torch.bfloat16, torch.float16, torch.float32) or any(t.dtype != dt for t in (k_cache, v_cache, v_new)):
+        raise RuntimeError(f"kv_append expects matching bf16/fp16/fp32 tensors, got {k_cache.dtype}/{k_new.dtype}")
+    k_cache, v_cache, k_new, v_new = (_rows_contiguous(t) for t in (k_cache, v_cache, k_new, v_new))
+    L_old, n = k_cache.shape[1], k_new.shape[1]
+    k_dst, k_in_place = _arena_target(k_cache, n)
+    v_dst, v_in_place = _arena_target(v_cache, n)
+    if L_old + n == 0:
+        return k_dst, v_dst
+    _launch_kv_append(k_cache, v_cache, k_new, v_new, k_dst, v_dst, k_in_place, v_in_place)
     return k_dst, v_dst
 
 

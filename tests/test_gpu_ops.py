@@ -286,3 +286,39 @@ print("SPLIT_OK")
     env = dict(os.environ, PCV_SPLIT="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode == 0 and "SPLIT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_kv_arena_decode_loop_in_place_append_on_device():
+    """Decode-style loop: every step feeds the returned cache back in.  The appended cache must equal torch.cat
+    bit for bit, earlier results must stay intact (functional contract), and attention over the arena's strided
+    row range must equal attention over a contiguous copy."""
+    from perceiver_io_b200 import ops
+
+    B, H, d = 2, 4, 64
+    g = torch.Generator().manual_seed(21)
+    k = torch.zeros(B, 0, H * d, dtype=torch.bfloat16, device="cuda")
+    v = torch.zeros(B, 0, H * d, dtype=torch.bfloat16, device="cuda")
+    ks, vs, held = [], [], []
+    for step in range(70):
+        n = 130 if step == 0 else 1           # prompt, then one token per step
+        kn = torch.randn(B, n, H * d, generator=g).bfloat16().cuda()
+        vn = torch.randn(B, n, H * d, generator=g).bfloat16().cuda()
+        ks.append(kn)
+        vs.append(vn)
+        k, v = ops.kv_append(k, v, kn, vn)
+        assert torch.equal(k, torch.cat(ks, 1)) and torch.equal(v, torch.cat(vs, 1))
+        if step % 16 == 0:
+            held.append((k, k.clone()))
+    assert k._base is not None and not k.is_contiguous()          # a row range of an arena with head-room
+    for view, snap in held:                                         # nothing handed out earlier has changed
+        assert torch.equal(view, snap)
+    q = torch.randn(B, 1, H * d, generator=g).bfloat16().cuda()
+    for impl in ("auto", "simt"):
+        a = ops.attention(q, k, v, H, d ** -0.5, impl=impl)
+        b = ops.attention(q, k.contiguous(), v.contiguous(), H, d ** -0.5, impl=impl)
+        assert torch.equal(a, b), impl
+    assert_close(a, oracle_core(q, k, v, H, d ** -0.5), REL_SIMT, "arena attention")
+    # a second continuation of an older cache must not disturb the newest one
+    old_k, old_snap = held[1]
+    branch, _ = ops.kv_append(old_k, old_k, torch.ones_like(kn), torch.ones_like(kn))
+    assert torch.equal(k, torch.cat(ks, 1)) and torch.equal(branch[:, :-1], old_snap)
