@@ -212,6 +212,51 @@ typedef struct pcv_peer_combine_params {
   int32_t reserved;
 } pcv_peer_combine_params;
 
+/*
+ * Fused K/V producer of the cross-attention module: replaces, for inference,
+ *   perceiver/model/core/modules.py:226      x_kv = self.kv_norm(x_kv)
+ *   perceiver/model/core/modules.py:114-115  k = self.k_proj(x_kv); v = self.v_proj(x_kv)
+ * with ONE pass over the raw input on the tcgen05 tensor cores.  LayerNorm is folded around the GEMM:
+ *     LN(x) W^T + b  =  rstd * ( x (gamma.W)^T - mean * s ) + t
+ * The caller prepares, once per set of weights,
+ *     w      : (n_k + n_v, C)  = [gamma.Wk ; gamma.Wv] rounded to `dtype`, row-major (the nn.Linear layout)
+ *     col_st : (n_k + n_v, 2) f32, per output column (s, t):  s = sum_c w[n, c] (of the ROUNDED w),
+ *              t = sum_c beta_c W[n, c] + bias[n]
+ * and, per call, the row statistics with pcv_ln_stats:  row_stats (rows, 2) f32 = (mean, 1/sqrt(var + eps)).
+ * row_stats == NULL means "no LayerNorm": out = x w^T + t (a plain projection with bias).
+ *   x      : (rows, C) with an element row stride (rows = B*M flattened)
+ *   k_out  : (rows, n_k), v_out : (rows, n_v), each with its own row stride — the un-rotated, pre-head-split
+ *            K / V rows the reference would have produced (and caches, modules.py:117-121)
+ * Constraints (else PCV_ERR_UNSUPPORTED; the host side then uses the library GEMM): C, n_v and the strides multiples
+ * of 8 elements, n_k a multiple of 64, 16-byte aligned pointers.
+ */
+typedef struct pcv_kvproj_params {
+  const void* x;
+  const void* w;
+  const float* col_st;
+  const float* row_stats;
+  void* k_out;
+  void* v_out;
+  int64_t x_stride_row, k_stride_row, v_stride_row;
+  int64_t rows;
+  int32_t C, n_k, n_v;
+  int32_t dtype;       /* PCV_BF16 / PCV_F16 */
+  int32_t cta_group;   /* 0 = library default, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2) */
+  int32_t reserved;
+} pcv_kvproj_params;
+
+/* LayerNorm row statistics (nn.LayerNorm semantics: biased variance): stats[r] = (mean, 1/sqrt(var + eps)) */
+typedef struct pcv_ln_stats_params {
+  const void* x;       /* (rows, C) */
+  float* stats;        /* (rows, 2) f32 */
+  int64_t x_stride_row;
+  int64_t rows;
+  int32_t C;
+  float eps;
+  int32_t dtype;
+  int32_t reserved;
+} pcv_ln_stats_params;
+
 /* library / device introspection */
 typedef struct pcv_device_info {
   int32_t device;
@@ -234,6 +279,10 @@ PCV_API int pcv_attn_combine_peers(const pcv_peer_combine_params* p, void* strea
 PCV_API int pcv_partial_rescale(const pcv_rescale_params* p, void* stream);
 PCV_API int pcv_rotary_apply(const pcv_rotary_params* p, void* stream);
 PCV_API int pcv_kv_append(const pcv_kv_append_params* p, void* stream);
+/* 1 if pcv_kv_project covers this problem (alignment, widths, device), else 0 (reason via pcv_last_error) */
+PCV_API int pcv_kv_project_supported(const pcv_kvproj_params* p);
+PCV_API int pcv_ln_stats(const pcv_ln_stats_params* p, void* stream);
+PCV_API int pcv_kv_project(const pcv_kvproj_params* p, void* stream);
 
 /*
  * Live timing of the dominant kernel (bench.py's roofline leg): between pcv_profile_begin() and

@@ -32,6 +32,9 @@ EXPORTS = (
     "pcv_partial_rescale",
     "pcv_rotary_apply",
     "pcv_kv_append",
+    "pcv_kv_project_supported",
+    "pcv_ln_stats",
+    "pcv_kv_project",
     "pcv_launch_count",
     "pcv_debug_plan",
     "pcv_profile_begin",
@@ -125,6 +128,25 @@ class KvAppendParams(C.Structure):
     ]
 
 
+class KvProjParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("col_st", C.c_void_p), ("row_stats", C.c_void_p),
+        ("k_out", C.c_void_p), ("v_out", C.c_void_p),
+        ("x_stride_row", C.c_int64), ("k_stride_row", C.c_int64), ("v_stride_row", C.c_int64),
+        ("rows", C.c_int64),
+        ("C", C.c_int32), ("n_k", C.c_int32), ("n_v", C.c_int32),
+        ("dtype", C.c_int32), ("cta_group", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class LnStatsParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("stats", C.c_void_p),
+        ("x_stride_row", C.c_int64), ("rows", C.c_int64),
+        ("C", C.c_int32), ("eps", C.c_float), ("dtype", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("sm_major", C.c_int32), ("sm_minor", C.c_int32),
@@ -170,6 +192,12 @@ def lib() -> C.CDLL:
         l.pcv_profile_end.restype = C.c_int
         l.pcv_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         l.pcv_kv_append.argtypes = [C.POINTER(KvAppendParams), C.c_void_p]
+        l.pcv_kv_project_supported.argtypes = [C.POINTER(KvProjParams)]
+        l.pcv_kv_project_supported.restype = C.c_int
+        l.pcv_ln_stats.argtypes = [C.POINTER(LnStatsParams), C.c_void_p]
+        l.pcv_ln_stats.restype = C.c_int
+        l.pcv_kv_project.argtypes = [C.POINTER(KvProjParams), C.c_void_p]
+        l.pcv_kv_project.restype = C.c_int
         l.pcv_debug_plan.argtypes = [C.c_int32] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
         l.pcv_debug_plan.restype = C.c_int
         for name in ("pcv_get_device_info", "pcv_attn_supported_tcgen05", "pcv_attn_workspace_bytes",

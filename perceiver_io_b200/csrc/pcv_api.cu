@@ -194,4 +194,22 @@ int pcv_kv_append(const pcv_kv_append_params* p, void* stream) {
   return launch_kv_append(*p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int pcv_kv_project_supported(const pcv_kvproj_params* p) {
+  if (p == nullptr) return 0;
+  const char* why = "";
+  const bool ok = kv_project_supported(*p, &why);
+  if (!ok) set_error("kv_project not applicable: %s", why);
+  return ok ? 1 : 0;
+}
+
+int pcv_ln_stats(const pcv_ln_stats_params* p, void* stream) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "ln_stats: params is NULL");
+  return launch_ln_stats(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pcv_kv_project(const pcv_kvproj_params* p, void* stream) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "kv_project: params is NULL");
+  return launch_kv_project(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

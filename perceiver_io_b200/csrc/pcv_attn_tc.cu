@@ -26,7 +26,9 @@
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
+#include <algorithm>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <tuple>
 #include <vector>
@@ -44,6 +46,12 @@ constexpr int kThreads = 384;  // 12 warps: 8 softmax + MMA + TMA + 2 idle (fill
 constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr float kRescaleThreshold = 8.f;  // log2 units
+// compile-time experiment knob: column pairs (of every 4) of an optimistic tile whose 2^x runs on the FMA pipes
+// (exp2_poly2) instead of MUFU.  0 in the product (measured slower at 1 of 4).
+#ifndef PCV_POLY_QUARTERS
+#define PCV_POLY_QUARTERS 0
+#endif
+constexpr int kPolyQuarter = PCV_POLY_QUARTERS;
 
 struct Segment {
   int b, h;
@@ -77,10 +85,8 @@ struct TcParams {
   int write_partial;
   float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
   float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
-  int rows_per_unit;                // query rows per work unit: 256 (two tiles per CTA), 128 (wide-dv), 512 (CTA pair)
+  int rows_per_unit;                // query rows per work unit: 256 (two tiles per CTA) or 128 (wide-dv / big-head)
   int slot_rows;                    // row stride of the partial slots (>= rows_per_unit)
-  int dbg;                          // developer experiments (PCV_DBG): 1 = softmax skips its math, 2 = no PV MMAs, 4 = no QK MMAs
-  int poly;                         // 1: every 4th column pair uses the FMA-pipe exp2 (optimistic tiles only)
   int optimistic;                   // 1: exponentiate against the current reference, verify the range afterwards
   int mmaopt;                       // attn_tc_kernel issuer: bit 0 = overlapped barrier probes, bit 1 = deferred kv_empty commits
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
@@ -157,7 +163,6 @@ struct TileCtx;
 __device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c);
 
 struct TileCtx {
-  uint32_t p_full_pair;  // 0: arrive on the local p_full[wg]; else shared::cluster address of the pair leader's p_full[wg]
   uint64_t* pv_bar;      // non-null: barrier (and parity) to wait on before rescaling O — kernels whose S(j) does not imply PV(j-1) done
   uint32_t pv_parity;
   uint32_t tS, tO;    // TMEM addresses (lane field included) of this thread's S / O row
@@ -177,10 +182,7 @@ __device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c) {
   // 4 arrivals per tile instead of 128 serialised updates of one shared-memory word
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
-    if (c.p_full_pair == 0)
-      mbar_arrive(&bar.p_full[c.wg]);
-    else
-      mbar_arrive_cluster(c.p_full_pair);
+    mbar_arrive(&bar.p_full[c.wg]);
   }
 }
 
@@ -421,21 +423,14 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const Segment& s
 
 template <int DQK, int DV, bool BF16>
 __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, int wg, int row, int seg_lo,
-                                             int seg_hi, int pair_rank = -1) {
-  // pair_rank < 0: single-CTA kernel.  Otherwise this CTA is rank `pair_rank` of a cta_group::2 pair: query tile
-  // `wg` of the pair spans 256 rows (128 per CTA) and the p_full / o_empty barriers live in the leader CTA.
-  const bool pair = pair_rank >= 0;
-  const int tile_rows = pair ? 2 * kTileM : kTileM;
-  const int row_in_unit = wg * tile_rows + (pair ? pair_rank * kTileM : 0) + row;
-  const uint32_t p_full_pair = pair ? mapa_cluster(smem_u32(&bar.p_full[wg]), 0) : 0u;
-  const uint32_t o_empty_pair = pair ? mapa_cluster(smem_u32(&bar.o_empty[wg]), 0) : 0u;
+                                             int seg_hi) {
+  const int row_in_unit = wg * kTileM + row;
   const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
   const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
   const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
   uint32_t n_s = 0, n_o = 0;
-  // loop-invariant dispatch, decided before the first barrier wait: 0 classic, 1 optimistic, 2 optimistic + FMA-pipe
-  // exp2 on a quarter of the columns, 3 protocol only (timing experiment)
-  const int mode = (p.dbg & 1) ? 3 : (p.optimistic ? (p.poly ? 2 : 1) : 0);
+  // loop-invariant dispatch, decided before the first barrier wait: 0 classic, 1 optimistic
+  const int mode = p.optimistic ? 1 : 0;
 
   for (int sg = seg_lo; sg < seg_hi; ++sg) {
     const Segment seg = p.segs[sg];
@@ -446,7 +441,6 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     st.l = 0.f;
     TileCtx c;
     c.tS = tS; c.tO = tO; c.wg = wg; c.row = row;
-    c.p_full_pair = p_full_pair;
     c.pv_bar = nullptr;
     c.pv_parity = 0;
     c.cshift = n + p.causal_shift;
@@ -469,16 +463,10 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
       ++n_s;
       tc_fence_after_sync();
       PCV_TRACE(p, wg, c.tt, 0, c.trace_on);
-      if (mode == 3) {  // timing experiment: protocol only
-        tc_fence_before_sync();
-        arrive_p_full(bar, c);
-        continue;
-      }
       if (masked_tile) {
         softmax_tile<DV, BF16, true>(p, bar, c, st);
       } else if (mode != 0 && !c.first_tile) {
-        const bool ok = mode == 2 ? softmax_tile_optimistic<DV, BF16, 1>(p, bar, c, st)
-                                  : softmax_tile_optimistic<DV, BF16, 0>(p, bar, c, st);
+        const bool ok = softmax_tile_optimistic<DV, BF16, kPolyQuarter>(p, bar, c, st);
         if (!ok) {
           // the reference must move: nothing was stored, redo on the classic path (max first)
           softmax_tile<DV, BF16, false>(p, bar, c, st);
@@ -496,12 +484,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     epilogue_row<DV, BF16>(p, seg, tO, n, row_in_unit, l, m_ref);
     tc_fence_before_sync();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-      if (!pair)
-        mbar_arrive(&bar.o_empty[wg]);
-      else
-        mbar_arrive_cluster(o_empty_pair);
-    }
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&bar.o_empty[wg]);
   }
 }
 
@@ -630,7 +613,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe0 = 0, n_oe1 = 0;
 
     auto issue_qk = [&](int i, uint32_t k_slot) {
-      if (leader && !(p.dbg & 4)) {
+      if (leader) {
         const uint64_t da = dq0 + (uint64_t)((i * C::kQTileBytes) >> 4);
         const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes) >> 4);
 #pragma unroll
@@ -641,7 +624,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
     };
     auto issue_pv = [&](int i, uint32_t v_slot, bool accumulate) {
-      if (leader && !(p.dbg & 2)) {
+      if (leader) {
         const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes) >> 4);
 #pragma unroll
         for (int kk = 0; kk < kTileN / 16; ++kk) {
@@ -775,692 +758,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
 
 // --------------------------------------------------------------------------------------------------
-// Split hand-off kernel (head dims <= 128).  Same roles, shared-memory ring and TMEM map as attn_tc_kernel;
-// what changes is the hand-over of P and who issues the MMAs:
-//   * the softmax row thread turns key columns [0,64) of the score tile into P_lo, hands it over, and works on
-//     columns [64,128) while the tensor pipe already runs P_lo V[0:64); after P_hi only half of P V and the next
-//     Q K^T remain on the chain  S ready -> softmax -> P ready -> P V + next Q K^T -> S ready;
-//   * each query tile has its own MMA issuing warp, so one tile's issuer never sits in a blocking tcgen05.mma of
-//     the other tile when its P arrives.
-// Accumulator rescales (rare: lazy reference) need every P V issued so far to be complete.  In the first half
-// that is implied by S(j) being ready (tcgen05.commit covers all earlier MMAs of the issuing thread, and
-// Q K^T(j) is issued after P V(j-1)); for the second half the issuer commits pv_lo[i] after P_lo V of every
-// tile (off the critical path: it would be waiting for P_hi anyway) and the rare path waits on that.
-// (Measured dead end, removed: also splitting Q K^T into two N = 64 halves so that the next tile's first half
-// overlaps the softmax of the second.  SS-mode MMAs re-read the 128 x 16 A slice from shared memory per
-// instruction, so N = 64 costs 6 KB per 32 tensor cycles — shared-memory bound, 1.11 PF)
-// --------------------------------------------------------------------------------------------------
-struct SplitBarriers {
-  uint64_t q_full, q_empty;
-  uint64_t kv_full[8], kv_empty[8];
-  uint64_t s_full[2], p_full[2][2], pv_lo[2], o_full[2], o_empty[2];
-  uint32_t tmem_base;
-  uint32_t issue_lock;  // held while an issuer queues its [P_hi V, next Q K^T] group (see the issuer loop)
-};
-
-constexpr int kHalfN = kTileN / 2;
-constexpr int kMmaWarp1 = 10;  // issuer of query tile 1 (query tile 0: kMmaWarp)
-
-struct HalfCtx {
-  uint64_t* p_bar;       // p_full[wg][half]
-  uint64_t* pv_bar;      // barrier whose phase `pv_parity` implies that every P V handed over so far has completed
-  uint32_t pv_parity;
-  uint32_t tS, tP, tO;   // TMEM addresses (lane field included): first S column of this half / first P column / O row
-  int j0;                // first key of the half
-  int cshift;            // key j (local) is causally masked for this row iff j > cshift
-  uint32_t mw0, mw1;     // padding bits of the 64 keys of the half
-  bool first;            // first half of the segment: no accumulator content yet
-};
-
-__device__ __forceinline__ void arrive_warp(uint64_t* b) {
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(b);
-}
-
-// classic half (max pass first): first half of a segment, masked halves, redo after an optimistic miss
-template <int DV, bool BF16, bool MASKED>
-__device__ __forceinline__ void softmax_half(const TcParams& p, const HalfCtx& c, RowState& st) {
-  uint32_t s[2][32];
-  tmem_ld32(c.tS + 0, s[0]);
-  tmem_ld32(c.tS + 32, s[1]);
-  tmem_wait_ld();
-
-  float m_tile;
-  float mul = p.scale_log2;
-  if (!MASKED) {
-    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      mx0 = max2(mx0, __uint_as_float(s[0][i]));
-      mx1 = max2(mx1, __uint_as_float(s[0][i + 1]));
-      mx2 = max2(mx2, __uint_as_float(s[1][i]));
-      mx3 = max2(mx3, __uint_as_float(s[1][i + 1]));
-    }
-    m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
-  } else {
-    const int oob_from = p.M - c.j0;
-    const int cmax = p.causal ? (c.cshift - c.j0) : 0x7fffffff;
-    float mx = -INFINITY;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const uint32_t word = q == 0 ? c.mw0 : c.mw1;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = q * 32 + i;
-        float tv = __uint_as_float(s[q][i]) * p.scale_log2;
-        if (((word >> i) & 1u) || col > cmax) tv = kMaskedScore;
-        if (col >= oob_from) tv = -INFINITY;
-        mx = fmaxf(mx, tv);
-        s[q][i] = __float_as_uint(tv);
-      }
-    }
-    m_tile = mx;
-    mul = 1.f;
-  }
-
-  const float m_new = fmaxf(st.m_ref, m_tile);
-  float alpha = 1.f;
-  bool moved = false;
-  if (m_new - st.m_ref > kRescaleThreshold) {
-    alpha = ex2(st.m_ref - m_new);
-    st.l *= alpha;
-    st.m_ref = m_new;
-    moved = !c.first;
-  }
-  if (__any_sync(0xffffffffu, moved)) {
-    if (c.pv_bar != nullptr) mbar_wait(c.pv_bar, c.pv_parity, 15);  // peek: consumed later by the normal wait
-    tc_fence_after_sync();
-#pragma unroll
-    for (int ch = 0; ch < DV / 32; ++ch) {
-      uint32_t o[32];
-      tmem_ld32(c.tO + ch * 32, o);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-      tmem_st32(c.tO + ch * 32, o);
-    }
-  }
-
-  float2 sum2 = make_float2(0.f, 0.f);
-  const float2 mul2 = make_float2(mul, mul);
-  const float2 negm2 = make_float2(-st.m_ref, -st.m_ref);
-  uint32_t pk[32];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float2 x = fma2(make_float2(__uint_as_float(s[q][i]), __uint_as_float(s[q][i + 1])), mul2, negm2);
-      const float2 e = make_float2(ex2(x.x), ex2(x.y));
-      sum2 = add2(sum2, e);
-      pk[q * 16 + (i >> 1)] = pack2(e.x, e.y, BF16);
-    }
-  }
-  tmem_st32(c.tP, pk);  // P (16-bit) of the 64 keys: 32 columns
-  st.l += sum2.x + sum2.y;
-  tmem_wait_st();
-  tc_fence_before_sync();
-  arrive_warp(c.p_bar);
-}
-
-// optimistic half: exponentiate against the current reference while the scores stream in; false = the
-// reference has to move (nothing stored), the caller redoes the half on the classic path
-template <int DV, bool BF16>
-__device__ __forceinline__ bool softmax_half_optimistic(const TcParams& p, const HalfCtx& c, RowState& st) {
-  uint32_t pk[32];
-  float2 sum2 = make_float2(0.f, 0.f);
-  const float2 mul2 = make_float2(p.scale_log2, p.scale_log2);
-  const float2 negm2 = make_float2(-st.m_ref, -st.m_ref);
-  uint32_t sa[32], sb[32];
-  tmem_ld32(c.tS + 0, sa);
-  tmem_wait_ld();
-  tmem_ld32(c.tS + 32, sb);
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    const float s0 = __uint_as_float(sa[i]), s1 = __uint_as_float(sa[i + 1]);
-    const float2 x = fma2(make_float2(s0, s1), mul2, negm2);
-    const float2 e = make_float2(ex2(x.x), ex2(x.y));
-    sum2 = add2(sum2, e);
-    pk[i >> 1] = pack2(e.x, e.y, BF16);
-  }
-  tmem_wait_ld();
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    const float s0 = __uint_as_float(sb[i]), s1 = __uint_as_float(sb[i + 1]);
-    const float2 x = fma2(make_float2(s0, s1), mul2, negm2);
-    const float2 e = make_float2(ex2(x.x), ex2(x.y));
-    sum2 = add2(sum2, e);
-    pk[16 + (i >> 1)] = pack2(e.x, e.y, BF16);
-  }
-  const float tsum = sum2.x + sum2.y;
-  if (__any_sync(0xffffffffu, !(tsum <= optimistic_limit<BF16>()))) return false;
-  tmem_st32(c.tP, pk);
-  st.l += tsum;
-  tmem_wait_st();
-  tc_fence_before_sync();
-  arrive_warp(c.p_bar);
-  return true;
-}
-
-template <int DQK, int DV, bool BF16>
-__device__ __forceinline__ void softmax_role_split(const TcParams& p, SplitBarriers& bar, int wg, int row,
-                                                   int seg_lo, int seg_hi) {
-  const int row_in_unit = wg * kTileM + row;
-  const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
-  const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
-  const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
-  uint32_t n_s = 0, n_o = 0, n_t = 0;  // consumed phases of s_full[wg] / o_full[wg]; tiles done (pv_lo[wg] parity)
-
-  for (int sg = seg_lo; sg < seg_hi; ++sg) {
-    const Segment seg = p.segs[sg];
-    if (wg == 1 && seg.ntile < 2) continue;
-    const int n = seg.q0 + row_in_unit;
-    RowState st;
-    st.m_ref = -INFINITY;
-    st.l = 0.f;
-    HalfCtx c;
-    c.tO = tO;
-    c.cshift = n + p.causal_shift;
-
-    for (int t = seg.t0; t < seg.t1; ++t) {
-      uint4 mw = make_uint4(0, 0, 0, 0);
-      if (p.pad_bits != nullptr)
-        mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
-      mbar_wait(&bar.s_full[wg], n_s & 1, 12);
-      ++n_s;
-      tc_fence_after_sync();
-      PCV_TRACE(p, wg, t - seg.t0, 0, row == 0 && sg == seg_lo);
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        c.j0 = t * kTileN + h * kHalfN;
-        c.tS = tS + (uint32_t)(h * kHalfN);      // scores of keys [64h, 64h+64)
-        c.tP = tS + (uint32_t)(h * kHalfN / 2);  // P over S columns [0,64), consumed by the time it is written
-        c.p_bar = &bar.p_full[wg][h];
-        c.first = (t == seg.t0) && (h == 0);
-        c.mw0 = h ? mw.z : mw.x;
-        c.mw1 = h ? mw.w : mw.y;
-        // S(t) ready => every P V up to tile t-1 complete; the second half also needs P_lo V of this tile
-        c.pv_bar = h ? &bar.pv_lo[wg] : nullptr;
-        c.pv_parity = n_t & 1;
-        // warp-uniform on purpose (tcgen05.ld/st are .sync.aligned)
-        const bool masked = __any_sync(0xffffffffu, (c.j0 + kHalfN > p.M) || ((c.mw0 | c.mw1) != 0u) ||
-                                                        (p.causal && (c.j0 + kHalfN - 1 > c.cshift)));
-        if (p.dbg & 1) {  // timing experiment: protocol only
-          tc_fence_before_sync();
-          arrive_warp(c.p_bar);
-          continue;
-        }
-        if (masked) {
-          softmax_half<DV, BF16, true>(p, c, st);
-        } else if (p.optimistic && !c.first) {
-          if (!softmax_half_optimistic<DV, BF16>(p, c, st)) softmax_half<DV, BF16, false>(p, c, st);
-        } else {
-          softmax_half<DV, BF16, false>(p, c, st);
-        }
-        PCV_TRACE(p, wg, t - seg.t0, h * 4 + 1, row == 0 && sg == seg_lo);
-      }
-      ++n_t;
-    }
-    const float l = st.l, m_ref = st.m_ref;
-
-    mbar_wait(&bar.o_full[wg], n_o & 1, 13);
-    ++n_o;
-    tc_fence_after_sync();
-    epilogue_row<DV, BF16>(p, seg, tO, n, row_in_unit, l, m_ref);
-    tc_fence_before_sync();
-    arrive_warp(&bar.o_empty[wg]);
-  }
-}
-
-template <int DQK, int DV, bool BF16>
-__global__ void __launch_bounds__(kThreads, 1)
-attn_tc_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                     const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
-  using C = Cfg<DQK, DV>;
-  static_assert(!C::kWide, "two query tiles per CTA");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* q_smem = smem;
-  uint8_t* kv_smem = smem + C::kQBytes;
-  SplitBarriers& bar = *reinterpret_cast<SplitBarriers*>(smem + C::kQBytes + C::kStages * C::kStageBytes);
-  static_assert(sizeof(SplitBarriers) <= C::kBarrierBytes, "barrier block");
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int seg_lo = p.cta_seg_begin[blockIdx.x];
-  const int seg_hi = p.cta_seg_begin[blockIdx.x + 1];
-
-  if (threadIdx.x == 0) {
-    mbar_init(&bar.q_full, 1);
-    mbar_init(&bar.q_empty, 2);  // both issuers
-    for (int i = 0; i < C::kStages; ++i) {
-      mbar_init(&bar.kv_full[i], 1);
-      mbar_init(&bar.kv_empty[i], 2);  // both issuers
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar.s_full[i], 1);
-      mbar_init(&bar.pv_lo[i], 1);
-      for (int h = 0; h < 2; ++h) mbar_init(&bar.p_full[i][h], 4);  // one arrive per softmax warp
-      mbar_init(&bar.o_full[i], 1);
-      mbar_init(&bar.o_empty[i], 4);
-    }
-    bar.issue_lock = 0u;
-    fence_mbar_init();
-  }
-  if (warp == kMmaWarp) {
-    tmem_alloc(&bar.tmem_base, 512);
-    tmem_relinquish();
-  }
-  if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-
-  if (warp < 8) {
-    reg_alloc<216>();
-    softmax_role_split<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
-  } else {
-    reg_dealloc<72>();
-  }
-  if (warp == kTmaWarp) {
-    // ===== TMA producer (as in attn_tc_kernel): Q once per segment, then K_j, V_j through the ring =====
-    const bool leader = elect_one();
-    uint32_t it = 0, n_q = 0;
-    for (int sg = seg_lo; sg < seg_hi; ++sg) {
-      const Segment seg = p.segs[sg];
-      const int bq = p.q_bcast ? 0 : seg.b;
-      mbar_wait(&bar.q_empty, (n_q & 1) ^ 1, 1);
-      ++n_q;
-      if (leader) {
-        mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(seg.ntile * C::kQTileBytes));
-        for (int i = 0; i < seg.ntile; ++i)
-          for (int bx = 0; bx < C::kQBoxes; ++bx)
-            tma_load_4d(q_smem + i * C::kQTileBytes + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64,
-                        seg.q0 + i * kTileM, seg.h, bq);
-      }
-      for (int t = seg.t0; t < seg.t1; ++t) {
-#pragma unroll
-        for (int kv = 0; kv < 2; ++kv) {
-          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
-          mbar_wait(&bar.kv_empty[slot], par ^ 1, 2 + kv);
-          if (leader) {
-            const int boxes = kv == 0 ? C::kQBoxes : C::kVBoxes;
-            mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(boxes * kBoxBytes));
-            for (int bx = 0; bx < boxes; ++bx)
-              tma_load_4d(kv_smem + slot * C::kStageBytes + bx * kBoxBytes, kv == 0 ? &tmap_k : &tmap_v,
-                          &bar.kv_full[slot], bx * 64, t * kTileN, seg.h, seg.b);
-          }
-          ++it;
-        }
-      }
-    }
-  } else if (warp == kMmaWarp || warp == kMmaWarp1) {
-    // ===== MMA issuer of query tile i (warp-converged, one elected lane issues) =====
-    const int i = warp == kMmaWarp ? 0 : 1;
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_qk = make_idesc(kTileM, kTileN, BF16, false);
-    constexpr uint32_t idesc_pv = make_idesc(kTileM, DV, BF16, true);
-    const uint32_t tS = bar.tmem_base + (uint32_t)(i * 128);
-    const uint32_t tO = bar.tmem_base + 256u + (uint32_t)(i * 128);
-    const uint64_t dq = make_smem_desc(smem_u32(q_smem + i * C::kQTileBytes), 16, 1024);
-    const uint64_t dk0 = make_smem_desc(smem_u32(kv_smem), 16, 1024);
-    const uint64_t dv0 = make_smem_desc(smem_u32(kv_smem), kBoxBytes, 1024);
-    uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe = 0;
-
-    auto issue_qk = [&](uint32_t k_slot) {
-      if (leader && !(p.dbg & 4)) {
-        const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes) >> 4);
-#pragma unroll
-        for (int kk = 0; kk < DQK / 16; ++kk) {
-          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          mma_ss(tS, dq + off, db + off, idesc_qk, kk > 0 ? 1u : 0u);
-        }
-      }
-    };
-    // O_i += P_h (128 x 64 keys, TMEM columns [32h, 32h+32) of the S tile) . V[64h .. 64h+64)
-    auto issue_pv = [&](int h, uint32_t v_slot, bool accumulate) {
-      if (leader && !(p.dbg & 2)) {
-        const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes + h * (kHalfN * 128)) >> 4);
-#pragma unroll
-        for (int kk = 0; kk < kHalfN / 16; ++kk)
-          mma_ts(tO, tS + h * (kHalfN / 2) + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
-                 (accumulate || kk > 0) ? 1u : 0u);
-      }
-    };
-    auto commit = [&](uint64_t* b) {
-      if (leader) tc_commit(b);
-    };
-
-    for (int sg = seg_lo; sg < seg_hi; ++sg) {
-      const Segment seg = p.segs[sg];
-      const bool active = i < seg.ntile;  // an idle issuer still walks the ring: every kv_empty / q_empty needs both
-      const int nt = seg.t1 - seg.t0;
-      mbar_wait(&bar.q_full, n_q & 1, 4);
-      ++n_q;
-
-      uint32_t k_slot = it % C::kStages;
-      mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 5);
-      ++it;
-      tc_fence_after_sync();
-      if (active) {
-        issue_qk(k_slot);
-        commit(&bar.s_full[i]);
-      }
-      commit(&bar.kv_empty[k_slot]);
-
-      for (int j = 0; j < nt; ++j) {
-        const uint32_t v_slot = it % C::kStages;
-        mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
-        ++it;
-        const bool more = (j + 1 < nt);
-        if (active) {
-          if (j == 0) {
-            mbar_wait(&bar.o_empty[i], (n_oe & 1) ^ 1, 7);
-            ++n_oe;
-          }
-          PCV_TRACE(p, 2, j, 0, leader && sg == seg_lo && i == 0);
-          mbar_wait(&bar.p_full[i][0], n_p0 & 1, 8);
-          ++n_p0;
-          tc_fence_after_sync();
-          PCV_TRACE(p, 2, j, 1, leader && sg == seg_lo && i == 0);
-          issue_pv(0, v_slot, j > 0);
-          commit(&bar.pv_lo[i]);
-          PCV_TRACE(p, 2, j, 2, leader && sg == seg_lo && i == 0);
-        }
-        if (more) {
-          k_slot = it % C::kStages;
-          mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
-          ++it;
-        }
-        if (active) {
-          mbar_wait(&bar.p_full[i][1], n_p1 & 1, 11);
-          ++n_p1;
-          // The two issuers must not interleave their [P_hi V, next Q K^T] groups MMA by MMA: both score tiles
-          // would then complete together, the two softmax warpgroups would run in lock-step and the tensor pipe
-          // and the exponent pipe would take turns idling (measured: 0.98 PF).  Queueing each group as a unit
-          // keeps the tiles at least one group apart.
-          if (leader) {
-            while (atomicCAS(&bar.issue_lock, 0u, 1u) != 0u) {
-            }
-          }
-          __syncwarp();
-          tc_fence_after_sync();
-          PCV_TRACE(p, 2, j, 3, leader && sg == seg_lo && i == 0);
-          issue_pv(1, v_slot, true);
-        }
-        commit(&bar.kv_empty[v_slot]);
-        if (more) {
-          if (active) {
-            issue_qk(k_slot);
-            commit(&bar.s_full[i]);
-          }
-          commit(&bar.kv_empty[k_slot]);
-        }
-        if (active) {
-          if (leader) atomicExch(&bar.issue_lock, 0u);
-          __syncwarp();
-        }
-        PCV_TRACE(p, 2, j, 4, leader && sg == seg_lo && i == 0);
-      }
-      commit(&bar.q_empty);
-      if (active) commit(&bar.o_full[i]);
-    }
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == kMmaWarp) {
-    tc_fence_after_sync();
-    tmem_dealloc(bar.tmem_base, 512);
-  }
-}
-
-// --------------------------------------------------------------------------------------------------
-// CTA-pair kernel (cta_group::2): a cluster of two CTAs on one TPC works on 512 query rows of one (b,h).
-// Every tcgen05.mma is M = 256 (128 rows from each CTA) and each CTA supplies only HALF of the B operand —
-// keys [64r, 64r+64) of the K tile for Q K^T, channels [64r, 64r+64) of the V tile for P V — so per SM the
-// shared-memory operand traffic, the TMA fill and the L2->SM traffic of K/V are all halved relative to the
-// single-CTA kernel (whose SS-mode Q K^T sits exactly on the 128 B/clk shared-memory ceiling).
-// Rank 0 (leader) issues all MMAs; completion is multicast to both CTAs with tcgen05.commit; both CTAs' TMA
-// transactions and softmax arrivals are counted on the leader's barriers.  dv is 128 (padded) in this kernel.
-// --------------------------------------------------------------------------------------------------
-template <int DQK>
-struct PairCfg {
-  static constexpr int DV = 128;
-  static constexpr int kQBoxes = DQK / 64;
-  static constexpr int kQTileBytes = kQBoxes * kBoxBytes;        // 128 rows x DQK
-  static constexpr int kQBytes = 2 * kQTileBytes;
-  static constexpr int kKHalfBytes = kQBoxes * (kBoxBytes / 2);  // 64 keys x DQK: kQBoxes boxes of 64 rows
-  static constexpr int kVHalfBytes = kBoxBytes;                  // 128 keys x 64 channels
-  static constexpr int kStageBytes = kKHalfBytes > kVHalfBytes ? kKHalfBytes : kVHalfBytes;
-  static constexpr int kBarrierBytes = 1024;
-  static constexpr int kMaxSmem = 232448 - 1024;
-  static constexpr int kStagesRaw = (kMaxSmem - kQBytes - kBarrierBytes) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kBarrierBytes + 1024;
-  static_assert(kStages >= 3, "ring too shallow");
-};
-
-template <int DQK, bool BF16>
-__global__ void __launch_bounds__(kThreads, 1)
-attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
-  using C = PairCfg<DQK>;
-  constexpr int DV = C::DV;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* q_smem = smem;
-  uint8_t* kv_smem = smem + C::kQBytes;
-  Barriers& bar = *reinterpret_cast<Barriers*>(smem + C::kQBytes + C::kStages * C::kStageBytes);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();  // 0 = leader
-  const int pair_id = blockIdx.x >> 1;
-  const int seg_lo = p.cta_seg_begin[pair_id];
-  const int seg_hi = p.cta_seg_begin[pair_id + 1];
-
-  if (threadIdx.x == 0) {
-    mbar_init(&bar.q_full, 2);    // leader: own arrive.expect_tx + the peer's remote arrive
-    mbar_init(&bar.q_empty, 1);   // multicast commit
-    for (int i = 0; i < C::kStages; ++i) {
-      mbar_init(&bar.kv_full[i], 2);
-      mbar_init(&bar.kv_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar.s_full[i], 1);
-      mbar_init(&bar.p_full[i], 8);   // one arrive per softmax warp, 4 warps x 2 CTAs
-      mbar_init(&bar.o_full[i], 1);
-      mbar_init(&bar.o_empty[i], 8);
-    }
-    fence_mbar_init();
-  }
-  if (warp == kMmaWarp) {
-    tmem_alloc_pair(&bar.tmem_base, 512);
-    tmem_relinquish_pair();
-  }
-  if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-  }
-  tc_fence_before_sync();
-  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
-  tc_fence_after_sync();
-
-  if (warp < 8) {
-    reg_alloc<216>();
-    softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi, (int)rank);
-  } else {
-    reg_dealloc<72>();
-  }
-
-  if (warp == kTmaWarp) {
-    // ===== TMA producer (both CTAs): own Q tiles, own half of every K / V tile; bytes counted on the leader =====
-    const bool leader_lane = elect_one();
-    const uint32_t q_full_leader = mapa_cluster(smem_u32(&bar.q_full), 0);
-    uint32_t it = 0, n_q = 0;
-    for (int sg = seg_lo; sg < seg_hi; ++sg) {
-      const Segment seg = p.segs[sg];
-      const int bq = p.q_bcast ? 0 : seg.b;
-      mbar_wait(&bar.q_empty, (n_q & 1) ^ 1, 1);
-      ++n_q;
-      if (leader_lane) {
-        if (rank == 0)
-          mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(2 * seg.ntile * C::kQTileBytes));
-        else
-          mbar_arrive_cluster(q_full_leader);
-        for (int i = 0; i < seg.ntile; ++i)
-          for (int bx = 0; bx < C::kQBoxes; ++bx)
-            tma_load_4d_pair(q_smem + i * C::kQTileBytes + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64,
-                             seg.q0 + i * 2 * kTileM + (int)rank * kTileM, seg.h, bq);
-      }
-      for (int t = seg.t0; t < seg.t1; ++t) {
-        {
-          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
-          mbar_wait(&bar.kv_empty[slot], par ^ 1, 2);
-          if (leader_lane) {
-            if (rank == 0)
-              mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(2 * C::kKHalfBytes));
-            else
-              mbar_arrive_cluster(mapa_cluster(smem_u32(&bar.kv_full[slot]), 0));
-#pragma unroll
-            for (int bx = 0; bx < C::kQBoxes; ++bx)  // K half: 64 keys x 64 channels per box
-              tma_load_4d_pair(kv_smem + slot * C::kStageBytes + bx * (kBoxBytes / 2), &tmap_k, &bar.kv_full[slot],
-                               bx * 64, t * kTileN + (int)rank * 64, seg.h, seg.b);
-          }
-          ++it;
-        }
-        {
-          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
-          mbar_wait(&bar.kv_empty[slot], par ^ 1, 3);
-          if (leader_lane) {
-            if (rank == 0)
-              mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(2 * C::kVHalfBytes));
-            else
-              mbar_arrive_cluster(mapa_cluster(smem_u32(&bar.kv_full[slot]), 0));
-            // V half: all 128 keys, channels [64*rank, 64*rank + 64)
-            tma_load_4d_pair(kv_smem + slot * C::kStageBytes, &tmap_v, &bar.kv_full[slot], (int)rank * 64, t * kTileN,
-                             seg.h, seg.b);
-          }
-          ++it;
-        }
-      }
-    }
-  } else if (warp == kMmaWarp && rank == 0) {
-    // ===== MMA issuer (leader CTA only) =====
-    const bool leader_lane = elect_one();
-    constexpr uint32_t idesc_qk = make_idesc(2 * kTileM, kTileN, BF16, false);
-    constexpr uint32_t idesc_pv = make_idesc(2 * kTileM, DV, BF16, true);
-    const uint32_t tmem = bar.tmem_base;
-    const uint64_t dq0 = make_smem_desc(smem_u32(q_smem), 16, 1024);
-    const uint64_t dk0 = make_smem_desc(smem_u32(kv_smem), 16, 1024);
-    const uint64_t dv0 = make_smem_desc(smem_u32(kv_smem), kBoxBytes, 1024);
-    uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe0 = 0, n_oe1 = 0;
-
-    auto issue_qk = [&](int i, uint32_t k_slot) {
-      if (leader_lane && !(p.dbg & 4)) {
-        const uint64_t da = dq0 + (uint64_t)((i * C::kQTileBytes) >> 4);
-        const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes) >> 4);
-#pragma unroll
-        for (int kk = 0; kk < DQK / 16; ++kk) {
-          const uint64_t offa = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          const uint64_t offb = (uint64_t)(((kk >> 2) * (kBoxBytes / 2) + (kk & 3) * 32) >> 4);
-          mma_ss_pair(tmem + i * 128, da + offa, db + offb, idesc_qk, kk > 0 ? 1u : 0u);
-        }
-      }
-    };
-    auto issue_pv = [&](int i, uint32_t v_slot, bool accumulate) {
-      if (leader_lane && !(p.dbg & 2)) {
-        const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes) >> 4);
-#pragma unroll
-        for (int kk = 0; kk < kTileN / 16; ++kk)
-          mma_ts_pair(tmem + 256 + i * 128, tmem + i * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
-                      (accumulate || kk > 0) ? 1u : 0u);
-      }
-    };
-    auto commit = [&](uint64_t* b) {
-      if (leader_lane) tc_commit_pair(b, 3);
-    };
-
-    for (int sg = seg_lo; sg < seg_hi; ++sg) {
-      const Segment seg = p.segs[sg];
-      const bool two = seg.ntile == 2;
-      const int nt = seg.t1 - seg.t0;
-      mbar_wait(&bar.q_full, n_q & 1, 4);
-      ++n_q;
-
-      uint32_t k_slot = it % C::kStages;
-      mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 5);
-      ++it;
-      tc_fence_after_sync();
-      issue_qk(0, k_slot);
-      commit(&bar.s_full[0]);
-      if (two) {
-        issue_qk(1, k_slot);
-        commit(&bar.s_full[1]);
-      }
-      commit(&bar.kv_empty[k_slot]);
-
-      for (int j = 0; j < nt; ++j) {
-        const uint32_t v_slot = it % C::kStages;
-        mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
-        ++it;
-        if (j == 0) {
-          mbar_wait(&bar.o_empty[0], (n_oe0 & 1) ^ 1, 7);
-          ++n_oe0;
-        }
-        mbar_wait(&bar.p_full[0], n_p0 & 1, 8);
-        ++n_p0;
-        tc_fence_after_sync();
-        issue_pv(0, v_slot, j > 0);
-        const bool more = (j + 1 < nt);
-        if (more) {
-          k_slot = it % C::kStages;
-          mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
-          ++it;
-          tc_fence_after_sync();
-          issue_qk(0, k_slot);
-          commit(&bar.s_full[0]);
-        }
-        if (two) {
-          if (j == 0) {
-            mbar_wait(&bar.o_empty[1], (n_oe1 & 1) ^ 1, 10);
-            ++n_oe1;
-          }
-          mbar_wait(&bar.p_full[1], n_p1 & 1, 11);
-          ++n_p1;
-          tc_fence_after_sync();
-          issue_pv(1, v_slot, j > 0);
-        }
-        commit(&bar.kv_empty[v_slot]);
-        if (more) {
-          if (two) {
-            issue_qk(1, k_slot);
-            commit(&bar.s_full[1]);
-          }
-          commit(&bar.kv_empty[k_slot]);
-        }
-      }
-      commit(&bar.q_empty);
-      commit(&bar.o_full[0]);
-      if (two) commit(&bar.o_full[1]);
-    }
-  }
-
-  tc_fence_before_sync();
-  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its pair can still touch its memory / barriers
-  if (warp == kMmaWarp) {
-    tc_fence_after_sync();
-    tmem_dealloc_pair(bar.tmem_base, 512);
-  }
-}
-
-
-// --------------------------------------------------------------------------------------------------
 // Big-head kernel: qk head dims up to 512 and v head dims up to 256 per pass (the optical-flow encoder /
 // decoder geometry, 322 and 512 channels per head).  One query tile (128 rows) per CTA.  Q and K stream through
 // shared memory in 128-channel chunks (Q is re-streamed from L2 for every key tile) and S accumulates over the
@@ -1538,7 +835,6 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       st.l = 0.f;
       TileCtx c;
       c.tO = tO; c.row = row;
-      c.p_full_pair = 0;
       c.pv_bar = &bb.pv_done;
       c.cshift = n + p.causal_shift;
       c.trace_on = false;
@@ -1634,7 +930,7 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(&bb.item_full[slot], (it / kBigItems) & 1, 5);
         ++it;
         tc_fence_after_sync();
-        if (leader && !(p.dbg & 4)) {
+        if (leader) {
           const uint64_t da = d0 + (uint64_t)((slot * kBigItemBytes) >> 4);
           const uint64_t db = da + (uint64_t)((2 * kBoxBytes) >> 4);
 #pragma unroll
@@ -1664,7 +960,7 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         mbar_wait(&bar.p_full[buf], (n_pvi >> 1) & 1, 8);
         tc_fence_after_sync();
-        if (leader && !(p.dbg & 2)) {
+        if (leader) {
           const uint64_t db = dv0 + (uint64_t)((slot * kBigItemBytes) >> 4);
 #pragma unroll
           for (int kk = 0; kk < kTileN / 16; ++kk)
@@ -1762,10 +1058,12 @@ struct Plan {
   Segment* d_segs = nullptr;
   int* d_cta = nullptr;
   UnitRec* d_units = nullptr;
+  int dev = 0;
+  uint64_t seq = 0;  // last use (LRU eviction)
 };
 
 void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms, int rows_per_unit, int rows_per_tile) {
-  // num_sms = number of workers (CTAs, or CTA pairs for the cta_group::2 kernel)
+  // num_sms = number of workers (CTAs)
   const int QB = (N + rows_per_unit - 1) / rows_per_unit;
   const int T = (M + kTileN - 1) / kTileN;
   const int BH = B * H;
@@ -1856,15 +1154,39 @@ int ensure_diag(int dev) {
 unsigned long long* g_trace_dev = nullptr;  // PCV_TRACE=1
 
 std::mutex g_plan_mu;
-std::map<std::tuple<int, int, int, int, int, int, int, int>, Plan*> g_plans;  // (device, B, H, N, M, workers, rows/unit, rows/tile)
+std::mutex g_attr_mu;  // guards the per-device cudaFuncSetAttribute flags of every kernel instantiation
+// The plan depends on (N, M) only through the number of query blocks, whether the last block holds one or two
+// query tiles, and the number of 128-key tiles, so the cache is keyed on those: a decode loop whose key count
+// grows by one per step hits the cache for 128 consecutive steps (no cudaMalloc / blocking copy on the step path).
+using PlanKey = std::tuple<int, int, int, int, int, int, int, int, int>;  // device, B, H, QB, last ntile, T, workers, rows/unit, rows/tile
+std::map<PlanKey, std::shared_ptr<Plan>> g_plans;
+uint64_t g_plan_seq = 0;
+constexpr size_t kMaxPlans = 256;
 
 struct Mode {
   int rows_per_unit, rows_per_tile, slot_rows;
-  bool pair;
   bool big;  // big-head kernel (qk head dim > 128 or v head dim > 256)
 };
 
-int get_plan(int B, int H, int N, int M, const Mode& mode, Plan** out) {
+void free_plan_tables(Plan& pl) {
+  // a kernel in flight on ANY stream of the plan's device may still read the tables
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != pl.dev) cudaSetDevice(pl.dev);
+  cudaDeviceSynchronize();
+  cudaFree(pl.d_segs);
+  cudaFree(pl.d_cta);
+  cudaFree(pl.d_units);
+  pl.d_segs = nullptr;
+  pl.d_cta = nullptr;
+  pl.d_units = nullptr;
+  if (cur != pl.dev) cudaSetDevice(cur);
+}
+
+// The returned shared_ptr keeps the host-side plan alive for the caller even if another thread evicts it; the
+// device tables of an evicted plan are released only after a synchronize of their device, and eviction removes
+// the least recently used half (never the entry being returned).
+int get_plan(int B, int H, int N, int M, const Mode& mode, std::shared_ptr<Plan>* out) {
   int dev = 0;
   PCV_CHECK_CUDA(cudaGetDevice(&dev));
   int sms = 0;
@@ -1874,14 +1196,20 @@ int get_plan(int B, int H, int N, int M, const Mode& mode, Plan** out) {
     int rc = ensure_diag(dev);
     if (rc != PCV_OK) return rc;
   }
-  if (mode.pair) sms /= 2;  // workers are CTA pairs
-  auto key = std::make_tuple(dev, B, H, N, M, sms, mode.rows_per_unit, mode.rows_per_tile);
+  const int QB = (N + mode.rows_per_unit - 1) / mode.rows_per_unit;
+  const int T = (M + kTileN - 1) / kTileN;
+  const int last_ntile =
+      (mode.rows_per_unit > mode.rows_per_tile && (N - (QB - 1) * mode.rows_per_unit) > mode.rows_per_tile) ? 2 : 1;
+  const PlanKey key = std::make_tuple(dev, B, H, QB, last_ntile, T, sms, mode.rows_per_unit, mode.rows_per_tile);
   auto it = g_plans.find(key);
   if (it != g_plans.end()) {
+    it->second->seq = ++g_plan_seq;
     *out = it->second;
     return PCV_OK;
   }
-  Plan* pl = new Plan();
+  auto pl = std::make_shared<Plan>();
+  pl->dev = dev;
+  pl->seq = ++g_plan_seq;
   build_plan(*pl, B, H, N, M, sms, mode.rows_per_unit, mode.rows_per_tile);
   PCV_CHECK_CUDA(cudaMalloc(&pl->d_segs, sizeof(Segment) * pl->segs.size()));
   PCV_CHECK_CUDA(cudaMalloc(&pl->d_cta, sizeof(int) * pl->cta_seg_begin.size()));
@@ -1892,15 +1220,19 @@ int get_plan(int B, int H, int N, int M, const Mode& mode, Plan** out) {
     PCV_CHECK_CUDA(cudaMalloc(&pl->d_units, sizeof(UnitRec) * pl->units.size()));
     PCV_CHECK_CUDA(cudaMemcpy(pl->d_units, pl->units.data(), sizeof(UnitRec) * pl->units.size(), cudaMemcpyHostToDevice));
   }
-  if (g_plans.size() > 256) {  // bounded cache: drop everything (plans are cheap to rebuild)
-    cudaDeviceSynchronize();   // kernels in flight may still read the tables about to be freed
-    for (auto& kv : g_plans) {
-      cudaFree(kv.second->d_segs);
-      cudaFree(kv.second->d_cta);
-      cudaFree(kv.second->d_units);
-      delete kv.second;
+  if (g_plans.size() >= kMaxPlans) {
+    std::vector<uint64_t> seqs;
+    for (auto& kv : g_plans) seqs.push_back(kv.second->seq);
+    std::nth_element(seqs.begin(), seqs.begin() + seqs.size() / 2, seqs.end());
+    const uint64_t cut = seqs[seqs.size() / 2];
+    for (auto jt = g_plans.begin(); jt != g_plans.end();) {
+      if (jt->second->seq < cut) {
+        free_plan_tables(*jt->second);
+        jt = g_plans.erase(jt);
+      } else {
+        ++jt;
+      }
     }
-    g_plans.clear();
   }
   g_plans[key] = pl;
   *out = pl;
@@ -1944,38 +1276,26 @@ size_t slots_bytes(const Plan& pl, int DV, int slot_rows) {
 }
 
 Mode choose_mode(const pcv_attn_params& a) {
-  // The CTA-pair kernel is opt-in (impl = PCV_IMPL_TCGEN05_PAIR, or PCV_PAIR=1 in the environment): measured at
-  // the north-star shape it is currently slower than the single-CTA kernel (0.9 vs 1.2 PFLOP/s).
-  static const int pair_env = [] { const char* e = getenv("PCV_PAIR"); return e ? atoi(e) : 0; }();
-  const bool want_pair = pair_env || a.impl == PCV_IMPL_TCGEN05_PAIR;
   const int DV = pad64(a.dv);
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static const int force_big = [] { const char* e = getenv("PCV_FORCE_BIG"); return e ? atoi(e) : 0; }();  // experiment
-  if (pad64(a.dqk) > 128 || DV > 256 || force_big) return Mode{kTileM, kTileM, kTileM, false, true};
-  if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false, false};
-  if (want_pair && DV == 128 && a.N > kRowsPerUnit && sms >= 2 && (sms % 2) == 0)
-    return Mode{4 * kTileM, 2 * kTileM, 4 * kTileM, true, false};
-  return Mode{kRowsPerUnit, kTileM, kRowsPerUnit, false, false};
+  if (pad64(a.dqk) > 128 || DV > 256) return Mode{kTileM, kTileM, kTileM, true};
+  if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false};
+  return Mode{kRowsPerUnit, kTileM, kRowsPerUnit, false};
 }
 
 template <int DQK, int DV, bool BF16>
 int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk,
                const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
   using C = Cfg<DQK, DV>;
-  // two query tiles per CTA (head dims <= 128): PCV_SPLIT=1 selects the split hand-off kernel
-  static const int split_env = [] { const char* e = getenv("PCV_SPLIT"); return e ? atoi(e) : 0; }();
   auto kern = attn_tc_kernel<DQK, DV, BF16>;
-  if constexpr (!C::kWide) {
-    if (split_env) kern = attn_tc_split_kernel<DQK, DV, BF16>;
-  }
   static bool attr_set[64] = {};  // per instantiation and device
   int dev = 0;
   PCV_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   prof_mark_begin(stream);
   kern<<<pl.num_ctas, kThreads, C::kSmemBytes, stream>>>(tq, tk, tv, p);
@@ -1991,43 +1311,6 @@ int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, 
   return PCV_OK;
 }
 
-template <int DQK, bool BF16>
-int launch_pair(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk,
-                const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
-  using C = PairCfg<DQK>;
-  auto kern = attn_tc_pair_kernel<DQK, BF16>;
-  static bool attr_set[64] = {};
-  int dev = 0;
-  PCV_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pl.num_ctas);  // num_ctas counts CTA pairs in this mode
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = C::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  prof_mark_begin(stream);
-  PCV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, p));
-  prof_mark_end(stream);
-  count_launch();
-  if (pl.num_units > 0) {
-    dim3 grid(pl.num_units, p.slot_rows / 8);
-    tc_combine_kernel<128, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
-    PCV_CHECK_CUDA(cudaGetLastError());
-    count_launch();
-  }
-  return PCV_OK;
-}
-
 template <bool BF16>
 int launch_big(const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, TcParams& p,
                cudaStream_t stream) {
@@ -2035,9 +1318,12 @@ int launch_big(const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk, con
   static bool attr_set[64] = {};
   int dev = 0;
   PCV_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigSmemBytes));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   prof_mark_begin(stream);
   kern<<<pl.num_ctas, kBigThreads, kBigSmemBytes, stream>>>(tq, tk, tv, p);
@@ -2118,7 +1404,7 @@ bool attn_tc_supported(const pcv_attn_params& p, const char** why) {
 }
 
 int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
-  Plan* pl = nullptr;
+  std::shared_ptr<Plan> pl;
   const Mode mode = choose_mode(p);
   int rc = get_plan(p.B, p.H, p.N, p.M, mode, &pl);
   if (rc != PCV_OK) return rc;
@@ -2130,11 +1416,11 @@ int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
 }
 
 int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
-  Plan* pl = nullptr;
+  std::shared_ptr<Plan> pl;
   const int DQK = pad64(a.dqk), DV = pad64(a.dv);
   const Mode mode = choose_mode(a);
-  PCV_REQUIRE(mode.pair || a.impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
-              "tcgen05 pair kernel needs N > 256, dv <= 128 (padded to 128) and an even SM count");
+  PCV_REQUIRE(a.impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
+              "the cta_group::2 attention kernel was a measured dead end (0.91 vs 1.25 PFLOP/s) and is no longer built");
   int rc = get_plan(a.B, a.H, a.N, a.M, mode, &pl);
   if (rc != PCV_OK) return rc;
   size_t need = 0;
@@ -2158,15 +1444,10 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   p.write_partial = a.write_partial;
   p.rows_per_unit = mode.rows_per_unit;
   p.slot_rows = mode.slot_rows;
+  p.optimistic = 1;
+  p.mmaopt = 3;
+#ifdef PCV_ENABLE_TRACE  // developer build only (make TRACE=1)
   {
-    static const int opt = [] { const char* e = getenv("PCV_OPT"); return e ? atoi(e) : 1; }();
-    p.optimistic = opt;
-    static const int poly = [] { const char* e = getenv("PCV_POLY"); return e ? atoi(e) : 0; }();
-    p.poly = poly;
-    static const int mmaopt = [] { const char* e = getenv("PCV_MMAOPT"); return e ? atoi(e) : 3; }();
-    p.mmaopt = mmaopt;
-    static const int dbg = [] { const char* e = getenv("PCV_DBG"); return e ? atoi(e) : 0; }();
-    p.dbg = dbg;
     static const int trace = [] { const char* e = getenv("PCV_TRACE"); return e ? atoi(e) : 0; }();
     if (trace) {
       const size_t bytes = sizeof(unsigned long long) * (kTraceStamps + 8 * kTraceMaxCtas);
@@ -2175,6 +1456,7 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
       p.trace = g_trace_dev;
     }
   }
+#endif
   p.fin_o = a.part_o; p.fin_m = a.part_m; p.fin_l = a.part_l;
   char* ws = reinterpret_cast<char*>(a.workspace);
   const size_t nrows = (size_t)pl->num_slots * mode.slot_rows;
@@ -2198,8 +1480,7 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   const int Bq = a.q_stride_b == 0 ? 1 : a.B;
   rc = make_tmap(&tq, a.q, a.dtype, a.dqk, a.N, a.H, Bq, a.q_stride_n, a.q_stride_h, a.q_stride_b);
   if (rc != PCV_OK) return rc;
-  rc = make_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b,
-                 mode.pair ? kTileN / 2 : kTileN);  // the pair kernel loads 64-key halves of every K tile
+  rc = make_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b);
   if (rc != PCV_OK) return rc;
   rc = make_tmap(&tv, a.v, a.dtype, a.dv, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
   if (rc != PCV_OK) return rc;
@@ -2219,11 +1500,6 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
       if (rc != PCV_OK) return rc;
     }
     return PCV_OK;
-  }
-  if (mode.pair) {
-    if (DQK == 128)
-      return bf ? launch_pair<128, true>(a, *pl, tq, tk, tv, p, stream) : launch_pair<128, false>(a, *pl, tq, tk, tv, p, stream);
-    return bf ? launch_pair<64, true>(a, *pl, tq, tk, tv, p, stream) : launch_pair<64, false>(a, *pl, tq, tk, tv, p, stream);
   }
 #define PCV_TC_CASE(DQ, DVV)                                                                          \
   if (DQK == DQ && DV == DVV)                                                                         \

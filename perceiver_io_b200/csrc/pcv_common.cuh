@@ -91,5 +91,8 @@ int launch_combine_peers(const pcv_peer_combine_params& p, cudaStream_t stream);
 int launch_rescale(const pcv_rescale_params& p, cudaStream_t stream);
 int launch_rotary(const pcv_rotary_params& p, cudaStream_t stream);
 int launch_kv_append(const pcv_kv_append_params& p, cudaStream_t stream);
+int launch_ln_stats(const pcv_ln_stats_params& p, cudaStream_t stream);
+bool kv_project_supported(const pcv_kvproj_params& p, const char** why);
+int launch_kv_project(const pcv_kvproj_params& p, cudaStream_t stream);
 
 }  // namespace pcv

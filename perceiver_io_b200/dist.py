@@ -230,10 +230,11 @@ def cross_attention_sharded(module, x_q: torch.Tensor, x_kv_shard: torch.Tensor,
     then the attention core is merged across ranks and ``o_proj`` is applied replicated."""
     from .utils import ModuleOutput
 
+    from .modules import project_kv
+
     attn = module.attention
-    x_q = module.q_norm(x_q)
-    x_kv = module.kv_norm(x_kv_shard)
-    q, k, v = attn.q_proj(x_q), attn.k_proj(x_kv), attn.v_proj(x_kv)
+    q = attn.q_proj(module.q_norm(x_q))
+    k, v = project_kv(module, x_kv_shard)  # fused LayerNorm + K/V producer on the local shard
     o = sharded_attention(q, k, v, attn.num_heads, attn.dp_scale, m_total, m_offset, pad_mask_shard,
                           attn.causal_attention, group, kernels, merge=merge)
     return ModuleOutput(last_hidden_state=attn.o_proj(o), kv_cache=None)

@@ -102,27 +102,83 @@ class MultiHeadAttention(nn.Module):
         """x_q (B|1, N, D), x_kv (B, L, C), pad_mask (B, L_total) bool with True = padding.
         Returns ``ModuleOutput(last_hidden_state=(B, N, F), kv_cache=(k, v) | None)``; cached k/v are
         (B, L_total, channels), un-rotated and pre-head-split exactly like the reference's."""
-        if self.training and self.dropout.p > 0.0:
-            raise NotImplementedError(
-                "attention-probability dropout is not fused into the sm_100a kernel yet; "
-                "run with dropout=0.0 (SURVEY.md §8(f) rank 2)"
-            )
         q = self.q_proj(x_q)
         k = self.k_proj(x_kv)
         v = self.v_proj(x_kv)
+        return attend(self, q, k, v, pad_mask, rot_pos_emb_q, rot_pos_emb_k, kv_cache)
 
-        if kv_cache is not None:
-            k, v = ops.kv_append(kv_cache[0], kv_cache[1], k, v)
-            kv_cache = (k, v)
 
-        if rot_pos_emb_q is not None:
-            q = _rotate_rows(rot_pos_emb_q, q, self.num_heads)
-        k_att = k if rot_pos_emb_k is None else _rotate_rows(rot_pos_emb_k, k, self.num_heads)
+def attend(mha, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_mask=None, rot_pos_emb_q=None,
+           rot_pos_emb_k=None, kv_cache: Optional[KVCache] = None):
+    """Everything of ``MultiHeadAttention.forward`` after the q/k/v projections (reference modules.py:117-170):
+    cache append, rotary, fused attention, ``o_proj``.  ``mha`` is this package's module or a patched reference
+    one (only its attributes are used)."""
+    if mha.training and mha.dropout.p > 0.0:
+        raise NotImplementedError(
+            "attention-probability dropout is not fused into the sm_100a kernel yet; "
+            "run with dropout=0.0 (SURVEY.md §8(f) rank 2)"
+        )
+    if kv_cache is not None:
+        k, v = ops.kv_append(kv_cache[0], kv_cache[1], k, v)
+        kv_cache = (k, v)
 
-        o = ops.attention(q, k_att, v, self.num_heads, self.dp_scale, pad_mask=pad_mask,
-                          causal=self.causal_attention, impl=self.kernel_impl)
-        o = self.o_proj(o)
-        return ModuleOutput(last_hidden_state=o, kv_cache=kv_cache)
+    if rot_pos_emb_q is not None:
+        q = _rotate_rows(rot_pos_emb_q, q, mha.num_heads)
+    k_att = k if rot_pos_emb_k is None else _rotate_rows(rot_pos_emb_k, k, mha.num_heads)
+
+    o = ops.attention(q, k_att, v, mha.num_heads, mha.dp_scale, pad_mask=pad_mask,
+                      causal=mha.causal_attention, impl=getattr(mha, "kernel_impl", "auto"))
+    o = mha.o_proj(o)
+    return ModuleOutput(last_hidden_state=o, kv_cache=kv_cache)
+
+
+#: Policy of the fused K/V producer (LayerNorm + k_proj + v_proj as one tcgen05 GEMM, ``ops.kv_project``).
+#: ``min_rows``: below this many key rows the two library GEMMs are used (launch-bound either way).
+kv_producer_config = {"enabled": True, "min_rows": 512}
+
+
+def _fold_cache(owner: nn.Module, slot: str, norm: Optional[nn.Module], linears, dtype: torch.dtype):
+    """Folded weights of ``norm`` followed by ``linears`` (ops.fold_ln_linear), cached on ``owner`` and rebuilt
+    whenever a parameter was modified in place, replaced or moved (data_ptr / ``_version`` of every tensor)."""
+    tensors = []
+    if norm is not None:
+        tensors += [norm.weight, norm.bias]
+    for lin in linears:
+        tensors += [lin.weight, lin.bias]
+    key = (dtype,) + tuple((None if t is None else (t.data_ptr(), t._version)) for t in tensors)
+    hit = owner.__dict__.get(slot)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    w_cat, col_st = ops.fold_ln_linear(None if norm is None else norm.weight, None if norm is None else norm.bias,
+                                       [lin.weight for lin in linears], [lin.bias for lin in linears], dtype)
+    owner.__dict__[slot] = (key, w_cat, col_st)
+    return w_cat, col_st
+
+
+def project_kv(cross_attn, x_kv: torch.Tensor):
+    """``k_proj(kv_norm(x_kv)), v_proj(kv_norm(x_kv))`` of a CrossAttention (reference modules.py:226, :114-115).
+
+    Inference on bf16/fp16 CUDA rows goes through the fused producer (one pass over x_kv on the tensor cores,
+    LayerNorm folded into the GEMM epilogue, ``pcv_ln_stats`` + ``pcv_kv_project``); everything else — autograd,
+    fp32, widths TMA cannot address, tiny inputs — uses LayerNorm + the two ``nn.Linear`` (library GEMMs)."""
+    attn = cross_attn.attention
+    norm = cross_attn.kv_norm
+    n_k, n_v = attn.k_proj.out_features, attn.v_proj.out_features
+    needs_grad = torch.is_grad_enabled() and (x_kv.requires_grad or attn.k_proj.weight.requires_grad
+                                              or attn.v_proj.weight.requires_grad
+                                              or (norm.weight is not None and norm.weight.requires_grad))
+    rows = x_kv.numel() // max(x_kv.shape[-1], 1)
+    fused = (kv_producer_config["enabled"] and not needs_grad and rows >= kv_producer_config["min_rows"]
+             and isinstance(norm, nn.LayerNorm) and len(norm.normalized_shape) == 1
+             and norm.normalized_shape[0] == x_kv.shape[-1]
+             and attn.k_proj.weight.dtype == x_kv.dtype and not torch.is_autocast_enabled()
+             and ops.kv_project_supported(x_kv, n_k, n_v))
+    if not fused:
+        x = norm(x_kv)
+        return attn.k_proj(x), attn.v_proj(x)
+    w_cat, col_st = _fold_cache(cross_attn, "_pcv_kv_fold", norm if norm.weight is not None else None,
+                                [attn.k_proj, attn.v_proj], x_kv.dtype)
+    return ops.kv_project(x_kv, w_cat, col_st, n_k, n_v, eps=norm.eps)
 
 
 class CrossAttention(nn.Module):
@@ -172,10 +228,10 @@ class CrossAttention(nn.Module):
         x_q = self.q_norm(x_q)
         if x_kv is None:
             x_kv = torch.cat([self.kv_norm(x_kv_prefix), x_q], dim=1)
-        else:
-            x_kv = self.kv_norm(x_kv)
-        return self.attention(x_q, x_kv, pad_mask=pad_mask, rot_pos_emb_q=rot_pos_emb_q,
-                              rot_pos_emb_k=rot_pos_emb_k, kv_cache=kv_cache)
+            return self.attention(x_q, x_kv, pad_mask=pad_mask, rot_pos_emb_q=rot_pos_emb_q,
+                                  rot_pos_emb_k=rot_pos_emb_k, kv_cache=kv_cache)
+        k, v = project_kv(self, x_kv)
+        return attend(self.attention, self.attention.q_proj(x_q), k, v, pad_mask, rot_pos_emb_q, rot_pos_emb_k, kv_cache)
 
 
 class SelfAttention(nn.Module):

@@ -18,11 +18,12 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import AttnParams, CombineParams, KvAppendParams, RescaleParams, RotaryParams, PcvError, check
+from ._lib import (AttnParams, CombineParams, KvAppendParams, KvProjParams, LnStatsParams, RescaleParams, RotaryParams,
+                   PcvError, check)
 
 __all__ = [
     "attention", "attention_partial", "combine_partials", "rescale_partial_", "rotary", "kv_append",
-    "device_info", "tcgen05_supported",
+    "device_info", "tcgen05_supported", "ln_stats", "fold_ln_linear", "kv_project", "kv_project_supported",
 ]
 
 
@@ -435,3 +436,101 @@ def tcgen05_supported(q, k, v, num_heads: int, pad_mask=None, causal: bool = Fal
     ok = bool(_lib.lib().pcv_attn_supported_tcgen05(C.byref(p)))
     del keep
     return ok
+
+
+# --------------------------------------------------------------------------------------------------
+# fused K/V producer: LayerNorm folded around ONE tcgen05 GEMM that writes K and V
+# --------------------------------------------------------------------------------------------------
+def ln_stats(x: torch.Tensor, eps: float) -> torch.Tensor:
+    """Row statistics of nn.LayerNorm over the last dim of x (..., C): (rows, 2) float32 = (mean, rstd)."""
+    _require_cuda(x)
+    x2 = _rows2d(x)
+    stats = torch.empty(x2.shape[0], 2, dtype=torch.float32, device=x.device)
+    p = LnStatsParams()
+    p.x, p.stats = x2.data_ptr(), stats.data_ptr()
+    p.x_stride_row, p.rows, p.C, p.eps = x2.stride(0), x2.shape[0], x2.shape[1], float(eps)
+    p.dtype = _pcv_dtype(x2.dtype)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().pcv_ln_stats(C.byref(p), _stream()), "pcv_ln_stats")
+    return stats
+
+
+def _rows2d(x: torch.Tensor) -> torch.Tensor:
+    """(..., C) -> (rows, C) view with ONE row stride (copies only if the leading dims are not collapsible)."""
+    if x.dim() == 2:
+        return x if x.stride(1) == 1 else x.contiguous()
+    x2 = x if x.stride(-1) == 1 else x.contiguous()
+    try:
+        return x2.view(-1, x2.shape[-1])
+    except RuntimeError:
+        return x2.reshape(-1, x2.shape[-1])
+
+
+def fold_ln_linear(norm_weight, norm_bias, weights, biases, dtype: torch.dtype):
+    """Fold a LayerNorm's affine part into the Linear layers that follow it (host-side, once per set of weights).
+
+    ``weights``: list of (n_i, C) Linear weights applied to LN(x); ``biases``: matching list (entries may be None).
+    Returns ``(w_cat (sum n_i, C) in `dtype`, col_st (sum n_i, 2) float32)`` with
+    ``w_cat = gamma * W`` (rounded), ``s = rowsum(w_cat)`` of the ROUNDED weights and ``t = W @ beta + bias``, so that
+    ``LN(x) W^T + b == rstd * (x w_cat^T - mean * s) + t`` (include/pcv_attn.h, pcv_kvproj_params).
+    ``norm_weight`` / ``norm_bias`` None = no LayerNorm (``w_cat = W``, ``t = bias``)."""
+    w = torch.cat([wi.detach().float() for wi in weights], dim=0)
+    n, Cin = w.shape
+    b = torch.cat([(torch.zeros(wi.shape[0], device=w.device) if bi is None else bi.detach().float())
+                   for wi, bi in zip(weights, biases)])
+    if norm_weight is not None:
+        t = b + (w @ norm_bias.detach().float() if norm_bias is not None else 0.0)
+        w = w * norm_weight.detach().float()[None, :]
+    else:
+        t = b
+    w_cat = w.to(dtype).contiguous()
+    s = w_cat.float().sum(dim=1)
+    col_st = torch.stack([s, t], dim=1).contiguous()
+    return w_cat, col_st
+
+
+def _fill_kvproj(x2, w_cat, col_st, n_k, n_v, stats, k_out, v_out, cta_group=0) -> KvProjParams:
+    p = KvProjParams()
+    p.x, p.w, p.col_st = x2.data_ptr(), w_cat.data_ptr(), col_st.data_ptr()
+    p.row_stats = None if stats is None else stats.data_ptr()
+    p.k_out = None if k_out is None else k_out.data_ptr()
+    p.v_out = None if v_out is None else v_out.data_ptr()
+    p.x_stride_row = x2.stride(0)
+    p.k_stride_row = 0 if k_out is None else k_out.stride(0)
+    p.v_stride_row = 0 if v_out is None else v_out.stride(0)
+    p.rows, p.C, p.n_k, p.n_v = x2.shape[0], x2.shape[1], n_k, n_v
+    p.dtype = _pcv_dtype(x2.dtype)
+    p.cta_group = cta_group
+    return p
+
+
+def kv_project_supported(x: torch.Tensor, n_k: int, n_v: int) -> bool:
+    """True when ``kv_project`` covers (x, n_k, n_v): CUDA bf16/fp16 rows, widths/strides TMA can address."""
+    if not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16) or x.numel() == 0:
+        return False
+    C_in = x.shape[-1]
+    return C_in % 8 == 0 and n_k % 64 == 0 and n_v % 8 == 0 and (n_k + n_v) > 0
+
+
+def kv_project(x: torch.Tensor, w_cat: torch.Tensor, col_st: torch.Tensor, n_k: int, n_v: int,
+               eps: Optional[float] = 1e-5, cta_group: int = 0):
+    """K, V = LN(x) Wk^T + bk, LN(x) Wv^T + bv for x (..., C) through pcv_ln_stats + pcv_kv_project.
+
+    ``w_cat`` / ``col_st`` come from :func:`fold_ln_linear`; ``eps=None`` skips the LayerNorm (plain projection).
+    Returns contiguous (..., n_k) and (..., n_v) tensors in x's dtype (``None`` for a width of 0)."""
+    _require_cuda(x, w_cat, col_st)
+    if w_cat.dtype != x.dtype or w_cat.shape != (n_k + n_v, x.shape[-1]) or not w_cat.is_contiguous():
+        raise ValueError("kv_project: w_cat must be a contiguous (n_k + n_v, C) tensor in x's dtype")
+    if col_st.dtype != torch.float32 or col_st.shape != (n_k + n_v, 2) or not col_st.is_contiguous():
+        raise ValueError("kv_project: col_st must be a contiguous (n_k + n_v, 2) float32 tensor")
+    lead = x.shape[:-1]
+    x2 = _rows2d(x)
+    with torch.cuda.device(x.device):
+        stats = None if eps is None else ln_stats(x2, eps)
+        k_out = torch.empty(x2.shape[0], n_k, dtype=x.dtype, device=x.device) if n_k else None
+        v_out = torch.empty(x2.shape[0], n_v, dtype=x.dtype, device=x.device) if n_v else None
+        p = _fill_kvproj(x2, w_cat, col_st, n_k, n_v, stats, k_out, v_out, cta_group)
+        check(_lib.lib().pcv_kv_project(C.byref(p), _stream()), "pcv_kv_project")
+    k = None if k_out is None else k_out.view(*lead, n_k)
+    v = None if v_out is None else v_out.view(*lead, n_v)
+    return k, v

@@ -11,7 +11,7 @@ import types
 
 from torch import nn
 
-from .modules import MultiHeadAttention
+from .modules import CrossAttention, MultiHeadAttention
 
 _REQUIRED = ("q_proj", "k_proj", "v_proj", "o_proj", "dp_scale", "num_heads", "causal_attention", "dropout")
 
@@ -20,9 +20,16 @@ def _is_reference_mha(module: nn.Module) -> bool:
     return type(module).__name__ == "MultiHeadAttention" and all(hasattr(module, a) for a in _REQUIRED)
 
 
+def _is_reference_cross_attention(module: nn.Module) -> bool:
+    return (type(module).__name__ == "CrossAttention" and not isinstance(module, CrossAttention)
+            and all(hasattr(module, a) for a in ("q_norm", "kv_norm", "attention")))
+
+
 def patch(model: nn.Module, impl: str = "auto") -> int:
     """Route every MultiHeadAttention under ``model`` through the sm_100a kernels.
 
+    Reference ``CrossAttention`` modules (modules.py:173-230) are rebound as well so that their
+    ``kv_norm`` -> ``k_proj`` / ``v_proj`` chain runs through the fused K/V producer (``modules.project_kv``).
     Returns the number of attention modules rebound; idempotent."""
     count = 0
     for module in model.modules():
@@ -33,4 +40,6 @@ def patch(model: nn.Module, impl: str = "auto") -> int:
             module.kernel_impl = impl
             module.forward = types.MethodType(MultiHeadAttention.forward, module)
             count += 1
+        elif _is_reference_cross_attention(module):
+            module.forward = types.MethodType(CrossAttention.forward, module)
     return count

@@ -16,6 +16,7 @@ from typing import Optional
 import torch
 
 from . import ops
+from .modules import project_kv
 from .utils import ModuleOutput
 
 
@@ -49,21 +50,19 @@ def cross_attention_from_host(module, x_q: torch.Tensor, x_kv_host: torch.Tensor
         part_l = torch.empty(G, B, H, N, dtype=torch.float32, device=device)
         pad_dev = None if pad_mask is None else pad_mask.to(device, non_blocking=True)
 
-        staged = [None, None]   # double-buffered device staging of the raw chunk
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        # Double-buffered device staging of the raw chunk.  The buffers and their "compute done" events persist per
+        # device: they are allocated on the MAIN stream (the stream that computes on them; the copy stream waits for
+        # that point once), and EVERY reuse of a slot — across calls too — waits for the event recorded after the
+        # last kernel that read it, so a copy can never overwrite a chunk that is still being consumed.
+        st = _staging(device, B, chunk, x_kv_host.shape[2], prm.dtype, main, copy)
+        staged, ready, freed = st["bufs"], st["ready"], st["freed"]
 
         def issue_copy(i):
             a, b = bounds[i]
             slot = i & 1
             with torch.cuda.stream(copy):
-                if i >= 2:
-                    copy.wait_event(freed[slot])          # compute on the chunk that used this buffer is done
-                buf = staged[slot]
-                if buf is None or buf.shape[1] < b - a:
-                    buf = torch.empty(B, chunk, x_kv_host.shape[2], dtype=prm.dtype, device=device)
-                    staged[slot] = buf
-                view = buf[:, : b - a]
+                copy.wait_event(freed[slot])              # compute on the chunk that last used this buffer is done
+                view = staged[slot][:, : b - a]
                 # one contiguous (rows x C) block per batch row: a strided host slice would be staged through
                 # a pageable temporary by torch and serialise the pipeline
                 for bi in range(B):
@@ -77,8 +76,7 @@ def cross_attention_from_host(module, x_q: torch.Tensor, x_kv_host: torch.Tensor
                 views[i + 1] = issue_copy(i + 1)
             slot = i & 1
             main.wait_event(ready[slot])
-            x = module.kv_norm(views.pop(i))
-            k, v = attn.k_proj(x), attn.v_proj(x)
+            k, v = project_kv(module, views.pop(i))
             ops.attention_partial(q, k, v, H, attn.dp_scale, pad_mask=None if pad_dev is None else pad_dev[:, a:b],
                                   causal=False, m_total=M, m_offset=a, out=(part_o[i], part_m[i], part_l[i]))
             freed[slot].record(main)
@@ -90,6 +88,25 @@ def cross_attention_from_host(module, x_q: torch.Tensor, x_kv_host: torch.Tensor
 
 
 _streams = {}
+_staging_cache = {}
+
+
+def _staging(device, B, chunk, C, dtype, main, copy):
+    key = str(device)
+    st = _staging_cache.get(key)
+    if st is None or st["shape"] != (B, chunk, C) or st["dtype"] != dtype:
+        if st is not None:
+            # the old buffers go back to the main stream's pool only after the copy stream is done with them
+            for buf in st["bufs"]:
+                buf.record_stream(copy)
+        bufs = [torch.empty(B, chunk, C, dtype=dtype, device=device) for _ in range(2)]
+        allocated = torch.cuda.Event()
+        allocated.record(main)
+        copy.wait_event(allocated)  # earlier main-stream users of these memory blocks are finished
+        st = {"shape": (B, chunk, C), "dtype": dtype, "bufs": bufs,
+              "ready": [torch.cuda.Event(), torch.cuda.Event()], "freed": [torch.cuda.Event(), torch.cuda.Event()]}
+        _staging_cache[key] = st
+    return st
 
 
 def _copy_stream(device) -> torch.cuda.Stream:

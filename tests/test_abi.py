@@ -53,6 +53,8 @@ def test_ctypes_layout_matches_header(tmp_path):
         "pcv_peer_combine_params": _lib.PeerCombineParams,
         "pcv_kv_append_params": _lib.KvAppendParams,
         "pcv_device_info": _lib.DeviceInfo,
+        "pcv_kvproj_params": _lib.KvProjParams,
+        "pcv_ln_stats_params": _lib.LnStatsParams,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, cls in structs.items():
@@ -70,6 +72,14 @@ def test_ctypes_layout_matches_header(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_kv_project_validates_before_any_cuda_call():
+    lib = _lib.lib()
+    assert lib.pcv_kv_project(None, None) == 1 and b"NULL" in lib.pcv_last_error()
+    assert lib.pcv_ln_stats(None, None) == 1 and b"NULL" in lib.pcv_last_error()
+    p = _lib.KvProjParams()
+    assert lib.pcv_kv_project(ctypes.byref(p), None) == 1 and b"NULL" in lib.pcv_last_error()
 
 
 def test_ops_refuse_cpu_tensors():

@@ -2,13 +2,29 @@
 import pytest
 import torch
 
-from gpu_util import assert_close, oracle_core
+from gpu_util import assert_close, assert_parity, oracle_core, torch_core
 from oracle import mha_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+# Parity of the attention kernels is gated by gpu_util.assert_parity: the DERIVED bound of BASELINE.md §3 /
+# SURVEY.md §8(d), 2 * max|ref_bf16_eager - ref_fp64| + 1e-3 * max|ref_fp64|, measured per case.  The two
+# constants below only remain for comparisons that have no eager counterpart (kernel vs kernel, merged vs single).
 REL_SIMT = 6e-3
 REL_TC = 1.2e-2
+
+
+def test_torch_reference_on_device_is_the_cpu_oracle():
+    """gpu_util.torch_core (the fp64 / eager-bf16 yardstick evaluated on the GPU) restates the same lines as
+    oracle/mha_oracle.py; pin one to the other on a case with every mask type."""
+    q, k, v = _qkv(3, 40, 300, 2, 64, 64, Bq=1, seed=3)
+    pad = torch.zeros(3, 300, dtype=torch.bool)
+    pad[0, :37] = True
+    pad[1, :] = True
+    for causal in (False, True):
+        a = torch_core(q, k, v, 2, 0.125, pad, causal, torch.float64).cpu()
+        b = oracle_core(q, k, v, 2, 0.125, pad, causal)
+        assert (a - b).abs().max().item() <= 1e-12 * max(b.abs().max().item(), 1.0)
 
 
 def _qkv(B, N, M, H, dqk, dv, Bq=None, seed=0, q_gain=1.0, dtype=torch.bfloat16):
@@ -46,7 +62,7 @@ def test_attention_matches_oracle(shape, impl):
     scale = dqk ** -0.5
     out = ops.attention(q, k, v, H, scale, impl=impl)
     assert out.shape == (B, N, H * dv) and out.dtype == torch.bfloat16
-    assert_close(out, oracle_core(q, k, v, H, scale), REL_SIMT if impl == "simt" else REL_TC, f"{impl} {shape}")
+    assert_parity(out, q, k, v, H, scale, what=f"{impl} {shape}")
 
 
 @pytest.mark.parametrize("impl", ["simt", "auto"])
@@ -59,10 +75,9 @@ def test_masks_broadcast_and_degenerate_rows(impl):
     pad[0, :37] = True            # left padding
     pad[1, :] = True              # fully padded row -> uniform average over ALL M values
     pad[2, 250:] = True           # right padding across a tile boundary
-    rel = REL_SIMT if impl == "simt" else REL_TC
     for causal in (False, True):
         out = ops.attention(q, k, v, H, d ** -0.5, pad_mask=pad.cuda(), causal=causal, impl=impl)
-        assert_close(out, oracle_core(q, k, v, H, d ** -0.5, pad, causal), rel, f"{impl} causal={causal}")
+        assert_parity(out, q, k, v, H, d ** -0.5, pad, causal, what=f"{impl} causal={causal}")
     # the fully padded batch row equals the plain mean of its values
     mean_v = v[1].float().mean(0).cpu()
     assert_close(out[1, 0], mean_v, 2e-2, "uniform row")
@@ -73,11 +88,10 @@ def test_peaked_and_flat_softmax_regimes(impl):
     from perceiver_io_b200 import ops
 
     B, N, M, H, d = 1, 128, 4096, 2, 128
-    rel = REL_SIMT if impl == "simt" else REL_TC
     for gain, name in ((0.02, "flat"), (6.0, "peaked")):
         q, k, v = _qkv(B, N, M, H, d, d, seed=11, q_gain=gain)
         out = ops.attention(q, k, v, H, d ** -0.5, impl=impl)
-        assert_close(out, oracle_core(q, k, v, H, d ** -0.5), rel, f"{impl} {name}")
+        assert_parity(out, q, k, v, H, d ** -0.5, what=f"{impl} {name}")
 
 
 def test_fp32_inputs_are_rounded_to_bf16_at_the_boundary():
@@ -86,8 +100,7 @@ def test_fp32_inputs_are_rounded_to_bf16_at_the_boundary():
     q, k, v = _qkv(1, 16, 64, 2, 32, 32, dtype=torch.float32)
     out = ops.attention(q, k, v, 2, 32 ** -0.5)
     assert out.dtype == torch.float32
-    ref = oracle_core(q.bfloat16(), k.bfloat16(), v.bfloat16(), 2, 32 ** -0.5)
-    assert_close(out, ref, REL_TC, "fp32 boundary")
+    assert_parity(out, q.bfloat16(), k.bfloat16(), v.bfloat16(), 2, 32 ** -0.5, what="fp32 boundary")
 
 
 def test_fp16_inputs():
@@ -96,7 +109,7 @@ def test_fp16_inputs():
     q, k, v = _qkv(2, 16, 100, 2, 64, 64, dtype=torch.float16)
     out = ops.attention(q, k, v, 2, 0.125)
     assert out.dtype == torch.float16
-    assert_close(out, oracle_core(q, k, v, 2, 0.125), 4e-3, "fp16")
+    assert_parity(out, q, k, v, 2, 0.125, what="fp16")
 
 
 @pytest.mark.parametrize("impl", ["simt", "auto"])
@@ -189,26 +202,6 @@ def test_head_major_4d_operands_by_stride():
     assert torch.equal(out, ops.attention(q, k, v, H, d ** -0.5))
 
 
-@pytest.mark.parametrize("shape", [(2, 300, 700, 2, 128, 128), (1, 512, 2048, 4, 64, 128), (3, 400, 900, 2, 96, 96)],
-                         ids=lambda s: "x".join(map(str, s)))
-def test_cta_pair_kernel_matches_oracle(shape):
-    """cta_group::2 kernel (two SMs per 256-row MMA), incl. padding + causal masks and ragged N / M."""
-    from perceiver_io_b200 import ops
-
-    B, N, M, H, dqk, dv = shape
-    q, k, v = _qkv(B, N, M, H, dqk, dv, Bq=1 if B == 3 else None, seed=17, q_gain=2.0)
-    pad = torch.zeros(B, M, dtype=torch.bool)
-    pad[0, : M // 5] = True
-    if B > 2:
-        pad[2, :] = True
-    for causal in (False, True):
-        out = ops.attention(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="tcgen05_pair")
-        assert_close(out, oracle_core(q, k, v, H, dqk ** -0.5, pad, causal), REL_TC, f"pair causal={causal}")
-    part = ops.attention_partial(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), impl="tcgen05_pair")
-    merged = ops.combine_partials(part[0][None], part[1][None], part[2][None])
-    assert_close(merged, oracle_core(q, k, v, H, dqk ** -0.5, pad, False), REL_TC, "pair partial state")
-
-
 @pytest.mark.parametrize("shape", [(1, 256, 3000, 2, 192, 320), (2, 130, 1500, 1, 322, 322), (1, 300, 2000, 1, 512, 512)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_big_head_kernel_multi_tile_with_masks(shape):
@@ -223,7 +216,7 @@ def test_big_head_kernel_multi_tile_with_masks(shape):
     pad[0, 100:900] = True
     for causal in (False, True):
         out = ops.attention(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="tcgen05")
-        assert_close(out, oracle_core(q, k, v, H, dqk ** -0.5, pad, causal), REL_TC, f"big-head causal={causal}")
+        assert_parity(out, q, k, v, H, dqk ** -0.5, pad, causal, what=f"big-head causal={causal}")
     if dqk % 8 == 0 and dv % 8 == 0:
         part = ops.attention_partial(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), impl="tcgen05")
         merged = ops.combine_partials(part[0][None], part[1][None], part[2][None])
@@ -257,35 +250,7 @@ def test_moving_reference_rescale_paths(dtype, step):
     pad[1, 1000:1100] = True
     for causal, pm in ((False, None), (True, pad)):
         out = ops.attention(q, k, v, H, d ** -0.5, pad_mask=None if pm is None else pm.cuda(), causal=causal, impl="tcgen05")
-        ref = oracle_core(q, k, v, H, d ** -0.5, pm, causal)
-        assert_close(out, ref, REL_TC if dtype == torch.bfloat16 else 5e-3, f"ramp {step} {dtype} causal={causal}")
-
-
-def test_split_handoff_kernel_subprocess():
-    """The opt-in split hand-off kernel (PCV_SPLIT=1 is read once per process) against the CUDA-core kernel."""
-    import os
-    import subprocess
-    import sys
-
-    code = r'''
-import torch
-from perceiver_io_b200 import ops
-for (B, N, M, H, d, causal) in ((2, 256, 512, 2, 128, False), (2, 200, 333, 2, 64, True), (1, 512, 4096, 4, 128, False)):
-    g = torch.Generator().manual_seed(1)
-    q = torch.randn(B, N, H * d, generator=g).bfloat16().cuda()
-    k = torch.randn(B, M, H * d, generator=g).bfloat16().cuda()
-    v = torch.randn(B, M, H * d, generator=g).bfloat16().cuda()
-    pad = torch.zeros(B, M, dtype=torch.bool); pad[0, :37] = True
-    a = ops.attention(q, k, v, H, d ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="tcgen05").float()
-    b = ops.attention(q, k, v, H, d ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="simt").float()
-    err = (a - b).abs().max().item(); ref = b.abs().max().item()
-    assert torch.isfinite(a).all() and err <= 1.2e-2 * ref, (B, N, M, H, d, causal, err, ref)
-print("SPLIT_OK")
-'''
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PCV_SPLIT="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=root)
-    assert r.returncode == 0 and "SPLIT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        assert_parity(out, q, k, v, H, d ** -0.5, pm, causal, what=f"ramp {step} {dtype} causal={causal}")
 
 
 def test_kv_arena_decode_loop_in_place_append_on_device():
