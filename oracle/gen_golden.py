@@ -218,6 +218,86 @@ def integer_cases(core):
     return 1
 
 
+def big_cases(core):
+    """Reference CrossAttention outputs at multi-tile sizes; inputs are rebuilt from seeds (tests/golden_big.py), only
+    every 4th output row is stored."""
+    from perceiver.model.core.modules import CrossAttention
+
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    import golden_big as GB
+
+    out = {}
+    for name in GB.BIG_CASES:
+        kw, sd_, x_q, x_kv, pad = GB.build(name)
+        m = CrossAttention(**kw).eval()
+        m.load_state_dict(sd_, strict=True)
+        with torch.no_grad():
+            y = m(x_q, x_kv, pad_mask=pad).last_hidden_state
+        out[name] = dict(rows=y[:, :: GB.ROW_STEP].clone(), checksums=GB.checksums(sd_, x_q, x_kv),
+                         out_abs_max=y.abs().max().item())
+    torch.save(out, os.path.join(OUT, "big_cases.pt"))
+    return len(out)
+
+
+def prefix_dropout_case(core):
+    """Training-mode Perceiver AR forward with cross-attention (prefix) dropout, reference modules.py:809-830.
+    `torch.rand` is intercepted to record the random matrix the reference drew; the tensors the reference hands to
+    its cross-attention layer AFTER the gather (kept prefix embeddings, key angles, pad mask) are recorded with a
+    forward pre-hook, and the keep mask is recomputed here with the reference's own three lines and verified to
+    reproduce that gather exactly."""
+    from perceiver.model.core.modules import CausalSequenceModel
+    from perceiver.model.core.config import CausalSequenceModelConfig
+
+    gen = torch.Generator().manual_seed(2468)
+    B, PREFIX, LATENTS, C, H = 3, 24, 8, 64, 4
+    cfg = dict(vocab_size=40, max_seq_len=PREFIX + LATENTS, max_latents=LATENTS, num_channels=C, num_heads=H,
+               num_self_attention_layers=1, num_self_attention_rotary_layers=1, cross_attention_dropout=0.4,
+               post_attention_dropout=0.0, residual_dropout=0.0, output_norm=True, abs_pos_emb=True)
+    csm = CausalSequenceModel(CausalSequenceModelConfig(**cfg))
+    randomize(csm, gen, scale=0.1)
+    csm.train()
+    tokens = torch.randint(0, 40, (B, PREFIX + LATENTS), generator=gen)
+    pad = torch.zeros(B, PREFIX + LATENTS, dtype=torch.bool)
+    pad[1, :5] = True
+    pad[2, :1] = True
+    drawn, seen = [], {}
+    real_rand = torch.rand
+
+    def rand_spy(*a, **k):
+        r = real_rand(*a, **k)
+        drawn.append(r.clone())
+        return r
+
+    def pre_hook(module, args, kwargs):
+        seen["x_latent"] = args[0].detach().clone()
+        seen["x_prefix"] = kwargs["x_kv_prefix"].detach().clone()
+        seen["pad_mask"] = kwargs["pad_mask"].clone()
+        seen["frq_keys"] = kwargs["rot_pos_emb_k"].frq_pos_enc.clone()
+        seen["frq_latent"] = kwargs["rot_pos_emb_q"].frq_pos_enc.clone()
+
+    h = csm.cross_attention.register_forward_pre_hook(pre_hook, with_kwargs=True)
+    torch.manual_seed(97)
+    torch.rand = rand_spy
+    try:
+        out = csm(tokens, prefix_len=PREFIX, pad_mask=pad)
+    finally:
+        torch.rand = real_rand
+        h.remove()
+    assert len(drawn) == 1 and drawn[0].shape == (B, PREFIX)
+    rand = drawn[0]
+    keep = PREFIX - int(PREFIX * cfg["cross_attention_dropout"])          # :817
+    keep_idx = rand.topk(keep, dim=-1).indices                              # :818
+    keep_mask = torch.zeros_like(rand, dtype=torch.bool).scatter_(dim=1, index=keep_idx, value=1)  # :820-821
+    assert torch.equal(seen["pad_mask"][:, :keep], pad[:, :PREFIX][keep_mask].reshape(B, keep))
+    assert seen["x_prefix"].shape == (B, keep, C)
+    torch.save(dict(config=cfg, state_dict=sd(csm), tokens=tokens, pad_mask=pad, prefix_len=PREFIX, rand=rand, keep=keep,
+                    keep_idx=keep_idx, keep_mask=keep_mask, x_prefix=seen["x_prefix"], x_latent=seen["x_latent"],
+                    ca_pad_mask=seen["pad_mask"], frq_keys=seen["frq_keys"], frq_latent=seen["frq_latent"],
+                    logits=out.logits.detach().clone(), hidden=out.last_hidden_state.detach().clone()),
+               os.path.join(OUT, "prefix_dropout_case.pt"))
+    return 1
+
+
 if __name__ == "__main__":
     core = import_reference_core()
     os.makedirs(OUT, exist_ok=True)
@@ -226,5 +306,7 @@ if __name__ == "__main__":
     print("layer cases:", layer_cases(core))
     print("io cases:", io_cases(core))
     print("integer cases:", integer_cases(core))
+    print("big cases:", big_cases(core))
+    print("prefix dropout case:", prefix_dropout_case(core))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -245,12 +245,24 @@ def self_attention_block(w: Weights, x: Tensor, num_heads: int, num_layers: int,
     return x, new_cache
 
 
+def prefix_keep_mask(rand: Tensor, prefix_len: int, p: float) -> Tuple[Tensor, Tensor, int]:
+    """Training-time prefix (cross-attention) dropout, integer path of modules.py:816-821: keep the
+    ``prefix_len - int(prefix_len * p)`` positions with the largest random numbers.  Returns
+    (keep_mask (b, prefix_len) bool, keep_idx (b, keep) int64, keep)."""
+    keep = prefix_len - int(prefix_len * p)                                                         # :817
+    keep_idx = rand.topk(keep, dim=-1).indices                                                      # :818
+    keep_mask = torch.zeros_like(rand, dtype=torch.bool).scatter_(dim=1, index=keep_idx, value=1)   # :820-821
+    return keep_mask, keep_idx, keep
+
+
 def perceiver_ar(w: Weights, x_tokens: Tensor, prefix_len: int, num_heads: int, num_layers: int,
                  num_rotary_layers: int, rotated_channels: int, abs_pos_emb: bool,
                  pad_mask: Optional[Tensor] = None, kv_cache: Optional[List] = None,
-                 output_norm: bool = False, output_bias: bool = True):
-    """CausalSequenceModel.forward = PerceiverAR.forward + logits (modules.py:768-871, 914-930), eval
-    mode (no prefix dropout).  Returns (hidden, logits, kv_cache)."""
+                 output_norm: bool = False, output_bias: bool = True,
+                 dropout_rand: Optional[Tensor] = None, dropout_p: float = 0.0):
+    """CausalSequenceModel.forward = PerceiverAR.forward + logits (modules.py:768-871, 914-930).  Eval mode
+    unless ``dropout_rand`` (the (b, prefix_len) matrix the reference draws with torch.rand, :816) is given, in
+    which case the training-time prefix dropout of :809-830 is applied.  Returns (hidden, logits, kv_cache)."""
     shift = None if pad_mask is None else pad_mask.sum(dim=1, keepdim=True)
     cache_active = kv_cache is not None and len(kv_cache) > 0
     b = x_tokens.shape[0]
@@ -270,6 +282,17 @@ def perceiver_ar(w: Weights, x_tokens: Tensor, prefix_len: int, num_heads: int, 
     else:
         x_latent, x_prefix = x[:, prefix_len:], x[:, :prefix_len]
     frq_latent = frq[:, prefix_len:]
+    frq_keys = frq
+    if dropout_rand is not None and prefix_len > 0 and dropout_p > 0.0:
+        if kv_cache is not None:
+            raise ValueError("cross-attention dropout not supported with caching")                  # :810-812
+        keep_mask, _, keep = prefix_keep_mask(dropout_rand, prefix_len, dropout_p)
+        x_prefix = x_prefix[keep_mask].reshape(b, keep, x_prefix.shape[-1])                         # :823
+        frq_prefix = frq[:, :prefix_len][keep_mask].reshape(b, keep, frq.shape[-1])                 # :824
+        frq_keys = torch.cat([frq_prefix, frq_latent], dim=1)                                       # :832
+        if pad_mask is not None:
+            pad_prefix = pad_mask[:, :prefix_len][keep_mask].reshape(b, keep)                       # :826-827
+            pad_mask = torch.cat([pad_prefix, pad_mask[:, prefix_len:]], dim=1)                     # :835-836
 
     ca_cache = None
     sa_cache = None
@@ -282,7 +305,7 @@ def perceiver_ar(w: Weights, x_tokens: Tensor, prefix_len: int, num_heads: int, 
             ca_cache, sa_cache = (x.new_zeros(b, 0, c), x.new_zeros(b, 0, cv)), []
 
     h, ca_new = cross_attention_layer(sub(w, "cross_attention."), x_latent, None, num_heads, x_kv_prefix=x_prefix,
-                                      pad_mask=pad_mask, rot_q=(frq_latent, True), rot_k=(frq, True),
+                                      pad_mask=pad_mask, rot_q=(frq_latent, True), rot_k=(frq_keys, True),
                                       kv_cache=ca_cache, causal=True)
     h, sa_new = self_attention_block(sub(w, "self_attention."), h, num_heads, num_layers, num_rotary_layers,
                                      rot=(frq_latent, True), kv_cache=sa_cache, causal=True)

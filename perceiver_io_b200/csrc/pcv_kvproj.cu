@@ -103,7 +103,12 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::kStages; ++i) {
-      mbar_init(&bar.full[i], CG);   // pair: the leader's expect_tx arrive + the peer's remote arrive
+      // ONE arrival: the (leader) producer's arrive.expect_tx, which announces the bytes of BOTH CTAs of a pair.  The
+      // peer never arrives: its loads only complete_tx on the leader's barrier (a transaction count may run negative
+      // until the matching expect_tx lands, and a phase cannot complete before the leader's arrival).  A remote
+      // mbarrier.arrive.release.cluster per stage compiles to MEMBAR + ERRBAR, which made the peer's producer wait for
+      // its own outstanding TMA loads before issuing the next one (measured: 2.6x slower, profiles/r02_kvproj_pair_membar.md).
+      mbar_init(&bar.full[i], 1);
       mbar_init(&bar.empty[i], 1);   // tcgen05.commit (multicast to both CTAs of a pair)
     }
     for (int i = 0; i < 2; ++i) {
@@ -154,10 +159,7 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             tma_load_2d(a_dst, &tmap_x, &bar.full[s], kb * kBK, row0);
             tma_load_2d(b_dst, &tmap_w, &bar.full[s], kb * kBK, wrow0);
           } else {
-            if (rank == 0)
-              mbar_arrive_expect_tx(&bar.full[s], (uint32_t)(2 * C::kStageBytes));
-            else
-              mbar_arrive_cluster(mapa_cluster(smem_u32(&bar.full[s]), 0));
+            if (rank == 0) mbar_arrive_expect_tx(&bar.full[s], (uint32_t)(2 * C::kStageBytes));
             tma_load_2d_pair(a_dst, &tmap_x, &bar.full[s], kb * kBK, row0);
             tma_load_2d_pair(b_dst, &tmap_w, &bar.full[s], kb * kBK, wrow0);
           }
@@ -297,8 +299,58 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
 
 // --------------------------------------------------------------------------------------------------
 // LayerNorm row statistics: one warp per row, (mean, 1/sqrt(var + eps)) with the biased variance of
-// nn.LayerNorm; mean first, then the centred second moment (the row is re-read from L1), fp32.
+// nn.LayerNorm, two-pass in fp32 (mean first, then the centred second moment: no cancellation however large
+// |mean| / sigma is).  HBM-bound: rows * C * 2 bytes in, 8 bytes per row out.  Rows of up to 2048 16-bit
+// channels (a multiple of 256) are held in registers between the passes (NCH 16-byte chunks per lane, all loads
+// of a row in flight at once, two rows per warp iteration); other widths re-read the row from L1.
 // --------------------------------------------------------------------------------------------------
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256) ln_stats_reg_kernel(const T* __restrict__ x, int64_t stride_row, int64_t rows,
+                                                            float eps, float2* __restrict__ stats) {
+  constexpr int C = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int64_t r = w0 * 2; r < rows; r += warps * 2) {
+    uint4 u[2][NCH];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const bool live = r + k < rows;
+      const uint4* xr = reinterpret_cast<const uint4*>(x + (r + k) * stride_row);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) u[k][i] = live ? __ldcs(xr + lane + 32 * i) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const typename Elem<T>::T2* h = reinterpret_cast<const typename Elem<T>::T2*>(&u[k][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = Elem<T>::to_f2(h[j]);
+          sum += f.x + f.y;
+        }
+      }
+      const float mean = warp_sum(sum) * (1.f / (float)C);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const typename Elem<T>::T2* h = reinterpret_cast<const typename Elem<T>::T2*>(&u[k][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = Elem<T>::to_f2(h[j]);
+          const float d0 = f.x - mean, d1 = f.y - mean;
+          sq = fmaf(d0, d0, sq);
+          sq = fmaf(d1, d1, sq);
+        }
+      }
+      const float var = warp_sum(sq) * (1.f / (float)C);
+      if (lane == 0 && r + k < rows) stats[r + k] = make_float2(mean, 1.f / sqrtf(var + eps));
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, int64_t stride_row, int64_t rows, int C,
                                                         float eps, float2* __restrict__ stats) {
@@ -346,6 +398,32 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, 
   }
 }
 
+template <typename T>
+int launch_ln_stats_t(const pcv_ln_stats_params& p, cudaStream_t stream) {
+  const T* x = reinterpret_cast<const T*>(p.x);
+  float2* st = reinterpret_cast<float2*>(p.stats);
+  const bool reg_ok = (p.C % 256 == 0) && p.C <= 2048 && (p.x_stride_row % 8 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+  if (reg_ok) {
+    const int blocks = (int)std::min<int64_t>((p.rows + 15) / 16, 148 * 8);
+#define PCV_LN_CASE(N)                                                                               \
+  case N:                                                                                            \
+    ln_stats_reg_kernel<T, N><<<blocks, 256, 0, stream>>>(x, p.x_stride_row, p.rows, p.eps, st);     \
+    break;
+    switch (p.C / 256) {
+      PCV_LN_CASE(1) PCV_LN_CASE(2) PCV_LN_CASE(3) PCV_LN_CASE(4) PCV_LN_CASE(5) PCV_LN_CASE(6) PCV_LN_CASE(7)
+      PCV_LN_CASE(8)
+    }
+#undef PCV_LN_CASE
+  } else {
+    const int blocks = (int)std::min<int64_t>((p.rows + 7) / 8, 148 * 8);
+    ln_stats_kernel<T><<<blocks, 256, 0, stream>>>(x, p.x_stride_row, p.rows, p.C, p.eps, st);
+  }
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PCV_OK;
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -391,10 +469,7 @@ int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap&
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
-  const int64_t max_workers = CG == 1 ? sms : sms / 2;
-  const int workers = (int)std::min<int64_t>(max_workers, gp.num_tiles);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(workers * CG));
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
@@ -405,6 +480,25 @@ int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  int64_t max_workers = sms;
+  if (CG == 2) {
+    // A persistent kernel must not launch more CTA pairs than can be co-resident (a pair needs both SMs of one TPC
+    // free; the second wave would double the run time): ask the occupancy calculator.
+    static int max_pairs[64] = {};
+    if (dev < 0 || dev >= 64 || max_pairs[dev] == 0) {
+      cfg.gridDim = dim3((unsigned)(sms / 2 * 2));
+      int n = 0;
+      PCV_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      if (n < 1) n = 1;
+      if (dev >= 0 && dev < 64) max_pairs[dev] = n;
+      max_workers = n;
+    } else {
+      max_workers = max_pairs[dev];
+    }
+    if (getenv("PCV_KVPROJ_VERBOSE")) fprintf(stderr, "[pcv] kvproj: %lld co-resident CTA pairs on %d SMs\n", (long long)max_workers, sms);
+  }
+  const int workers = (int)std::min<int64_t>(max_workers, gp.num_tiles);
+  cfg.gridDim = dim3((unsigned)(workers * CG));
   prof_mark_begin(stream);
   PCV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tk, tv, gp));
   prof_mark_end(stream);
@@ -419,16 +513,7 @@ int launch_ln_stats(const pcv_ln_stats_params& p, cudaStream_t stream) {
   PCV_REQUIRE(p.rows >= 0 && p.C >= 1, PCV_ERR_INVALID, "ln_stats: rows=%lld C=%d", (long long)p.rows, p.C);
   PCV_REQUIRE(p.dtype == PCV_BF16 || p.dtype == PCV_F16, PCV_ERR_INVALID, "ln_stats: dtype must be bf16/fp16");
   if (p.rows == 0) return PCV_OK;
-  const int blocks = (int)std::min<int64_t>((p.rows + 7) / 8, 148 * 8);
-  if (p.dtype == PCV_BF16)
-    ln_stats_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(p.x), p.x_stride_row,
-                                                               p.rows, p.C, p.eps, reinterpret_cast<float2*>(p.stats));
-  else
-    ln_stats_kernel<__half><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __half*>(p.x), p.x_stride_row, p.rows, p.C,
-                                                        p.eps, reinterpret_cast<float2*>(p.stats));
-  PCV_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return PCV_OK;
+  return p.dtype == PCV_BF16 ? launch_ln_stats_t<__nv_bfloat16>(p, stream) : launch_ln_stats_t<__half>(p, stream);
 }
 
 bool kv_project_supported(const pcv_kvproj_params& p, const char** why) {

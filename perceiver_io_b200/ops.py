@@ -280,27 +280,14 @@ def rescale_partial_(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.T
         check(_lib.lib().pcv_partial_rescale(C.byref(p), _stream()), "pcv_partial_rescale")
 
 
-def rotary(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: bool) -> torch.Tensor:
-    """Rotate the first ``angles.shape[-1]`` channels of every head of x (B, n, H*d).
-
-    ``angles`` is the reference's ``frq_pos_enc`` (B or 1, n_angles, rotate_dim); row selection follows
-    /root/reference/perceiver/model/core/position.py:32-37 (last n rows if right_align else first n)."""
+def _rotary_forward(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: bool) -> torch.Tensor:
     _require_cuda(x, angles)
     out_dtype = x.dtype
     cdt = _compute_dtype(x.dtype)
     x = _rows_contiguous(x if x.dtype == cdt else x.to(cdt))
-    if angles.dim() == 4:  # (B, 1, n, f) as stored by RotaryPositionEmbedding
-        angles = angles[:, 0]
-    angles = angles.float()
-    if angles.stride(-1) != 1:
-        angles = angles.contiguous()
     B, n, Cx = x.shape
     d = Cx // num_heads
     Ba, n_angles, f = angles.shape
-    if Ba not in (1, B):
-        raise ValueError(f"angle batch {Ba} must be 1 or {B}")
-    if n_angles < n:
-        raise ValueError(f"rotary: {n_angles} angle rows for a sequence of {n}")
     y = torch.empty(B, n, Cx, dtype=cdt, device=x.device)
     if n == 0:
         return y.to(out_dtype)
@@ -319,13 +306,69 @@ def rotary(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: b
     return y if cdt == out_dtype else y.to(out_dtype)
 
 
-class _KvArena:
-    """Backing buffer ``(B, capacity, C)`` of a growing KV cache plus the first unused row."""
+class _Rotary(torch.autograd.Function):
+    """Forward = pcv_rotary_apply.  Backward = TRAINING-SUPPORT SHIM in torch ops (like ``_FusedAttention``): the
+    transpose of the pairwise rotation,  dx[2p] = dy[2p] cos a[2p] + dy[2p+1] sin a[2p+1],
+    dx[2p+1] = dy[2p+1] cos a[2p+1] - dy[2p] sin a[2p],  channels beyond ``rotate_dim`` pass through.  Without it the
+    rotated q / k would be constants for autograd and q_proj / k_proj of every rotary layer would get no gradient."""
 
-    __slots__ = ("buf", "used")
+    @staticmethod
+    def forward(ctx, x, angles, num_heads, right_align):
+        ctx.save_for_backward(angles)
+        ctx.meta = (num_heads, right_align)
+        return _rotary_forward(x, num_heads, angles, right_align)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (angles,) = ctx.saved_tensors
+        H, right_align = ctx.meta
+        B, n, Cx = gy.shape
+        d, f = Cx // H, angles.shape[-1]
+        a = angles[:, angles.shape[1] - n:] if right_align else angles[:, :n]
+        a = a[:, :, None, :].float()                       # (Ba, n, 1, f)
+        g = gy.float().reshape(B, n, H, d)
+        gr = g[..., :f]
+        ge, go = gr[..., 0::2], gr[..., 1::2]
+        ae, ao = a[..., 0::2], a[..., 1::2]
+        dxe = ge * torch.cos(ae) + go * torch.sin(ao)
+        dxo = go * torch.cos(ao) - ge * torch.sin(ae)
+        dx = torch.cat([torch.stack([dxe, dxo], dim=-1).flatten(-2), g[..., f:]], dim=-1)
+        return dx.reshape(B, n, Cx).to(gy.dtype), None, None, None
+
+
+def rotary(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: bool) -> torch.Tensor:
+    """Rotate the first ``angles.shape[-1]`` channels of every head of x (B, n, H*d).
+
+    ``angles`` is the reference's ``frq_pos_enc`` (B or 1, n_angles, rotate_dim); row selection follows
+    /root/reference/perceiver/model/core/position.py:32-37 (last n rows if right_align else first n)."""
+    _require_cuda(x, angles)
+    if angles.dim() == 4:  # (B, 1, n, f) as stored by RotaryPositionEmbedding
+        angles = angles[:, 0]
+    angles = angles.float()
+    if angles.stride(-1) != 1:
+        angles = angles.contiguous()
+    B, n, _ = x.shape
+    Ba, n_angles, _ = angles.shape
+    if Ba not in (1, B):
+        raise ValueError(f"angle batch {Ba} must be 1 or {B}")
+    if n_angles < n:
+        raise ValueError(f"rotary: {n_angles} angle rows for a sequence of {n}")
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _Rotary.apply(x, angles, num_heads, bool(right_align))
+    return _rotary_forward(x, num_heads, angles, bool(right_align))
+
+
+class _KvArena:
+    """Bookkeeping of a growing KV cache's backing buffer ``(B, capacity, C)``: the first unused row.  The arena is
+    an attribute OF the buffer and refers back to it only weakly, so a superseded buffer is released by reference
+    counting as soon as the last cache view of it is dropped (no tensor <-> arena cycle waiting for the cyclic GC)."""
+
+    __slots__ = ("buf_ref", "used")
 
     def __init__(self, buf: torch.Tensor):
-        self.buf = buf
+        import weakref
+
+        self.buf_ref = weakref.ref(buf)
         self.used = 0
 
 
@@ -342,7 +385,7 @@ def _arena_of(t: torch.Tensor):
     reordering, :140-144) yields a fresh tensor and is not."""
     root = t._base if t._base is not None else t
     arena = getattr(root, _ARENA_ATTR, None)
-    if arena is None or arena.buf is not root or t.dim() != 3 or t.dtype != root.dtype:
+    if arena is None or arena.buf_ref() is not root or t.dim() != 3 or t.dtype != root.dtype:
         return None
     B, cap, C = root.shape
     if t.shape[0] != B or t.shape[2] != C or t.shape[1] == 0:
@@ -367,9 +410,10 @@ def _arena_target(cache: torch.Tensor, n: int):
     hit = _arena_of(cache) if kv_arena_config["enabled"] else None
     if hit is not None:
         arena, start = hit
-        if start + L == arena.used and arena.used + n <= arena.buf.shape[1]:
+        root = cache._base if cache._base is not None else cache
+        if start + L == arena.used and arena.used + n <= root.shape[1]:
             arena.used += n
-            return arena.buf[:, start:start + L + n], True
+            return root[:, start:start + L + n], True
     if not kv_arena_config["enabled"]:
         return torch.empty(B, L + n, C, dtype=cache.dtype, device=cache.device), False
     cap = max(int((L + n) * kv_arena_config["growth"]) + 1, kv_arena_config["min_rows"], L + n)
@@ -412,9 +456,25 @@ def kv_append(k_cache: torch.Tensor, v_cache: torch.Tensor, k_new: torch.Tensor,
     They are row ranges of arenas with head-room (see :func:`_arena_target`): a decode loop that feeds the
     returned cache back in appends its new row in place instead of re-copying the whole cache every step."""
     _require_cuda(k_cache, v_cache, k_new, v_new)
+    # torch.cat type-promotes (reference modules.py:119-121): under autocast the first cached step meets an fp32
+    # empty cache and bf16 projections.  An EMPTY cache simply adopts the dtype of the new rows (so a decode loop
+    # keeps its cache in the compute dtype); otherwise both sides are promoted like torch.cat would.
+    def _common(cache, new):
+        if cache.dtype == new.dtype:
+            return cache, new
+        if cache.shape[1] == 0:
+            return cache.to(new.dtype), new
+        dt_ = torch.promote_types(cache.dtype, new.dtype)
+        return cache.to(dt_), new.to(dt_)
+
+    k_cache, k_new = _common(k_cache, k_new)
+    v_cache, v_new = _common(v_cache, v_new)
+    if k_new.dtype != v_new.dtype:
+        dt_ = torch.promote_types(k_new.dtype, v_new.dtype)
+        k_cache, k_new, v_cache, v_new = (t.to(dt_) for t in (k_cache, k_new, v_cache, v_new))
     dt = k_new.dtype
-    if dt not in (torch.bfloat16, torch.float16, torch.float32) or any(t.dtype != dt for t in (k_cache, v_cache, v_new)):
-        raise RuntimeError(f"kv_append expects matching bf16/fp16/fp32 tensors, got {k_cache.dtype}/{k_new.dtype}")
+    if dt not in (torch.bfloat16, torch.float16, torch.float32):
+        raise RuntimeError(f"kv_append supports bf16/fp16/fp32 caches, got {dt}")
     k_cache, v_cache, k_new, v_new = (_rows_contiguous(t) for t in (k_cache, v_cache, k_new, v_new))
     L_old, n = k_cache.shape[1], k_new.shape[1]
     k_dst, k_in_place = _arena_target(k_cache, n)

@@ -86,3 +86,22 @@ def assert_parity(got, q, k, v, H, scale, pad=None, causal=False, what="", eager
     print(f"[parity] {what}: err {err:.3e}  bound {bound:.3e} (= 2 x eager {eager_err:.3e} + 1e-3 x max|ref| {ref_max:.3e})")
     assert err <= bound, f"{what}: max err {err:.3e} > derived bound {bound:.3e} (eager bf16 err {eager_err:.3e}, max|ref| {ref_max:.3e})"
     return err, bound, eager_err
+
+
+def torch_cross_attention(sd, x_q, x_kv, H, pad=None, dtype=torch.float64, device="cuda"):
+    """CrossAttention.forward (reference modules.py:204-230 -> :113-170) restated with torch ops in `dtype` on
+    `device` from a reference state_dict: the fp64 yardstick / the eager-bf16 yardstick of module-level cases."""
+    import torch.nn.functional as F
+
+    w = {k: v.to(device=device, dtype=dtype) for k, v in sd.items()}
+    xq = x_q.to(device=device, dtype=dtype)
+    xkv = x_kv.to(device=device, dtype=dtype)
+    xq = F.layer_norm(xq, xq.shape[-1:], w["q_norm.weight"], w["q_norm.bias"], 1e-5)          # :220
+    xkv = F.layer_norm(xkv, xkv.shape[-1:], w["kv_norm.weight"], w["kv_norm.bias"], 1e-5)     # :226
+    a = "attention."
+    q = F.linear(xq, w[a + "q_proj.weight"], w.get(a + "q_proj.bias"))                          # :113
+    k = F.linear(xkv, w[a + "k_proj.weight"], w.get(a + "k_proj.bias"))                         # :114
+    v = F.linear(xkv, w[a + "v_proj.weight"], w.get(a + "v_proj.bias"))                         # :115
+    scale = (q.shape[-1] // H) ** -0.5                                                          # :73
+    o = torch_core(q, k, v, H, scale, None if pad is None else pad.to(device), False, dtype)
+    return F.linear(o, w[a + "o_proj.weight"], w.get(a + "o_proj.bias"))                        # :168

@@ -287,3 +287,23 @@ def test_kv_arena_decode_loop_in_place_append_on_device():
     old_k, old_snap = held[1]
     branch, _ = ops.kv_append(old_k, old_k, torch.ones_like(kn), torch.ones_like(kn))
     assert torch.equal(k, torch.cat(ks, 1)) and torch.equal(branch[:, :-1], old_snap)
+
+
+def test_rotary_is_differentiable_and_matches_the_torch_rotation():
+    """ops.rotary keeps its input in the autograd graph: gradient = transpose of the pairwise rotation."""
+    from perceiver_io_b200 import ops
+
+    g = torch.Generator().manual_seed(2)
+    B, n, H, d, f = 2, 19, 3, 16, 8
+    x = torch.randn(B, n, H * d, generator=g).cuda().requires_grad_(True)
+    pos = O.positions(B, n + 4, torch.tensor([[0], [3]]))
+    angles = O.frequency_angles(pos, f).cuda()
+    wgt = torch.randn(B, n, H * d, generator=g).cuda()
+    for right in (True, False):
+        y = ops.rotary(x, H, angles, right)
+        assert y.requires_grad
+        (gx,) = torch.autograd.grad((y * wgt).sum(), x)
+        xr = x.detach().double().cpu().requires_grad_(True)
+        ref = O.merge_heads(O.rotate(O.split_heads(xr, H), angles.double().cpu(), right))
+        (gref,) = torch.autograd.grad((ref * wgt.double().cpu()).sum(), xr)
+        assert_close(gx, gref, 1e-5, f"rotary grad right_align={right}")

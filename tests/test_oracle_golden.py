@@ -151,3 +151,38 @@ def test_partial_states_merge_exactly():
             parts = [O.partial_state(q, k[:, :, a:b], v[:, :, a:b], 0.25, pad[:, a:b], causal, M, a)
                      for a, b in zip(cuts[:-1], cuts[1:])]
             assert (O.merge_states(parts) - full).abs().max() < 1e-12
+
+
+def test_prefix_dropout_integer_path_and_forward():
+    """Training-mode forward of the REAL reference with prefix dropout (fixture written by oracle/gen_golden.py):
+    keep indices / mask / gathered pad mask bit-exact given the reference's own random matrix, logits to fp32
+    re-association."""
+    g = load_golden("prefix_dropout_case.pt")
+    cfg = g["config"]
+    mask, idx, keep = O.prefix_keep_mask(g["rand"], g["prefix_len"], cfg["cross_attention_dropout"])
+    assert keep == g["keep"] and torch.equal(idx, g["keep_idx"]) and torch.equal(mask, g["keep_mask"])
+    hidden, logits, _ = O.perceiver_ar(
+        g["state_dict"], g["tokens"], g["prefix_len"], pad_mask=g["pad_mask"], num_heads=cfg["num_heads"],
+        num_layers=cfg["num_self_attention_layers"], num_rotary_layers=cfg["num_self_attention_rotary_layers"],
+        rotated_channels=cfg["num_channels"] // cfg["num_heads"] // 2, abs_pos_emb=True, output_norm=True,
+        output_bias=True, dropout_rand=g["rand"], dropout_p=cfg["cross_attention_dropout"])
+    close(hidden, g["hidden"])
+    close(logits, g["logits"])
+
+
+BIG = load_golden("big_cases.pt")
+
+
+@pytest.mark.parametrize("name", sorted(BIG))
+def test_big_reference_cases_rebuild_and_match_the_oracle(name):
+    """The seeded rebuild of weights / inputs reproduces the tensors the fixture was generated from (checksums), and
+    the oracle's CrossAttention restatement matches the reference's committed output rows at multi-tile sizes."""
+    import golden_big as GB
+
+    kw, sd, x_q, x_kv, pad = GB.build(name)
+    sums = GB.checksums(sd, x_q, x_kv)
+    for key, val in BIG[name]["checksums"].items():
+        assert abs(sums[key] - val) <= 1e-9 * max(1.0, abs(val)), f"{name}: regenerated {key} differs from the fixture"
+    out, _ = O.cross_attention(sd, x_q, x_kv, kw["num_heads"], pad_mask=pad)
+    out = out.expand(x_kv.shape[0], -1, -1)
+    close(out[:, :: GB.ROW_STEP], BIG[name]["rows"], atol=5e-5)
