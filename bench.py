@@ -160,22 +160,49 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of CrossAttention.forward on host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_cross_attention_sample(steps: int, warmup: int, min_seconds: float = 0.0):
-    """Times oracle.cross_attention (fp32, torch CPU, all threads) on ONE batch row of the workload."""
+def _reference_cross_attention():
+    """(kind, callable(x_q, x_kv) -> tensor): the reference's OWN CrossAttention.forward (krasserm/perceiver-io,
+    perceiver/model/core/modules.py:173-230, installed unmodified into baseline/_ref by baseline/install_ref.py) when
+    it travelled to this box, else the oracle port of the same lines."""
     import torch
-    from oracle import mha_oracle as O
 
     w = WORKLOAD
-    ncpu = os.cpu_count() or 1
-    torch.set_num_threads(ncpu)
+    d, H = w["d"], w["H"]
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import install_ref
+
+        if install_ref.available():
+            core = install_ref.import_reference_core()
+            torch.manual_seed(0)
+            layer = core.CrossAttention(num_heads=H, num_q_input_channels=d, num_kv_input_channels=d)
+            core.init_parameters(layer, 0.02) if hasattr(core, "init_parameters") else None
+            layer.eval()
+            return "reference", (lambda x_q, x_kv: layer(x_q, x_kv).last_hidden_state)
+    except Exception as exc:  # noqa: BLE001 — fall back to the port, say why
+        print(f"[bench] baseline/_ref unusable ({type(exc).__name__}: {exc}); timing the oracle port", file=sys.stderr)
+    from oracle import mha_oracle as O
+
     g = torch.Generator().manual_seed(0)
-    d = w["d"]
     weights = {}
     for name in ("q_norm", "kv_norm"):
         weights[name + ".weight"], weights[name + ".bias"] = torch.ones(d), torch.zeros(d)
     for name in ("q_proj", "k_proj", "v_proj", "o_proj"):
         weights[f"attention.{name}.weight"] = torch.randn(d, d, generator=g) * 0.02
         weights[f"attention.{name}.bias"] = torch.zeros(d)
+    return "port", (lambda x_q, x_kv: O.cross_attention(weights, x_q, x_kv, H)[0])
+
+
+def cpu_cross_attention_sample(steps: int, warmup: int, min_seconds: float = 0.0):
+    """Times the reference's CrossAttention.forward (fp32, torch CPU) on ONE batch row of the workload."""
+    import torch
+
+    w = WORKLOAD
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
+    kind, fwd = _reference_cross_attention()
+    g = torch.Generator().manual_seed(0)
+    d = w["d"]
     x_q = torch.randn(1, w["N"], d, generator=g)
     x_kv = torch.randn(1, w["M"], d, generator=g)
     times = []
@@ -184,30 +211,32 @@ def cpu_cross_attention_sample(steps: int, warmup: int, min_seconds: float = 0.0
         best = (None, float("inf"))
         for nt in sorted({ncpu, max(1, ncpu // 2), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
             torch.set_num_threads(nt)
-            O.cross_attention(weights, x_q, x_kv, w["H"])
+            fwd(x_q, x_kv)
             t0 = time.perf_counter()
-            O.cross_attention(weights, x_q, x_kv, w["H"])
+            fwd(x_q, x_kv)
             dt = time.perf_counter() - t0
             if dt < best[1]:
                 best = (nt, dt)
         torch.set_num_threads(best[0])
         for _ in range(warmup):
-            O.cross_attention(weights, x_q, x_kv, w["H"])
+            fwd(x_q, x_kv)
         t_all = time.perf_counter()
         for i in range(max(steps, 1)):
             t0 = time.perf_counter()
-            O.cross_attention(weights, x_q, x_kv, w["H"])
+            fwd(x_q, x_kv)
             times.append(time.perf_counter() - t0)
         while time.perf_counter() - t_all < min_seconds:
             t0 = time.perf_counter()
-            O.cross_attention(weights, x_q, x_kv, w["H"])
+            fwd(x_q, x_kv)
             times.append(time.perf_counter() - t0)
     mean_s = sum(times) / len(times)
     flops = core_flops(1, w["N"], w["M"], d)
+    what = ("the reference's own CrossAttention.forward (krasserm/perceiver-io, unmodified, from baseline/_ref)"
+            if kind == "reference" else "oracle port of CrossAttention.forward (baseline/_ref did not travel)")
     return dict(
-        tflops=flops / mean_s / 1e12, seconds=mean_s, steps=len(times), cores=torch.get_num_threads(),
+        tflops=flops / mean_s / 1e12, seconds=mean_s, steps=len(times), cores=torch.get_num_threads(), kind=kind,
         sample=(f"1 of {w['B']} batch rows of the workload (B=1, M={w['M']}, N={w['N']}, d={d}, H={w['H']}), fp32, "
-                f"oracle port of CrossAttention.forward (LayerNorm + q/k/v/o projections + attention), "
+                f"{what}: LayerNorm + q/k/v/o projections + attention, "
                 f"{len(times)} timed passes, fastest of several torch thread counts on {ncpu} host cores"),
     )
 
@@ -224,7 +253,7 @@ def run_reference(args, rank):
         "input_tokens_per_s": w["M"] / r["seconds"],
         "config": {"workload": "synthetic cross-attn sweep point M=65536 (BASELINE.json configs[4]), CPU sample", **w,
                    "parallelism": "host threads"},
-        "cpu_baseline": {"value": r["tflops"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["tflops"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["tflops"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -324,7 +353,10 @@ def run_ours(args, rank, world, local_rank):
     hbm_bytes = 2.0 * B * Mg * d * 2 + 2.0 * B * N * d * 2
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_tflops"], "traffic": args.traffic_bytes,
+        "frac": achieved / peaks["bf16_tflops"],
+        # dram bytes per launch from the committed ncu capture of the 1-GPU launch; a rank of an M-sharded run reads
+        # its shard only, for which no capture exists: null rather than a misleading constant
+        "traffic": args.traffic_bytes if world == 1 else None,
         "kernel_ms": main_ms, "kernel_launches_per_step": main_n / max(args.steps, 1),
         "peak_source": peaks["source"],
         "hbm_gbs_algorithmic": hbm_bytes / (main_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
@@ -345,10 +377,15 @@ def run_ours(args, rank, world, local_rank):
     from perceiver_io_b200.streaming import cross_attention_from_host
 
     def e2e_step():
-        if world == 1 and args.e2e_mode == "streamed":
-            # public host-input entry point: PCIe copy of chunk i+1 overlaps LayerNorm/projections/attention of chunk i
+        if args.e2e_mode == "streamed":
+            # public host-input entry point: PCIe copy of chunk i+1 overlaps LayerNorm/projections/attention of chunk i;
+            # with several ranks every rank streams its own key shard and the states are merged over peer memory
             with torch.no_grad():
-                cross_attention_from_host(layer, xq_host, xkv_host, chunk=args.e2e_chunk, out_host=out_host)
+                if world == 1:
+                    cross_attention_from_host(layer, xq_host, xkv_host, chunk=args.e2e_chunk, out_host=out_host)
+                else:
+                    cross_attention_from_host(layer, xq_host, xkv_host, chunk=min(args.e2e_chunk, max(Mg // 2, 1024)),
+                                              out_host=out_host, m_total=M, m_offset=m0)
             return
         xq = xq_host.to(dev, non_blocking=True)
         xkv = xkv_host.to(dev, non_blocking=True)
@@ -364,11 +401,36 @@ def run_ours(args, rank, world, local_rank):
     h2d = xq_host.numel() * 2 + xkv_host.numel() * 2
     d2h = out_host.numel() * 2
 
+    # ---- module: device-resident CrossAttention.forward (SURVEY.md §8(d) "module" work) --------------------
+    # LayerNorm + q/k/v/o projections + attention with x_q / x_kv already in HBM: 3.316e12 FLOP at the headline shape,
+    # all of it on hand-written kernels (pcv_ln_stats, pcv_kv_project x3, pcv_attn_fwd).
+    module = None
+    if world == 1 and not args.skip_module:
+        xq_dev = xq_host.to(dev)
+        xkv_dev = xkv_host.to(dev)
+        torch.cuda.synchronize()
+
+        def module_step():
+            with torch.no_grad():
+                return layer(xq_dev, xkv_dev).last_hidden_state
+
+        l0 = _lib.launch_count()
+        ms_mod = timed(module_step, args.steps, min(args.warmup, 3))
+        l_mod = (_lib.launch_count() - l0) // (args.steps + min(args.warmup, 3))
+        mod_flops = flops + 4.0 * B * M * d * d + 4.0 * B * N * d * d
+        mod_tf = mod_flops / (ms_mod * 1e-3) / 1e12
+        module = {"api": "perceiver_io_b200.CrossAttention.forward, device-resident inputs", "ms_per_step": ms_mod,
+                  "flops": mod_flops, "value": mod_tf, "unit": UNIT, "frac_of_tensor_peak": mod_tf / peaks["bf16_tflops"],
+                  "library_launches_per_step": l_mod,
+                  "min_hbm_bytes": 2.0 * B * M * d + 3 * 2.0 * B * M * d + 8.0 * B * M,   # x read twice (stats + GEMM), K,V written + read
+                  "note": "fused K/V producer: LayerNorm folded into one tcgen05 GEMM; q/o projections on the same kernel"}
+        del xq_dev, xkv_dev
+
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
     cpu = None
     if world == 1 and rank == 0 and not args.skip_cpu:
         r = cpu_cross_attention_sample(steps=2, warmup=1, min_seconds=args.cpu_seconds)
-        cpu = {"value": r["tflops"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+        cpu = {"value": r["tflops"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "seconds_per_sample": r["seconds"]}
 
     if rank == 0:
@@ -389,8 +451,9 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps,
                     "api": ("perceiver_io_b200.streaming.cross_attention_from_host (CrossAttention.forward semantics: LayerNorm + q/k/v/o "
-                            "projections + attention; key axis chunked so the PCIe copy overlaps compute)"
-                            if (world == 1 and args.e2e_mode == "streamed") else
+                            "projections + attention; key axis chunked so the PCIe copy overlaps compute"
+                            + ("; every rank streams its own key shard, states merged over peer memory)" if world > 1 else ")")
+                            if args.e2e_mode == "streamed" else
                             "perceiver_io_b200.CrossAttention.forward (LayerNorm + q/k/v/o projections + attention)")},
             "gpu_launches": int(launches_timed),
             "roofline": roofline,
@@ -398,6 +461,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if module is not None:
+            line["module"] = module
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -422,6 +487,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-module", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes/launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()

@@ -175,6 +175,23 @@ typedef struct pcv_kv_append_params {
 } pcv_kv_append_params;
 
 /*
+ * Merge `num_parts` partial states into ONE partial state (still un-normalised): the local step of a two-level
+ * merge (chunks of a host-streamed shard on one GPU, then pcv_attn_combine_peers / an all-reduce across GPUs).
+ *   part_* : (num_parts, rows[, dv]) f32, rows = B*H*N;   out_* : (rows[, dv]) f32
+ *   out_m = max_g m_g ;  out_l = sum_g l_g 2^(m_g - out_m) ;  out_o = sum_g part_o_g 2^(m_g - out_m)
+ */
+typedef struct pcv_merge_params {
+  const float* part_o;
+  const float* part_m;
+  const float* part_l;
+  float* out_o;
+  float* out_m;
+  float* out_l;
+  int64_t rows;
+  int32_t num_parts, dv;
+} pcv_merge_params;
+
+/*
  * In-place change of reference maximum of a partial state (used between the two all-reduces of the
  * M-sharded path, perceiver_io_b200/dist.py):  w = 2^(part_m[r] - new_m[r]);  part_o[r,:] *= w;
  * part_l[r] *= w;  part_m[r] = new_m[r].   rows = B*H*N.  new_m[r] >= part_m[r] is expected.
@@ -276,6 +293,7 @@ PCV_API int pcv_attn_workspace_bytes(const pcv_attn_params* p, size_t* bytes);
 PCV_API int pcv_attn_fwd(const pcv_attn_params* p, void* stream);
 PCV_API int pcv_attn_combine(const pcv_combine_params* p, void* stream);
 PCV_API int pcv_attn_combine_peers(const pcv_peer_combine_params* p, void* stream);
+PCV_API int pcv_attn_merge_partials(const pcv_merge_params* p, void* stream);
 PCV_API int pcv_partial_rescale(const pcv_rescale_params* p, void* stream);
 PCV_API int pcv_rotary_apply(const pcv_rotary_params* p, void* stream);
 PCV_API int pcv_kv_append(const pcv_kv_append_params* p, void* stream);

@@ -29,6 +29,7 @@ EXPORTS = (
     "pcv_attn_fwd",
     "pcv_attn_combine",
     "pcv_attn_combine_peers",
+    "pcv_attn_merge_partials",
     "pcv_partial_rescale",
     "pcv_rotary_apply",
     "pcv_kv_append",
@@ -76,6 +77,14 @@ class CombineParams(C.Structure):
         ("num_parts", C.c_int32),
         ("B", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("dv", C.c_int32),
         ("dtype", C.c_int32),
+    ]
+
+
+class MergeParams(C.Structure):
+    _fields_ = [
+        ("part_o", C.c_void_p), ("part_m", C.c_void_p), ("part_l", C.c_void_p),
+        ("out_o", C.c_void_p), ("out_m", C.c_void_p), ("out_l", C.c_void_p),
+        ("rows", C.c_int64), ("num_parts", C.c_int32), ("dv", C.c_int32),
     ]
 
 
@@ -188,6 +197,8 @@ def lib() -> C.CDLL:
         l.pcv_partial_rescale.argtypes = [C.POINTER(RescaleParams), C.c_void_p]
         l.pcv_attn_combine_peers.argtypes = [C.POINTER(PeerCombineParams), C.c_void_p]
         l.pcv_attn_combine_peers.restype = C.c_int
+        l.pcv_attn_merge_partials.argtypes = [C.POINTER(MergeParams), C.c_void_p]
+        l.pcv_attn_merge_partials.restype = C.c_int
         l.pcv_profile_begin.restype = C.c_int
         l.pcv_profile_end.restype = C.c_int
         l.pcv_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32)]

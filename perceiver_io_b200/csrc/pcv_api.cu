@@ -179,6 +179,11 @@ int pcv_attn_combine_peers(const pcv_peer_combine_params* p, void* stream) {
   return launch_combine_peers(*p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int pcv_attn_merge_partials(const pcv_merge_params* p, void* stream) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "merge_partials: params is NULL");
+  return launch_merge_partials(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int pcv_partial_rescale(const pcv_rescale_params* p, void* stream) {
   PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "rescale: params is NULL");
   return launch_rescale(*p, reinterpret_cast<cudaStream_t>(stream));

@@ -289,6 +289,15 @@ int launch_combine(const pcv_combine_params& p, cudaStream_t stream) {
                            p.o_stride_n, p.o_stride_h, nullptr, nullptr, nullptr, stream);
 }
 
+int launch_merge_partials(const pcv_merge_params& p, cudaStream_t stream) {
+  PCV_REQUIRE(p.part_o && p.part_m && p.part_l && p.out_o && p.out_m && p.out_l, PCV_ERR_INVALID, "merge_partials: null pointer");
+  PCV_REQUIRE(p.num_parts >= 1 && p.rows >= 1 && p.rows < (int64_t)1 << 31 && p.dv >= 1, PCV_ERR_INVALID,
+              "merge_partials: bad dimension");
+  // rows are independent: present them to the row-per-warp merge kernel as (B=1, H=1, N=rows)
+  return combine_t<__nv_bfloat16>(p.part_o, p.part_m, p.part_l, p.num_parts, 1, 1, (int)p.rows, p.dv, nullptr, 0, 0, 0,
+                                  p.out_o, p.out_m, p.out_l, stream);
+}
+
 int launch_combine_peers(const pcv_peer_combine_params& p, cudaStream_t stream) {
   PCV_REQUIRE(p.num_peers >= 1 && p.num_peers <= PCV_MAX_PEERS, PCV_ERR_INVALID, "combine_peers: num_peers=%d", p.num_peers);
   PCV_REQUIRE(p.rank >= 0 && p.rank < p.num_peers, PCV_ERR_INVALID, "combine_peers: bad rank %d", p.rank);

@@ -88,6 +88,7 @@ int launch_combine(const pcv_combine_params& p, cudaStream_t stream);
 int launch_combine_ex(const float* po, const float* pm, const float* pl, int nparts,
                       const pcv_attn_params& p, cudaStream_t stream);
 int launch_combine_peers(const pcv_peer_combine_params& p, cudaStream_t stream);
+int launch_merge_partials(const pcv_merge_params& p, cudaStream_t stream);
 int launch_rescale(const pcv_rescale_params& p, cudaStream_t stream);
 int launch_rotary(const pcv_rotary_params& p, cudaStream_t stream);
 int launch_kv_append(const pcv_kv_append_params& p, cudaStream_t stream);

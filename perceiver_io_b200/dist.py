@@ -230,11 +230,11 @@ def cross_attention_sharded(module, x_q: torch.Tensor, x_kv_shard: torch.Tensor,
     then the attention core is merged across ranks and ``o_proj`` is applied replicated."""
     from .utils import ModuleOutput
 
-    from .modules import project_kv
+    from .modules import fused_linear, project_kv
 
     attn = module.attention
-    q = attn.q_proj(module.q_norm(x_q))
+    q = fused_linear(module, "_pcv_q_fold", module.q_norm, attn.q_proj, x_q)
     k, v = project_kv(module, x_kv_shard)  # fused LayerNorm + K/V producer on the local shard
     o = sharded_attention(q, k, v, attn.num_heads, attn.dp_scale, m_total, m_offset, pad_mask_shard,
                           attn.causal_attention, group, kernels, merge=merge)
-    return ModuleOutput(last_hidden_state=attn.o_proj(o), kv_cache=None)
+    return ModuleOutput(last_hidden_state=fused_linear(attn, "_pcv_o_fold", None, attn.o_proj, o), kv_cache=None)

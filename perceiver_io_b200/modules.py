@@ -128,7 +128,7 @@ def attend(mha, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_mask=None
 
     o = ops.attention(q, k_att, v, mha.num_heads, mha.dp_scale, pad_mask=pad_mask,
                       causal=mha.causal_attention, impl=getattr(mha, "kernel_impl", "auto"))
-    o = mha.o_proj(o)
+    o = fused_linear(mha, "_pcv_o_fold", None, mha.o_proj, o)
     return ModuleOutput(last_hidden_state=o, kv_cache=kv_cache)
 
 
@@ -155,6 +155,36 @@ def _fold_cache(owner: nn.Module, slot: str, norm: Optional[nn.Module], linears,
     return w_cat, col_st
 
 
+def _fusable(x: torch.Tensor, linears, norm) -> bool:
+    """Inference on bf16/fp16 CUDA rows with parameters in the same dtype: the case the tcgen05 projection kernel
+    (ops.kv_project) covers; autograd, autocast, fp32 and tiny inputs stay on LayerNorm + nn.Linear (library GEMMs)."""
+    if not kv_producer_config["enabled"] or not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16):
+        return False
+    if x.numel() // max(x.shape[-1], 1) < kv_producer_config["min_rows"] or torch.is_autocast_enabled():
+        return False
+    if norm is not None and not (isinstance(norm, nn.LayerNorm) and len(norm.normalized_shape) == 1
+                                 and norm.normalized_shape[0] == x.shape[-1]):
+        return False
+    if any(lin.weight.dtype != x.dtype or lin.in_features != x.shape[-1] for lin in linears):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or any(lin.weight.requires_grad for lin in linears)
+                                    or (norm is not None and norm.weight is not None and norm.weight.requires_grad)):
+        return False
+    return True
+
+
+def fused_linear(owner: nn.Module, slot: str, norm: Optional[nn.Module], linear: nn.Linear, x: torch.Tensor):
+    """``linear(norm(x))`` (``norm`` may be None) through the tcgen05 projection kernel when it applies — the q_norm ->
+    q_proj chain of CrossAttention (reference modules.py:220, :113) and o_proj (:168) — else the library path."""
+    n_out = linear.out_features
+    if not (_fusable(x, [linear], norm) and ops.kv_project_supported(x, n_out, 0)):
+        return linear(x if norm is None else norm(x))
+    affine = norm if (norm is not None and norm.weight is not None) else None
+    w_cat, col_st = _fold_cache(owner, slot, affine, [linear], x.dtype)
+    y, _ = ops.kv_project(x, w_cat, col_st, n_out, 0, eps=None if norm is None else norm.eps)
+    return y
+
+
 def project_kv(cross_attn, x_kv: torch.Tensor):
     """``k_proj(kv_norm(x_kv)), v_proj(kv_norm(x_kv))`` of a CrossAttention (reference modules.py:226, :114-115).
 
@@ -164,16 +194,7 @@ def project_kv(cross_attn, x_kv: torch.Tensor):
     attn = cross_attn.attention
     norm = cross_attn.kv_norm
     n_k, n_v = attn.k_proj.out_features, attn.v_proj.out_features
-    needs_grad = torch.is_grad_enabled() and (x_kv.requires_grad or attn.k_proj.weight.requires_grad
-                                              or attn.v_proj.weight.requires_grad
-                                              or (norm.weight is not None and norm.weight.requires_grad))
-    rows = x_kv.numel() // max(x_kv.shape[-1], 1)
-    fused = (kv_producer_config["enabled"] and not needs_grad and rows >= kv_producer_config["min_rows"]
-             and isinstance(norm, nn.LayerNorm) and len(norm.normalized_shape) == 1
-             and norm.normalized_shape[0] == x_kv.shape[-1]
-             and attn.k_proj.weight.dtype == x_kv.dtype and not torch.is_autocast_enabled()
-             and ops.kv_project_supported(x_kv, n_k, n_v))
-    if not fused:
+    if not (_fusable(x_kv, [attn.k_proj, attn.v_proj], norm) and ops.kv_project_supported(x_kv, n_k, n_v)):
         x = norm(x_kv)
         return attn.k_proj(x), attn.v_proj(x)
     w_cat, col_st = _fold_cache(cross_attn, "_pcv_kv_fold", norm if norm.weight is not None else None,
@@ -225,13 +246,14 @@ class CrossAttention(nn.Module):
     ):
         """With ``x_kv_prefix`` (Perceiver AR) the key/value input is prefix ⧺ query, where the query
         half is normalised by ``q_norm`` and only the prefix by ``kv_norm`` (reference :222-224)."""
-        x_q = self.q_norm(x_q)
         if x_kv is None:
+            x_q = self.q_norm(x_q)
             x_kv = torch.cat([self.kv_norm(x_kv_prefix), x_q], dim=1)
             return self.attention(x_q, x_kv, pad_mask=pad_mask, rot_pos_emb_q=rot_pos_emb_q,
                                   rot_pos_emb_k=rot_pos_emb_k, kv_cache=kv_cache)
+        q = fused_linear(self, "_pcv_q_fold", self.q_norm, self.attention.q_proj, x_q)
         k, v = project_kv(self, x_kv)
-        return attend(self.attention, self.attention.q_proj(x_q), k, v, pad_mask, rot_pos_emb_q, rot_pos_emb_k, kv_cache)
+        return attend(self.attention, q, k, v, pad_mask, rot_pos_emb_q, rot_pos_emb_k, kv_cache)
 
 
 class SelfAttention(nn.Module):

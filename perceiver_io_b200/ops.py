@@ -22,7 +22,7 @@ from ._lib import (AttnParams, CombineParams, KvAppendParams, KvProjParams, LnSt
                    PcvError, check)
 
 __all__ = [
-    "attention", "attention_partial", "combine_partials", "rescale_partial_", "rotary", "kv_append",
+    "attention", "attention_partial", "combine_partials", "merge_partials", "rescale_partial_", "rotary", "kv_append",
     "device_info", "tcgen05_supported", "ln_stats", "fold_ln_linear", "kv_project", "kv_project_supported",
 ]
 
@@ -265,6 +265,29 @@ def combine_partials(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.T
         p.dtype = _pcv_dtype(cdt)
         check(_lib.lib().pcv_attn_combine(C.byref(p), _stream()), "pcv_attn_combine")
     return out if cdt == out_dtype else out.to(out_dtype)
+
+
+def merge_partials(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.Tensor, out=None):
+    """Merge G partial states (G,B,H,N,dv)/(G,B,H,N)/(G,B,H,N) into ONE un-normalised partial state
+    (B,H,N,dv)/(B,H,N)/(B,H,N) — the local level of a two-level merge.  ``out`` may supply the destination tensors
+    (e.g. views of a symmetric-memory buffer)."""
+    _require_cuda(part_o, part_m, part_l)
+    G, B, H, N, dv = part_o.shape
+    part_o, part_m, part_l = part_o.contiguous(), part_m.contiguous(), part_l.contiguous()
+    if out is None:
+        out = (torch.empty(B, H, N, dv, dtype=torch.float32, device=part_o.device),
+               torch.empty(B, H, N, dtype=torch.float32, device=part_o.device),
+               torch.empty(B, H, N, dtype=torch.float32, device=part_o.device))
+    for t in out:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("merge_partials: `out` tensors must be contiguous float32")
+    p = _lib.MergeParams()
+    p.part_o, p.part_m, p.part_l = part_o.data_ptr(), part_m.data_ptr(), part_l.data_ptr()
+    p.out_o, p.out_m, p.out_l = out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()
+    p.rows, p.num_parts, p.dv = B * H * N, G, dv
+    with torch.cuda.device(part_o.device):
+        check(_lib.lib().pcv_attn_merge_partials(C.byref(p), _stream()), "pcv_attn_merge_partials")
+    return out
 
 
 def rescale_partial_(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.Tensor, new_m: torch.Tensor) -> None:

@@ -16,17 +16,23 @@ from typing import Optional
 import torch
 
 from . import ops
-from .modules import project_kv
+from .modules import fused_linear, project_kv
 from .utils import ModuleOutput
 
 
 def cross_attention_from_host(module, x_q: torch.Tensor, x_kv_host: torch.Tensor, pad_mask: Optional[torch.Tensor] = None,
-                              chunk: int = 8192, device=None, out_host: Optional[torch.Tensor] = None):
+                              chunk: int = 8192, device=None, out_host: Optional[torch.Tensor] = None,
+                              m_total: Optional[int] = None, m_offset: int = 0, group=None):
     """``module``: a CrossAttention (this package's, or a patched reference one) living on a CUDA device.
 
     x_q: (1|B, N, D) on the device or in (pinned) host memory; x_kv_host: (B, M, C) in pinned host memory;
     pad_mask: optional (B, M) bool on host or device.  Returns ModuleOutput(last_hidden_state (B, N, F)) on the
-    device; if ``out_host`` (pinned) is given the result is also copied into it asynchronously."""
+    device; if ``out_host`` (pinned) is given the result is also copied into it asynchronously.
+
+    M-sharded use (one process per GPU, ``m_total`` given): ``x_kv_host`` is THIS rank's key shard
+    [m_offset, m_offset + M) of ``m_total``; the chunk states are merged locally (``pcv_attn_merge_partials``) into
+    the rank's partial state, which is merged across the ranks of ``group`` over peer memory (``dist.PeerMerger``)
+    before the replicated ``o_proj``."""
     attn = module.attention
     prm = next(module.parameters())
     device = prm.device if device is None else torch.device(device)
@@ -41,7 +47,7 @@ def cross_attention_from_host(module, x_q: torch.Tensor, x_kv_host: torch.Tensor
 
     with torch.cuda.device(device):
         xq = x_q.to(device, non_blocking=True)
-        q = attn.q_proj(module.q_norm(xq))
+        q = fused_linear(module, "_pcv_q_fold", module.q_norm, attn.q_proj, xq)
         bounds = [(a, min(a + chunk, M)) for a in range(0, M, chunk)]
         G = len(bounds)
         N, dv = q.shape[1], attn.num_v_channels // H
@@ -78,10 +84,20 @@ def cross_attention_from_host(module, x_q: torch.Tensor, x_kv_host: torch.Tensor
             main.wait_event(ready[slot])
             k, v = project_kv(module, views.pop(i))
             ops.attention_partial(q, k, v, H, attn.dp_scale, pad_mask=None if pad_dev is None else pad_dev[:, a:b],
-                                  causal=False, m_total=M, m_offset=a, out=(part_o[i], part_m[i], part_l[i]))
+                                  causal=False, m_total=M if m_total is None else m_total, m_offset=m_offset + a,
+                                  out=(part_o[i], part_m[i], part_l[i]))
             freed[slot].record(main)
-        o = ops.combine_partials(part_o, part_m, part_l, q.dtype)
-        out = attn.o_proj(o)
+        if m_total is None:
+            o = ops.combine_partials(part_o, part_m, part_l, q.dtype)
+        else:
+            from .dist import PeerMerger
+
+            cdt = q.dtype if q.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
+            pm = PeerMerger.get(B, H, N, dv, cdt, device, group)
+            ops.merge_partials(part_o, part_m, part_l, out=(pm.po, pm.pm, pm.pl))
+            o = pm.merge()
+            o = o if o.dtype == q.dtype else o.to(q.dtype)
+        out = fused_linear(attn, "_pcv_o_fold", None, attn.o_proj, o)
         if out_host is not None:
             out_host.copy_(out, non_blocking=True)
     return ModuleOutput(last_hidden_state=out, kv_cache=None)

@@ -126,7 +126,11 @@ def _csm(seed=7):
 def test_patch_on_reference_causal_sequence_model_logits_and_cache():
     """Perceiver AR: left padding, right-aligned rotary over all head channels, causal prefix cross-attention,
     causal latent stack; then 3 cached decode steps must agree with the uncached forward (the reference's own
-    tests/kv_cache_test.py:191-234 pattern) and with the reference's fp64 logits."""
+    tests/kv_cache_test.py:191-234 pattern) and with the reference's fp64 logits.  The bf16 arms run the fp32 model
+    under torch.autocast (Lightning's precision="bf16"): a `.bfloat16()` model computes its rotary angles
+    position x inv_freq in bf16 — radians of error at position 1400 in BOTH arms, which would drown the comparison."""
+    import perceiver_io_b200 as P
+
     m = _csm()
     g = torch.Generator().manual_seed(8)
     B, n0, prefix = 2, 1400, 1000
@@ -136,14 +140,17 @@ def test_patch_on_reference_causal_sequence_model_logits_and_cache():
     t, p = tokens.cuda(), pad.cuda()
     with torch.no_grad():
         m64 = copy.deepcopy(m).double().cuda()
-        m16 = copy.deepcopy(m).bfloat16().cuda()
-        mine = _patched_bf16(m)
+        m16 = copy.deepcopy(m).cuda()
+        mine = copy.deepcopy(m).cuda()
+        assert P.patch(mine) > 0
         r64 = m64(t[:, :n0], prefix_len=prefix, pad_mask=p[:, :n0]).logits
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         eager = m16(t[:, :n0], prefix_len=prefix, pad_mask=p[:, :n0]).logits
         full = mine(t[:, :n0], prefix_len=prefix, pad_mask=p[:, :n0], kv_cache=[])
         _gate(full.logits, r64, eager, "reference CausalSequenceModel, patched: full forward logits")
         cache = full.kv_cache
-        r64_all = m64(t, prefix_len=prefix, pad_mask=p).logits
+        with torch.autocast("cuda", enabled=False):
+            r64_all = m64(t, prefix_len=prefix, pad_mask=p).logits
         eager_all = m16(t, prefix_len=prefix, pad_mask=p).logits
         for s in range(3):
             step = mine(t[:, n0 + s: n0 + s + 1], prefix_len=prefix, pad_mask=p[:, : n0 + s + 1], kv_cache=cache)
