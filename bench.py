@@ -477,8 +477,9 @@ def main():
     ap.add_argument("--kernel", choices=["auto", "tcgen05", "simt"], default="auto")
     ap.add_argument("--kv-layout", choices=["token_major", "head_major"], default="token_major",
                     help="memory layout of the projected K/V: (B,M,H*dh) as nn.Linear writes it, or (B,H,M,dh)")
-    ap.add_argument("--merge", choices=["auto", "peer", "nccl"], default="auto",
-                    help="multi-GPU merge transport: symmetric-memory peer kernel or NCCL all-reduces")
+    ap.add_argument("--merge", choices=["auto", "fused", "peer", "nccl"], default="auto",
+                    help="multi-GPU merge: fused into the attention kernel's tail (one launch), separate symmetric-memory peer "
+                         "kernel with host-launched barriers, or NCCL all-reduces")
     ap.add_argument("--e2e-mode", choices=["streamed", "plain"], default="streamed",
                     help="1-GPU e2e leg: chunked host->device pipeline (streaming.cross_attention_from_host) or one big copy")
     ap.add_argument("--e2e-chunk", type=int, default=8192)

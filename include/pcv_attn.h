@@ -274,6 +274,28 @@ typedef struct pcv_ln_stats_params {
   int32_t reserved;
 } pcv_ln_stats_params;
 
+/*
+ * M-sharded attention with the cross-GPU merge FUSED INTO THE KERNEL TAIL (SURVEY.md §8(e) option 3): one launch per
+ * rank computes the partial softmax state of this rank's key shard, publishes it to its peers through NVLink-mapped
+ * symmetric memory, merges the rows it owns from all ranks and pushes the normalised rows into every rank's output
+ * buffer.  No NCCL and no host-launched barrier is on the path; the kernel returns when this rank's output buffer is
+ * complete.  All ranks must call with the same shapes and the same `epoch` (1, 2, 3, ... per call on one set of
+ * buffers); `p` is a pcv_attn_params with write_partial = 1 (part_* are ignored: the state lives in part[rank]).
+ *   part[g]  : rank g's buffer, f32 [ numerator (B,H,N,dv) | row max (B,H,N) | denominator (B,H,N) ]
+ *   out[g]   : rank g's output (B,N,H,dv) in p->dtype with the strides below; every rank ends with the full result
+ *   flags[g] : rank g's flag block, >= 32 zero-initialised uint32 words (never reset: values are epochs)
+ * Rank r merges rows [R*r/G, R*(r+1)/G) of the flattened (b,h,n) space, R = B*H*N.
+ */
+typedef struct pcv_shard_fuse {
+  void* part[PCV_MAX_PEERS];
+  void* out[PCV_MAX_PEERS];
+  uint32_t* flags[PCV_MAX_PEERS];
+  int64_t o_stride_b, o_stride_n, o_stride_h;
+  int32_t num_peers, rank;
+  uint32_t epoch;
+  int32_t reserved;
+} pcv_shard_fuse;
+
 /* library / device introspection */
 typedef struct pcv_device_info {
   int32_t device;
@@ -294,6 +316,9 @@ PCV_API int pcv_attn_fwd(const pcv_attn_params* p, void* stream);
 PCV_API int pcv_attn_combine(const pcv_combine_params* p, void* stream);
 PCV_API int pcv_attn_combine_peers(const pcv_peer_combine_params* p, void* stream);
 PCV_API int pcv_attn_merge_partials(const pcv_merge_params* p, void* stream);
+/* 1 if pcv_attn_fwd_sharded covers this problem (tcgen05 kernel, head dims <= 128 / 256, dv % 4 == 0) */
+PCV_API int pcv_attn_fwd_sharded_supported(const pcv_attn_params* p);
+PCV_API int pcv_attn_fwd_sharded(const pcv_attn_params* p, const pcv_shard_fuse* fuse, void* stream);
 PCV_API int pcv_partial_rescale(const pcv_rescale_params* p, void* stream);
 PCV_API int pcv_rotary_apply(const pcv_rotary_params* p, void* stream);
 PCV_API int pcv_kv_append(const pcv_kv_append_params* p, void* stream);

@@ -30,6 +30,8 @@ EXPORTS = (
     "pcv_attn_combine",
     "pcv_attn_combine_peers",
     "pcv_attn_merge_partials",
+    "pcv_attn_fwd_sharded_supported",
+    "pcv_attn_fwd_sharded",
     "pcv_partial_rescale",
     "pcv_rotary_apply",
     "pcv_kv_append",
@@ -100,6 +102,14 @@ class PeerCombineParams(C.Structure):
         ("num_peers", C.c_int32), ("rank", C.c_int32),
         ("B", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("dv", C.c_int32),
         ("dtype", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class ShardFuse(C.Structure):
+    _fields_ = [
+        ("part", C.c_void_p * PCV_MAX_PEERS), ("out", C.c_void_p * PCV_MAX_PEERS), ("flags", C.c_void_p * PCV_MAX_PEERS),
+        ("o_stride_b", C.c_int64), ("o_stride_n", C.c_int64), ("o_stride_h", C.c_int64),
+        ("num_peers", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("reserved", C.c_int32),
     ]
 
 
@@ -199,6 +209,10 @@ def lib() -> C.CDLL:
         l.pcv_attn_combine_peers.restype = C.c_int
         l.pcv_attn_merge_partials.argtypes = [C.POINTER(MergeParams), C.c_void_p]
         l.pcv_attn_merge_partials.restype = C.c_int
+        l.pcv_attn_fwd_sharded_supported.argtypes = [C.POINTER(AttnParams)]
+        l.pcv_attn_fwd_sharded_supported.restype = C.c_int
+        l.pcv_attn_fwd_sharded.argtypes = [C.POINTER(AttnParams), C.POINTER(ShardFuse), C.c_void_p]
+        l.pcv_attn_fwd_sharded.restype = C.c_int
         l.pcv_profile_begin.restype = C.c_int
         l.pcv_profile_end.restype = C.c_int
         l.pcv_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32)]

@@ -169,6 +169,32 @@ int pcv_attn_fwd(const pcv_attn_params* p, void* stream) {
   return launch_attn_simt(*p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int pcv_attn_fwd_sharded_supported(const pcv_attn_params* p) {
+  if (validate_attn(p) != PCV_OK) return 0;
+  const char* why = "";
+  const bool ok = p->impl != PCV_IMPL_SIMT && attn_tc_fuse_supported(*p, &why);
+  if (!ok) set_error("fused M-shard merge not applicable: %s", why);
+  return ok ? 1 : 0;
+}
+
+int pcv_attn_fwd_sharded(const pcv_attn_params* p, const pcv_shard_fuse* f, void* stream) {
+  PCV_REQUIRE(p != nullptr && f != nullptr, PCV_ERR_INVALID, "attn_fwd_sharded: NULL argument");
+  PCV_REQUIRE(f->num_peers >= 1 && f->num_peers <= PCV_MAX_PEERS && f->rank >= 0 && f->rank < f->num_peers, PCV_ERR_INVALID,
+              "attn_fwd_sharded: rank %d of %d", f->rank, f->num_peers);
+  PCV_REQUIRE(f->epoch >= 1, PCV_ERR_INVALID, "attn_fwd_sharded: epoch must start at 1");
+  for (int g = 0; g < f->num_peers; ++g)
+    PCV_REQUIRE(f->part[g] && f->out[g] && f->flags[g], PCV_ERR_INVALID, "attn_fwd_sharded: NULL buffer of rank %d", g);
+  pcv_attn_params q = *p;
+  q.write_partial = 1;
+  // validate_attn wants part_* for a partial launch; they are replaced by part[rank] inside the launcher
+  q.part_o = reinterpret_cast<float*>(f->part[f->rank]);
+  q.part_m = q.part_o;
+  q.part_l = q.part_o;
+  int rc = validate_attn(&q);
+  if (rc != PCV_OK) return rc;
+  return launch_attn_tc(q, reinterpret_cast<cudaStream_t>(stream), f);
+}
+
 int pcv_attn_combine(const pcv_combine_params* p, void* stream) {
   PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "combine: params is NULL");
   return launch_combine(*p, reinterpret_cast<cudaStream_t>(stream));

@@ -27,6 +27,7 @@
 
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -59,13 +60,31 @@ struct Segment {
   int ntile;   // 1 or 2 active query tiles
   int t0, t1;  // key tiles [t0, t1)
   int slot;    // >= 0: partial slot index; -1: the segment covers every key tile (final)
-  int pad_;
+  int unit;    // >= 0: index of the split unit (UnitRec) this segment is a part of; -1: whole key range
 };
 
 struct UnitRec {  // a (b,h,query-block) whose key range was split over several segments
   int b, h, q0;
   int slot_begin, slot_count;
   int pad_[3];
+};
+
+// M-sharded launch with the cross-GPU merge fused into the kernel tail (pcv_attn_fwd_sharded): after its segments
+// every CTA turns into a merge worker.  All pointers of index g are rank g's symmetric-memory buffers as mapped
+// into THIS process (index `rank` is the local one).  Flag words per rank: [0, G) "partial state of rank i is
+// complete" (written by rank i), [G, 2G) "rank i has pushed all its output rows" (written by rank i), [16, 19)
+// grid-wide arrival counters of the local kernel.  All flags / counters are monotonic in the call epoch.
+struct PeerTail {
+  int enabled;
+  int num_peers, rank;
+  uint32_t epoch;
+  const float* part_o[PCV_MAX_PEERS];
+  const float* part_m[PCV_MAX_PEERS];
+  const float* part_l[PCV_MAX_PEERS];
+  void* out[PCV_MAX_PEERS];
+  uint32_t* flags[PCV_MAX_PEERS];
+  int64_t osb, osn, osh;
+  int64_t row_begin, row_end;  // rows of the flattened (b, h, n) space this rank merges
 };
 
 struct TcParams {
@@ -85,11 +104,19 @@ struct TcParams {
   int write_partial;
   float *fin_o, *fin_m, *fin_l;     // caller's partial state (B,H,N,dv),(B,H,N),(B,H,N)
   float *slot_o, *slot_m, *slot_l;  // workspace slots [slot][256][DV], [slot][256]
+  // in-kernel fix-up of split units (attn_tc_kernel): the segment that starts at key tile 0 is the LAST segment of
+  // its CTA, all other parts of the unit are FIRST segments of theirs (or whole CTAs) — it finishes last, waits for
+  // the per-warp "rows stored" flags of the other parts and folds their slots into its own accumulator rows while
+  // writing the result, so no separate merge kernel (and no extra pass over the state) is needed.
+  const UnitRec* units;
+  unsigned long long* slot_flags;   // [slot][8]: == fixup_tag once warp w of that part has stored its 32 rows
+  unsigned long long fixup_tag;     // unique per launch (workspace memory is not cleared between launches)
   int rows_per_unit;                // query rows per work unit: 256 (two tiles per CTA) or 128 (wide-dv / big-head)
   int slot_rows;                    // row stride of the partial slots (>= rows_per_unit)
   int optimistic;                   // 1: exponentiate against the current reference, verify the range afterwards
   int mmaopt;                       // attn_tc_kernel issuer: bit 0 = overlapped barrier probes, bit 1 = deferred kv_empty commits
   unsigned long long* trace;        // debugging aid (PCV_TRACE=1): clock64 stamps of CTA 0, [role][tile][event]
+  PeerTail tail;
 };
 
 template <int DQK, int DV>
@@ -352,70 +379,152 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
   return true;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// wait (bounded) until another CTA's warp has published its 32 slot rows; call with the whole warp converged
+__device__ __forceinline__ void wait_slot_rows(const TcParams& p, int slot, int warp_in_unit) {
+  const unsigned long long* f = p.slot_flags + (int64_t)slot * 8 + warp_in_unit;
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (ld_acquire_gpu_u64(f) != p.fixup_tag) {
+      if ((++spins & 0xFFu) == 0) {
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) {
+          t0 = now;
+        } else if (now - t0 > kWaitTimeoutNs) {
+          uint32_t* d = g_wait_diag;
+          if (d != nullptr && atomicCAS(d, 0u, 1u) == 0u) {
+            d[1] = 40;
+            d[2] = blockIdx.x;
+            d[3] = threadIdx.x;
+            d[4] = (uint32_t)slot;
+            d[5] = spins;
+            __threadfence_system();
+          }
+          __trap();
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // O row of this thread (TMEM, `DV` accumulator columns starting at tO) -> global memory: the normalised output,
 // the caller's partial state, or a split-M slot.  Channels [0, dv_pass) of the accumulator map to output channels
-// [dv_off, dv_off + dv_pass) (dv_off > 0 only in the second pass of the big-head kernel).
-template <int DV, bool BF16>
+// [dv_off, dv_off + dv_pass) (dv_off > 0 only in the second pass of the big-head kernel).  With FIXUP the part of a
+// split unit that starts at key tile 0 merges the other parts' slots on the fly and writes the unit's result.
+template <int DV, bool BF16, bool FIXUP>
 __device__ __forceinline__ void epilogue_row(const TcParams& p, const Segment& seg, uint32_t tO, int n,
                                              int row_in_unit, float l, float m_ref) {
   const bool valid = n < p.N;
-  if (seg.slot < 0 && !p.write_partial) {
-    const float inv = 1.f / l;
-    char* orow = reinterpret_cast<char*>(p.out) +
-                 2 * ((int64_t)seg.b * p.osb + (int64_t)n * p.osn + (int64_t)seg.h * p.osh);
+  const bool owner = FIXUP && seg.slot >= 0 && seg.t0 == 0;
+  if (seg.slot >= 0 && !owner) {
+    // one part of a split unit: un-normalised rows into the slot, then (FIXUP) tell the owning part
+    const int64_t r = (int64_t)seg.slot * p.slot_rows + row_in_unit;
+    float* dst = p.slot_o + r * DV;
+    p.slot_m[r] = m_ref;
+    p.slot_l[r] = l;
 #pragma unroll
     for (int ch = 0; ch < DV / 32; ++ch) {
       uint32_t o[32];
       tmem_ld32(tO + ch * 32, o);
       tmem_wait_ld();
-      if (valid) {
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const int col = ch * 32 + c8 * 8;
-          if (col < p.dv_pass) {
-            uint4 w;
-            w.x = pack2(__uint_as_float(o[c8 * 8 + 0]) * inv, __uint_as_float(o[c8 * 8 + 1]) * inv, BF16);
-            w.y = pack2(__uint_as_float(o[c8 * 8 + 2]) * inv, __uint_as_float(o[c8 * 8 + 3]) * inv, BF16);
-            w.z = pack2(__uint_as_float(o[c8 * 8 + 4]) * inv, __uint_as_float(o[c8 * 8 + 5]) * inv, BF16);
-            w.w = pack2(__uint_as_float(o[c8 * 8 + 6]) * inv, __uint_as_float(o[c8 * 8 + 7]) * inv, BF16);
-            *reinterpret_cast<uint4*>(orow + 2 * (p.dv_off + col)) = w;
-          }
-        }
-      }
+      for (int c4 = 0; c4 < 8; ++c4)
+        *reinterpret_cast<uint4*>(dst + ch * 32 + c4 * 4) = make_uint4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
     }
-  } else {
-    float* dst;
-    int ncols;
-    bool store;
-    if (seg.slot < 0) {  // whole key range, caller wants the un-normalised state
-      const int64_t r = ((int64_t)seg.b * p.H + seg.h) * p.N + n;
-      dst = p.fin_o + r * p.dv + p.dv_off;
-      ncols = p.dv_pass;
-      store = valid;
-      if (valid) {
-        p.fin_m[r] = m_ref;
-        p.fin_l[r] = l;
-      }
-    } else {
-      const int64_t r = (int64_t)seg.slot * p.slot_rows + row_in_unit;
-      dst = p.slot_o + r * DV;
-      ncols = DV;
-      store = true;
-      p.slot_m[r] = m_ref;
-      p.slot_l[r] = l;
+    if (FIXUP) {
+      __threadfence();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) st_release_gpu_u64(p.slot_flags + (int64_t)seg.slot * 8 + (row_in_unit >> 5), p.fixup_tag);
     }
+    return;
+  }
+
+  // this thread writes the row's result: whole key range, or the owning part of a split unit
+  float w_own = 1.f;
+  int s_begin = 0, s_end = 0;
+  if (owner) {
+    const UnitRec u = p.units[seg.unit];
+    s_begin = u.slot_begin;
+    s_end = u.slot_begin + u.slot_count;
+    float m = m_ref;
+    for (int sl = s_begin; sl < s_end; ++sl) {
+      if (sl == seg.slot) continue;
+      wait_slot_rows(p, sl, row_in_unit >> 5);
+      m = fmaxf(m, __ldcg(p.slot_m + (int64_t)sl * p.slot_rows + row_in_unit));
+    }
+    w_own = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m);
+    float lt = l * w_own;
+    for (int sl = s_begin; sl < s_end; ++sl) {
+      if (sl == seg.slot) continue;
+      const int64_t r = (int64_t)sl * p.slot_rows + row_in_unit;
+      const float ms = __ldcg(p.slot_m + r);
+      lt = fmaf(__ldcg(p.slot_l + r), (ms == -INFINITY) ? 0.f : exp2f(ms - m), lt);
+    }
+    l = lt;
+    m_ref = m;
+  }
+  const float inv = 1.f / l;
+  const int64_t fr = ((int64_t)seg.b * p.H + seg.h) * p.N + n;
+  char* orow = reinterpret_cast<char*>(p.out) + 2 * ((int64_t)seg.b * p.osb + (int64_t)n * p.osn + (int64_t)seg.h * p.osh);
+  if (p.write_partial && valid) {
+    p.fin_m[fr] = m_ref;
+    p.fin_l[fr] = l;
+  }
 #pragma unroll
-    for (int ch = 0; ch < DV / 32; ++ch) {
-      uint32_t o[32];
-      tmem_ld32(tO + ch * 32, o);
-      tmem_wait_ld();
-      if (store) {
+  for (int ch = 0; ch < DV / 32; ++ch) {
+    uint32_t o[32];
+    tmem_ld32(tO + ch * 32, o);
+    tmem_wait_ld();
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * w_own);
+      for (int sl = s_begin; sl < s_end; ++sl) {
+        if (sl == seg.slot) continue;
+        const int64_t r = (int64_t)sl * p.slot_rows + row_in_unit;
+        const float ms = __ldcg(p.slot_m + r);
+        const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - m_ref);
+        const float4* src = reinterpret_cast<const float4*>(p.slot_o + r * DV + ch * 32);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          const int col = ch * 32 + c4 * 4;
-          if (col < ncols)
-            *reinterpret_cast<uint4*>(dst + col) = make_uint4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
+          const float4 x = __ldcg(src + c4);
+          o[c4 * 4 + 0] = __float_as_uint(fmaf(x.x, w, __uint_as_float(o[c4 * 4 + 0])));
+          o[c4 * 4 + 1] = __float_as_uint(fmaf(x.y, w, __uint_as_float(o[c4 * 4 + 1])));
+          o[c4 * 4 + 2] = __float_as_uint(fmaf(x.z, w, __uint_as_float(o[c4 * 4 + 2])));
+          o[c4 * 4 + 3] = __float_as_uint(fmaf(x.w, w, __uint_as_float(o[c4 * 4 + 3])));
         }
+      }
+    }
+    if (!valid) continue;
+    if (!p.write_partial) {
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const int col = ch * 32 + c8 * 8;
+        if (col < p.dv_pass) {
+          uint4 w;
+          w.x = pack2(__uint_as_float(o[c8 * 8 + 0]) * inv, __uint_as_float(o[c8 * 8 + 1]) * inv, BF16);
+          w.y = pack2(__uint_as_float(o[c8 * 8 + 2]) * inv, __uint_as_float(o[c8 * 8 + 3]) * inv, BF16);
+          w.z = pack2(__uint_as_float(o[c8 * 8 + 4]) * inv, __uint_as_float(o[c8 * 8 + 5]) * inv, BF16);
+          w.w = pack2(__uint_as_float(o[c8 * 8 + 6]) * inv, __uint_as_float(o[c8 * 8 + 7]) * inv, BF16);
+          *reinterpret_cast<uint4*>(orow + 2 * (p.dv_off + col)) = w;
+        }
+      }
+    } else {
+      float* dst = p.fin_o + fr * p.dv + p.dv_off;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const int col = ch * 32 + c4 * 4;
+        if (col < p.dv_pass)
+          *reinterpret_cast<uint4*>(dst + col) = make_uint4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
       }
     }
   }
@@ -481,11 +590,181 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     mbar_wait(&bar.o_full[wg], n_o & 1, 13);
     ++n_o;
     tc_fence_after_sync();
-    epilogue_row<DV, BF16>(p, seg, tO, n, row_in_unit, l, m_ref);
+    epilogue_row<DV, BF16, true>(p, seg, tO, n, row_in_unit, l, m_ref);
     tc_fence_before_sync();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&bar.o_empty[wg]);
   }
+}
+
+// --------------------------------------------------------------------------------------------------
+// fused cross-GPU merge (kernel tail of an M-sharded launch; SURVEY.md §8(e) option 3)
+//
+//   A  grid-wide arrival: every partial-state row of this GPU is written (system-scope fence first; split units
+//      were already folded together by the epilogue fix-up)
+//   2  "ready" flag of this rank is stored (release, system scope) into every peer's flag block
+//   3  wait until every peer's ready flag shows this call's epoch
+//   4  owned rows: pull (m, l, numerator row) of every rank through the NVLink-mapped pointers (relaxed system-scope
+//      loads: the same addresses are re-read every call, they must not be served from a stale L1 line), merge exactly,
+//      push the normalised row into the output buffer of EVERY rank
+//   5  grid-wide arrival, then the "done" flag of this rank goes to every peer; CTA 0 waits for all done flags, so
+//      the kernel only completes when this GPU's output buffer has received every row slice — no host-side barrier
+// Executed by the 8 softmax warps (the control warps hold 88 registers); CTA-level sync is named barrier 2.
+// Every wait is bounded by the watchdog (a dead peer becomes a trap with a diagnosis, not a hung GPU).  Needs all
+// CTAs of the grid co-resident: grid <= #SMs at one CTA per SM, which is how this kernel is always launched.
+// --------------------------------------------------------------------------------------------------
+constexpr int kTailThreads = 256;
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f32x4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void tail_wait_ge(const uint32_t* flag, uint32_t value, uint32_t site) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while ((int32_t)(ld_acquire_sys_u32(flag) - value) < 0) {
+    if ((++spins & 0xFFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > kWaitTimeoutNs) {
+        uint32_t* d = g_wait_diag;
+        if (d != nullptr && atomicCAS(d, 0u, 1u) == 0u) {
+          d[1] = site;
+          d[2] = blockIdx.x;
+          d[3] = threadIdx.x;
+          d[4] = value;
+          d[5] = ld_acquire_sys_u32(flag);
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
+  }
+}
+
+// all kTailThreads threads of every CTA call this; `counter` is a device-local word, monotonic over calls
+__device__ __forceinline__ void tail_grid_arrive_wait(uint32_t* counter, uint32_t target, uint32_t site) {
+  __threadfence_system();  // this thread's partial-state / output stores are visible system-wide before the arrival
+  named_bar_sync(2, kTailThreads);
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1u);
+    tail_wait_ge(counter, target, site);
+  }
+  named_bar_sync(2, kTailThreads);
+}
+
+template <int DV, bool BF16>
+__device__ void peer_tail(const TcParams& p) {
+  const PeerTail& t = p.tail;
+  const int G = t.num_peers;
+  uint32_t* lf = t.flags[t.rank];
+  const uint32_t target = t.epoch * gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = kTailThreads / 32;
+  // phase clock of CTA 0 (ns since tail entry) in flag words [24, 30): cheap, always on, read by tools/dist_check.py
+  const uint64_t t_in = globaltimer_ns();
+#define PCV_TAIL_STAMP(i)                                                                      \
+  do {                                                                                         \
+    if (blockIdx.x == 0 && threadIdx.x == 0) lf[24 + (i)] = (uint32_t)(globaltimer_ns() - t_in); \
+  } while (0)
+
+  tail_grid_arrive_wait(lf + 16, target, 30);
+  PCV_TAIL_STAMP(0);
+
+  PCV_TAIL_STAMP(1);
+
+  // publish: flags[g][rank] = epoch on every rank g (release: ordered after the grid-wide arrival above)
+  if (blockIdx.x == 0 && threadIdx.x < G) st_release_sys_u32(t.flags[threadIdx.x] + t.rank, t.epoch);
+  if (threadIdx.x < G) tail_wait_ge(lf + threadIdx.x, t.epoch, 32);
+  named_bar_sync(2, kTailThreads);
+  PCV_TAIL_STAMP(2);
+
+  // owned rows: pull, merge, push.  A warp keeps PCV_MAX_PEERS (row, rank) sources in flight at once — with 2 ranks
+  // that is 4 rows per iteration — so that every lane always has 8 x 16 bytes of (mostly remote) loads outstanding;
+  // with one row per warp iteration the phase is bound by the NVLink round trip, not by bandwidth.
+  const int RB = PCV_MAX_PEERS / G;  // rows per warp iteration
+  const int64_t nblk = (t.row_end - t.row_begin + RB - 1) / RB;
+  for (int64_t blk = (int64_t)blockIdx.x * kWarps + warp; blk < nblk; blk += (int64_t)gridDim.x * kWarps) {
+    const int64_t r0 = t.row_begin + blk * RB;
+    for (int c = lane * 4; c < p.dv; c += 128) {
+      float mg[PCV_MAX_PEERS], lg[PCV_MAX_PEERS];
+      float4 x[PCV_MAX_PEERS];
+#pragma unroll
+      for (int j = 0; j < PCV_MAX_PEERS; ++j) {
+        const int rr = j / G, g = j - rr * G;   // source j = row r0 + rr of rank g
+        const int64_t r = r0 + rr;
+        const bool live = rr < RB && r < t.row_end;
+        mg[j] = -INFINITY;
+        lg[j] = 0.f;
+        x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+          mg[j] = ld_relaxed_sys_f32(t.part_m[g] + r);
+          lg[j] = ld_relaxed_sys_f32(t.part_l[g] + r);
+          x[j] = ld_relaxed_sys_f32x4(t.part_o[g] + r * p.dv + c);
+        }
+      }
+      for (int rr = 0; rr < RB; ++rr) {
+        const int64_t r = r0 + rr;
+        if (r >= t.row_end) break;
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < PCV_MAX_PEERS; ++j)
+          if (j / G == rr) m = fmaxf(m, mg[j]);
+        float l = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < PCV_MAX_PEERS; ++j) {
+          if (j / G != rr) continue;
+          const float w = (mg[j] != -INFINITY) ? exp2f(mg[j] - m) : 0.f;
+          l = fmaf(lg[j], w, l);
+          acc.x = fmaf(x[j].x, w, acc.x);
+          acc.y = fmaf(x[j].y, w, acc.y);
+          acc.z = fmaf(x[j].z, w, acc.z);
+          acc.w = fmaf(x[j].w, w, acc.w);
+        }
+        const float inv = 1.f / l;
+        uint2 packed;
+        packed.x = pack2(acc.x * inv, acc.y * inv, BF16);
+        packed.y = pack2(acc.z * inv, acc.w * inv, BF16);
+        const int n = (int)(r % p.N);
+        const int h = (int)((r / p.N) % p.H);
+        const int b = (int)(r / ((int64_t)p.N * p.H));
+        const int64_t o_off = (int64_t)b * t.osb + (int64_t)n * t.osn + (int64_t)h * t.osh;
+#pragma unroll
+        for (int g = 0; g < PCV_MAX_PEERS; ++g)
+          if (g < G) *reinterpret_cast<uint2*>(reinterpret_cast<char*>(t.out[g]) + 2 * (o_off + c)) = packed;
+      }
+    }
+  }
+
+  PCV_TAIL_STAMP(3);
+  tail_grid_arrive_wait(lf + 18, target, 33);
+  PCV_TAIL_STAMP(4);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < G) {
+      st_release_sys_u32(t.flags[threadIdx.x] + G + t.rank, t.epoch);
+      tail_wait_ge(lf + G + threadIdx.x, t.epoch, 34);
+    }
+    named_bar_sync(2, kTailThreads);
+  }
+  PCV_TAIL_STAMP(5);
+#undef PCV_TAIL_STAMP
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -550,6 +829,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp < 8) {
     reg_alloc<208>();  // 256*208 + 128*88 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
     softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
+    if (p.tail.enabled) peer_tail<DV, BF16>(p);
   } else {
     reg_dealloc<88>();
   }
@@ -868,7 +1148,7 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       mbar_wait(&bb.o_full, n_o & 1, 13);
       ++n_o;
       tc_fence_after_sync();
-      epilogue_row<256, BF16>(p, seg, tO, n, row, st.l, st.m_ref);
+      epilogue_row<256, BF16, false>(p, seg, tO, n, row, st.l, st.m_ref);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bb.o_empty);
@@ -1087,6 +1367,7 @@ void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms, int rows_per_
         for (int r = 0; r < QB; ++r) {
           Segment s{};
           s.b = bh / H; s.h = bh % H; s.q0 = r * rows_per_unit; s.ntile = ntile_of(r); s.t0 = t0; s.t1 = t1;
+          s.unit = -1;
           if (t0 == 0 && t1 == T) {
             s.slot = -1;
           } else {
@@ -1099,18 +1380,24 @@ void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms, int rows_per_
       }
     }
     // slots of one unit must be contiguous for the combine kernel: renumber
-    std::map<int, int> remap;
+    std::map<int, int> remap, unit_of;
     int next = 0;
     for (auto& kv : unit_slots) {
       UnitRec u{};
       u.b = kv.first.first / H; u.h = kv.first.first % H; u.q0 = kv.first.second * rows_per_unit;
       u.slot_begin = next; u.slot_count = (int)kv.second.size();
-      for (int old : kv.second) remap[old] = next++;
+      for (int old : kv.second) {
+        unit_of[old] = (int)pl.units.size();
+        remap[old] = next++;
+      }
       pl.units.push_back(u);
     }
     for (auto& v : per_cta)
       for (auto& s : v)
-        if (s.slot >= 0) s.slot = remap[s.slot];
+        if (s.slot >= 0) {
+          s.unit = unit_of[s.slot];
+          s.slot = remap[s.slot];
+        }
   } else {
     // many query blocks: whole (b,h,query-block) units, contiguous chunks per CTA, no splitting
     const int64_t U = (int64_t)BH * QB;
@@ -1121,6 +1408,7 @@ void build_plan(Plan& pl, int B, int H, int N, int M, int num_sms, int rows_per_
         const int bh = (int)(u / QB), qb = (int)(u % QB);
         Segment s{};
         s.b = bh / H; s.h = bh % H; s.q0 = qb * rows_per_unit; s.ntile = ntile_of(qb); s.t0 = 0; s.t1 = T; s.slot = -1;
+        s.unit = -1;
         per_cta[c].push_back(s);
       }
     }
@@ -1272,7 +1560,8 @@ int make_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int ro
 inline int pad64(int d) { return (d + 63) / 64 * 64; }
 
 size_t slots_bytes(const Plan& pl, int DV, int slot_rows) {
-  return sizeof(float) * (size_t)pl.num_slots * slot_rows * (DV + 2);
+  // [slot][row][DV] numerators, [slot][row] row max, [slot][row] denominators, then [slot][8] 64-bit fix-up flags
+  return sizeof(float) * (size_t)pl.num_slots * slot_rows * (DV + 2) + sizeof(unsigned long long) * (size_t)pl.num_slots * 8;
 }
 
 Mode choose_mode(const pcv_attn_params& a) {
@@ -1297,18 +1586,19 @@ int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, 
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
+  if (p.tail.enabled || pl.num_units > 0) {
+    // grid-wide arrivals of the merge tail and the in-kernel fix-up of split units (one part waits for flags written
+    // by other CTAs) both need every CTA of the grid co-resident
+    int sms = 0;
+    PCV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PCV_REQUIRE(pl.num_ctas <= sms, PCV_ERR_UNSUPPORTED, "%d CTAs cannot be co-resident on %d SMs", pl.num_ctas, sms);
+  }
   prof_mark_begin(stream);
   kern<<<pl.num_ctas, kThreads, C::kSmemBytes, stream>>>(tq, tk, tv, p);
   prof_mark_end(stream);
   PCV_CHECK_CUDA(cudaGetLastError());
   count_launch();
-  if (pl.num_units > 0) {
-    dim3 grid(pl.num_units, p.slot_rows / 8);
-    tc_combine_kernel<DV, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
-    PCV_CHECK_CUDA(cudaGetLastError());
-    count_launch();
-  }
-  return PCV_OK;
+  return PCV_OK;  // split units are merged by the fix-up in the kernel's own epilogue: no second launch
 }
 
 template <bool BF16>
@@ -1415,7 +1705,21 @@ int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
   return PCV_OK;
 }
 
-int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
+bool attn_tc_fuse_supported(const pcv_attn_params& a, const char** why) {
+  if (!attn_tc_supported(a, why)) return false;
+  const Mode mode = choose_mode(a);
+  if (mode.big) {
+    *why = "the fused merge tail is built into the head-dim <= 128 / v-dim <= 256 kernel only";
+    return false;
+  }
+  if (a.dv % 4) {
+    *why = "fused merge needs v head dim % 4 == 0";
+    return false;
+  }
+  return true;
+}
+
+int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream, const pcv_shard_fuse* fuse) {
   std::shared_ptr<Plan> pl;
   const int DQK = pad64(a.dqk), DV = pad64(a.dv);
   const Mode mode = choose_mode(a);
@@ -1458,12 +1762,45 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream) {
   }
 #endif
   p.fin_o = a.part_o; p.fin_m = a.part_m; p.fin_l = a.part_l;
+  if (fuse != nullptr) {
+    const char* why = "";
+    PCV_REQUIRE(attn_tc_fuse_supported(a, &why), PCV_ERR_UNSUPPORTED, "fused merge: %s", why);
+    PCV_REQUIRE(a.write_partial, PCV_ERR_INVALID, "fused merge: the launch must write the partial state (write_partial = 1)");
+    PeerTail& t = p.tail;
+    t.enabled = 1;
+    t.num_peers = fuse->num_peers;
+    t.rank = fuse->rank;
+    t.epoch = fuse->epoch;
+    const int64_t R = (int64_t)a.B * a.H * a.N;
+    for (int g = 0; g < fuse->num_peers; ++g) {
+      const float* base = reinterpret_cast<const float*>(fuse->part[g]);
+      t.part_o[g] = base;
+      t.part_m[g] = base + R * a.dv;
+      t.part_l[g] = base + R * a.dv + R;
+      t.out[g] = fuse->out[g];
+      t.flags[g] = fuse->flags[g];
+    }
+    t.osb = fuse->o_stride_b; t.osn = fuse->o_stride_n; t.osh = fuse->o_stride_h;
+    t.row_begin = R * fuse->rank / fuse->num_peers;
+    t.row_end = R * (fuse->rank + 1) / fuse->num_peers;
+    // the local partial state IS this rank's symmetric buffer
+    p.fin_o = const_cast<float*>(t.part_o[fuse->rank]);
+    p.fin_m = const_cast<float*>(t.part_m[fuse->rank]);
+    p.fin_l = const_cast<float*>(t.part_l[fuse->rank]);
+  }
   char* ws = reinterpret_cast<char*>(a.workspace);
   const size_t nrows = (size_t)pl->num_slots * mode.slot_rows;
   const int slot_dv = mode.big ? 256 : DV;
   p.slot_o = reinterpret_cast<float*>(ws);
   p.slot_m = p.slot_o + nrows * slot_dv;
   p.slot_l = p.slot_m + nrows;
+  p.slot_flags = reinterpret_cast<unsigned long long*>(p.slot_l + nrows);  // 8-byte aligned: nrows is a multiple of 128
+  p.units = pl->d_units;
+  {
+    // unique per launch in this process; the upper bits keep it apart from anything a stale workspace may hold
+    static std::atomic<unsigned long long> launch_seq{0};
+    p.fixup_tag = 0x5043560000000000ull ^ (launch_seq.fetch_add(1, std::memory_order_relaxed) + 1);
+  }
   if (a.pad_mask != nullptr) {
     size_t off = (slots_bytes(*pl, slot_dv, mode.slot_rows) + 255) / 256 * 256;
     uint32_t* bits = reinterpret_cast<uint32_t*>(ws + off);

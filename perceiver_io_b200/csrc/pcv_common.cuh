@@ -75,7 +75,8 @@ int launch_attn_simt(const pcv_attn_params& p, cudaStream_t stream);
 int attn_simt_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
 
 bool attn_tc_supported(const pcv_attn_params& p, const char** why);
-int launch_attn_tc(const pcv_attn_params& p, cudaStream_t stream);
+int launch_attn_tc(const pcv_attn_params& p, cudaStream_t stream, const pcv_shard_fuse* fuse = nullptr);
+bool attn_tc_fuse_supported(const pcv_attn_params& p, const char** why);
 int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
 int debug_read(uint32_t* out, int n);
 int debug_plan(int B, int H, int N, int M, int workers, int rows_per_unit, int rows_per_tile, int32_t* segs,

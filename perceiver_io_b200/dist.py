@@ -103,16 +103,42 @@ class PeerMerger:
         self.pl = self.part[rows * dv + rows:].view(B, H, N)
         self.part_ptrs = [int(p) for p in self.part_hdl.buffer_ptrs]
         self.out_ptrs = [int(p) for p in self.out_hdl.buffer_ptrs]
+        # flag block of the fused kernel-tail merge (pcv_attn_fwd_sharded): epochs, never reset
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.flags_hdl = symm_mem.rendezvous(self.flags, group)
+        self.flag_ptrs = [int(p) for p in self.flags_hdl.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        self.flags_hdl.barrier(channel=2)  # every rank's flags are zero before anybody's first kernel can write them
+        self.epoch = 0
         # contiguous, equal row slices: rank r merges rows [r*R/G, (r+1)*R/G)
         self.row_begin = rows * self.rank // self.world
         self.row_end = rows * (self.rank + 1) // self.world
 
     @classmethod
-    def get(cls, B, H, N, dv, dtype, device, group):
-        key = (id(group), B, H, N, dv, dtype, str(device))
+    def get(cls, B, H, N, dv, dtype, device, group, tag=None):
+        """``tag`` separates states whose kernels run with different grids (the fused tail counts CTA arrivals)."""
+        key = (id(group), B, H, N, dv, dtype, str(device), tag)
         if key not in cls._cache:
             cls._cache[key] = cls(B, H, N, dv, dtype, device, group)
         return cls._cache[key]
+
+    def fused_attention(self, q, k_shard, v_shard, num_heads, scale, m_total, m_offset, pad_mask_shard=None,
+                        causal=False) -> torch.Tensor:
+        """ONE kernel launch on this rank: partial state of the local key shard, then — in the same kernel — publish
+        it, merge the rows this rank owns from all ranks over NVLink-mapped memory and push the normalised rows into
+        every rank's output buffer.  Returns this rank's (complete) output buffer, valid until the next call."""
+        from . import _lib, ops
+
+        self.epoch += 1
+        f = _lib.ShardFuse()
+        for g in range(self.world):
+            f.part[g], f.out[g], f.flags[g] = self.part_ptrs[g], self.out_ptrs[g], self.flag_ptrs[g]
+        f.o_stride_b, f.o_stride_n, f.o_stride_h = self.N * self.H * self.dv, self.H * self.dv, self.dv
+        f.num_peers, f.rank, f.epoch = self.world, self.rank, self.epoch
+        ops.attention_sharded_fused(q, k_shard, v_shard, num_heads, scale, f, pad_mask=pad_mask_shard, causal=causal,
+                                    m_total=m_total, m_offset=m_offset)
+        return self.out.view(self.B, self.N, self.H * self.dv)
 
     def merge(self) -> torch.Tensor:
         """Partials (written into self.po/pm/pl by the local kernel) -> full normalised output on every rank."""
@@ -167,14 +193,16 @@ def sharded_attention(q: torch.Tensor, k_shard: torch.Tensor, v_shard: torch.Ten
                       merge: str = "auto", copy_out: bool = True) -> torch.Tensor:
     """softmax(QK^T)V with K/V sharded along M over ``group``; every rank returns the full (B,N,H*dv).
 
-    ``merge``: "peer" (symmetric-memory kernel over NVLink), "nccl" (two all-reduces) or "auto" (peer when
-    available and no custom ``kernels`` are injected).  With the peer merge the result lives in a reused
-    symmetric buffer; ``copy_out=False`` returns that buffer itself (valid until the next call)."""
+    ``merge``: "fused" (ONE launch per rank: the merge runs in the attention kernel's tail over NVLink-mapped
+    symmetric memory, no host-launched barrier, no NCCL), "peer" (partial-state kernel, signal-pad barrier, separate
+    merge kernel, barrier), "nccl" (two all-reduces) or "auto" (fused when the kernel family covers the shapes and all
+    shards are equally long, else peer, else nccl).  With the fused / peer merge the result lives in a reused symmetric
+    buffer; ``copy_out=False`` returns that buffer itself (valid until the next call)."""
     world_now = dist.get_world_size(group) if dist.is_initialized() else 1
     merge_requested = merge
     if merge == "auto":
-        merge = "peer" if (kernels is None and not PeerMerger.disabled and _peer_merge_possible(k_shard, world_now)) else "nccl"
-    if merge == "peer" and world_now > 1:
+        merge = "fused" if (kernels is None and not PeerMerger.disabled and _peer_merge_possible(k_shard, world_now)) else "nccl"
+    if merge in ("peer", "fused") and world_now > 1:
         from . import ops
 
         H = num_heads
@@ -193,6 +221,20 @@ def sharded_attention(q: torch.Tensor, k_shard: torch.Tensor, v_shard: torch.Ten
         if pm is None:
             return sharded_attention(q, k_shard, v_shard, num_heads, scale, m_total, m_offset, pad_mask_shard, causal,
                                      group, kernels, merge="nccl")
+        if merge == "fused":
+            # every rank must take the same path: equal shard lengths (identical work plans, hence identical grids) and
+            # shapes the kernel family with the built-in tail covers; the decision depends on shapes only
+            M_local = k_shard.shape[1]
+            even = (m_total % world_now == 0) and (M_local * world_now == m_total)
+            ok = even and ops.attention_sharded_fused(q, k_shard, v_shard, H, scale, None, pad_mask=pad_mask_shard,
+                                                      causal=causal, m_total=m_total, m_offset=m_offset, check_only=True)
+            if ok:
+                pmf = PeerMerger.get(B, H, N, dv, cdt, k_shard.device, group, tag=("fused", M_local))
+                out = pmf.fused_attention(q, k_shard, v_shard, H, scale, m_total, m_offset, pad_mask_shard, causal)
+                out = out.clone() if copy_out else out
+                return out if out.dtype == q.dtype else out.to(q.dtype)
+            if merge_requested == "fused":
+                raise RuntimeError("fused merge requested but the shapes are not covered (uneven shards or big-head kernel)")
         ops.attention_partial(q, k_shard, v_shard, H, scale, pad_mask=pad_mask_shard, causal=causal,
                               m_total=m_total, m_offset=m_offset, out=(pm.po, pm.pm, pm.pl))
         out = pm.merge()

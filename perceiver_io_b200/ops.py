@@ -22,7 +22,7 @@ from ._lib import (AttnParams, CombineParams, KvAppendParams, KvProjParams, LnSt
                    PcvError, check)
 
 __all__ = [
-    "attention", "attention_partial", "combine_partials", "merge_partials", "rescale_partial_", "rotary", "kv_append",
+    "attention", "attention_partial", "attention_sharded_fused", "combine_partials", "merge_partials", "rescale_partial_", "rotary", "kv_append",
     "device_info", "tcgen05_supported", "ln_stats", "fold_ln_linear", "kv_project", "kv_project_supported",
 ]
 
@@ -247,6 +247,32 @@ def attention_partial(q, k, v, num_heads: int, scale: float, pad_mask=None, caus
         _run_attn(p, k.device)
     del keep
     return part_o, part_m, part_l
+
+
+def attention_sharded_fused(q, k, v, num_heads: int, scale: float, fuse, pad_mask=None, causal: bool = False,
+                            m_total: Optional[int] = None, m_offset: int = 0, check_only: bool = False):
+    """One launch: partial state of this rank's key shard + cross-GPU merge in the kernel tail (pcv_attn_fwd_sharded).
+
+    ``fuse`` is a filled ``_lib.ShardFuse`` (symmetric-memory pointers of every rank, this call's epoch).  With
+    ``check_only`` nothing is launched: returns whether the fused path covers these operands."""
+    q, k, v, _ = _prep(q, k, v)
+    with torch.cuda.device(k.device):
+        p, keep = _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, m_total, m_offset, "auto")
+        p.write_partial = 1
+        if check_only:
+            dummy = torch.empty(16, device=k.device)
+            p.part_o = p.part_m = p.part_l = dummy.data_ptr()
+            return bool(_lib.lib().pcv_attn_fwd_sharded_supported(C.byref(p)))
+        dummy_ptr = fuse.part[fuse.rank]
+        p.part_o = p.part_m = p.part_l = dummy_ptr
+        need = C.c_size_t(0)
+        check(_lib.lib().pcv_attn_workspace_bytes(C.byref(p), C.byref(need)), "pcv_attn_workspace_bytes")
+        ws = None
+        if need.value:
+            ws = torch.empty(need.value, dtype=torch.uint8, device=k.device)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), need.value
+        check(_lib.lib().pcv_attn_fwd_sharded(C.byref(p), C.byref(fuse), _stream()), "pcv_attn_fwd_sharded")
+    del keep
 
 
 def combine_partials(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.Tensor,
