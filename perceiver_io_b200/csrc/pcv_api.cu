@@ -56,13 +56,22 @@ static int validate_attn(const pcv_attn_params* p) {
   } else {
     PCV_REQUIRE(p->out != nullptr, PCV_ERR_INVALID, "attn: out pointer is NULL");
   }
-  PCV_REQUIRE(p->impl >= PCV_IMPL_AUTO && p->impl <= PCV_IMPL_TCGEN05_PAIR, PCV_ERR_INVALID, "attn: unknown impl %d", p->impl);
+  PCV_REQUIRE(p->impl >= PCV_IMPL_AUTO && p->impl <= PCV_IMPL_DECODE, PCV_ERR_INVALID, "attn: unknown impl %d", p->impl);
   return PCV_OK;
 }
 
+// few query rows against a long cache: the streaming kernel (HBM-bound) beats a 128-row tensor-core tile
+static bool use_decode(const pcv_attn_params& p, const char** why) {
+  if (p.impl != PCV_IMPL_AUTO && p.impl != PCV_IMPL_DECODE) {
+    *why = "another kernel was requested";
+    return false;
+  }
+  return attn_decode_supported(p, why);
+}
+
 static bool use_tc(const pcv_attn_params& p, const char** why) {
-  if (p.impl == PCV_IMPL_SIMT) {
-    *why = "simt requested";
+  if (p.impl == PCV_IMPL_SIMT || p.impl == PCV_IMPL_DECODE) {
+    *why = "another kernel was requested";
     return false;
   }
   return attn_tc_supported(p, why);
@@ -153,6 +162,8 @@ int pcv_attn_workspace_bytes(const pcv_attn_params* p, size_t* bytes) {
   if (rc != PCV_OK) return rc;
   PCV_REQUIRE(bytes != nullptr, PCV_ERR_INVALID, "attn: bytes is NULL");
   const char* why = "";
+  if (use_decode(*p, &why)) return attn_decode_workspace_bytes(*p, bytes);
+  PCV_REQUIRE(p->impl != PCV_IMPL_DECODE, PCV_ERR_UNSUPPORTED, "attn: decode kernel requested but %s", why);
   if (use_tc(*p, &why)) return attn_tc_workspace_bytes(*p, bytes);
   PCV_REQUIRE(p->impl != PCV_IMPL_TCGEN05 && p->impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
               "attn: tcgen05 kernel requested but %s", why);
@@ -163,6 +174,8 @@ int pcv_attn_fwd(const pcv_attn_params* p, void* stream) {
   int rc = validate_attn(p);
   if (rc != PCV_OK) return rc;
   const char* why = "";
+  if (use_decode(*p, &why)) return launch_attn_decode(*p, reinterpret_cast<cudaStream_t>(stream));
+  PCV_REQUIRE(p->impl != PCV_IMPL_DECODE, PCV_ERR_UNSUPPORTED, "attn: decode kernel requested but %s", why);
   if (use_tc(*p, &why)) return launch_attn_tc(*p, reinterpret_cast<cudaStream_t>(stream));
   PCV_REQUIRE(p->impl != PCV_IMPL_TCGEN05 && p->impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
               "attn: tcgen05 kernel requested but %s", why);

@@ -83,6 +83,10 @@ int debug_plan(int B, int H, int N, int M, int workers, int rows_per_unit, int r
                int max_segs, int32_t* counts);  // host-only dump of the tcgen05 work plan
 int debug_trace_read(unsigned long long* out, int n);  // PCV_TRACE=1 clock stamps (3 x 48 x 8)  // watchdog record of the tcgen05 kernel (16 words)
 
+bool attn_decode_supported(const pcv_attn_params& p, const char** why);
+int launch_attn_decode(const pcv_attn_params& p, cudaStream_t stream);
+int attn_decode_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
+
 int launch_combine(const pcv_combine_params& p, cudaStream_t stream);
 // Merge `nparts` partial states laid out [part][B][H][N]([dv]) either into p.out (normalised) or,
 // when p.write_partial is set, into p.part_o / p.part_m / p.part_l (still un-normalised).

@@ -307,3 +307,42 @@ def test_rotary_is_differentiable_and_matches_the_torch_rotation():
         ref = O.merge_heads(O.rotate(O.split_heads(xr, H), angles.double().cpu(), right))
         (gref,) = torch.autograd.grad((ref * wgt.double().cpu()).sum(), xr)
         assert_close(gx, gref, 1e-5, f"rotary grad right_align={right}")
+
+
+DECODE_SHAPES = [
+    # B, N, M, H, dqk, dv
+    (8, 1, 16384, 8, 128, 128),   # the Perceiver-AR decode step of BASELINE.json configs[3] (d = 1024)
+    (2, 1, 5000, 8, 96, 96),      # giantmidi head dim, ragged key count
+    (3, 2, 2049, 4, 64, 64),      # two query rows
+    (2, 4, 3000, 8, 32, 160),     # asymmetric head widths, four query rows
+    (1, 3, 2500, 1, 256, 256),    # widest rows the streaming kernel takes
+    (2, 1, 2048, 2, 8, 8),        # one 16-byte chunk per row
+]
+
+
+@pytest.mark.parametrize("shape", DECODE_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_decode_kernel_matches_oracle(shape, dtype):
+    """The streaming kernel for N <= 4 query rows (pcv_attn_decode.cu): padding + right-aligned causal masks, batch-1
+    queries broadcast, partial-state output, and `auto` must select it for these shapes."""
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, dqk, dv = shape
+    q, k, v = _qkv(B, N, M, H, dqk, dv, seed=31, q_gain=2.0, dtype=dtype)
+    pad = torch.zeros(B, M, dtype=torch.bool)
+    pad[0, : M // 9] = True
+    if B > 1:
+        pad[1, :] = True              # fully padded batch row: uniform average of all values
+    scale = dqk ** -0.5
+    for causal in (False, True):
+        out = ops.attention(q, k, v, H, scale, pad_mask=pad.cuda(), causal=causal, impl="decode")
+        assert_parity(out, q, k, v, H, scale, pad, causal, what=f"decode {shape} causal={causal}")
+        auto = ops.attention(q, k, v, H, scale, pad_mask=pad.cuda(), causal=causal)
+        assert torch.equal(auto, out), "auto did not select the decode kernel"
+    q1 = q[:1]
+    out = ops.attention(q1, k, v, H, scale, impl="decode")
+    assert_parity(out, q1, k, v, H, scale, what=f"decode {shape} broadcast q")
+    part = ops.attention_partial(q, k[:, : M // 2], v[:, : M // 2], H, scale, pad_mask=pad.cuda()[:, : M // 2], m_total=M, m_offset=0, impl="decode")
+    part2 = ops.attention_partial(q, k[:, M // 2:], v[:, M // 2:], H, scale, pad_mask=pad.cuda()[:, M // 2:], m_total=M, m_offset=M // 2)
+    merged = ops.combine_partials(torch.stack([part[0], part2[0]]), torch.stack([part[1], part2[1]]), torch.stack([part[2], part2[2]]), dtype)
+    assert_parity(merged, q, k, v, H, scale, pad, False, what=f"decode {shape} two key shards merged")
