@@ -240,8 +240,10 @@ typedef struct pcv_peer_combine_params {
  *     w      : (n_k + n_v, C)  = [gamma.Wk ; gamma.Wv] rounded to `dtype`, row-major (the nn.Linear layout)
  *     col_st : (n_k + n_v, 2) f32, per output column (s, t):  s = sum_c w[n, c] (of the ROUNDED w),
  *              t = sum_c beta_c W[n, c] + bias[n]
- * and, per call, the row statistics with pcv_ln_stats:  row_stats (rows, 2) f32 = (mean, 1/sqrt(var + eps)).
- * row_stats == NULL means "no LayerNorm": out = x w^T + t (a plain projection with bias).
+ * The row statistics (mean, 1/sqrt(var + eps)) come either from pcv_ln_stats (row_stats (rows, 2) f32: two-pass, one
+ * extra read of x) or — row_stats == NULL and ln_eps > 0 — from the GEMM kernel itself, which computes them in one
+ * pass (shifted by the row's first element) from the input tiles it stages anyway.
+ * row_stats == NULL and ln_eps == 0 means "no LayerNorm": out = x w^T + t (a plain projection with bias).
  *   x      : (rows, C) with an element row stride (rows = B*M flattened)
  *   k_out  : (rows, n_k), v_out : (rows, n_v), each with its own row stride — the un-rotated, pre-head-split
  *            K / V rows the reference would have produced (and caches, modules.py:117-121)
@@ -260,7 +262,8 @@ typedef struct pcv_kvproj_params {
   int32_t C, n_k, n_v;
   int32_t dtype;       /* PCV_BF16 / PCV_F16 */
   int32_t cta_group;   /* 0 = library default, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2) */
-  int32_t reserved;
+  float ln_eps;        /* row_stats == NULL: > 0 = LayerNorm with statistics computed INSIDE the GEMM kernel from the
+                          staged input tiles (no separate pass over x), 0 = no LayerNorm.  Ignored when row_stats is given */
 } pcv_kvproj_params;
 
 /* LayerNorm row statistics (nn.LayerNorm semantics: biased variance): stats[r] = (mean, 1/sqrt(var + eps)) */

@@ -153,7 +153,7 @@ class KvProjParams(C.Structure):
         ("x_stride_row", C.c_int64), ("k_stride_row", C.c_int64), ("v_stride_row", C.c_int64),
         ("rows", C.c_int64),
         ("C", C.c_int32), ("n_k", C.c_int32), ("n_v", C.c_int32),
-        ("dtype", C.c_int32), ("cta_group", C.c_int32), ("reserved", C.c_int32),
+        ("dtype", C.c_int32), ("cta_group", C.c_int32), ("ln_eps", C.c_float),
     ]
 
 

@@ -92,8 +92,10 @@ struct TcParams {
   const int* cta_seg_begin;
   int B, H, N, M, dv;
   int dv_off, dv_pass;              // this launch writes output channels [dv_off, dv_off + dv_pass)
-  int nc;                           // big-head kernel: number of 128-channel chunks of the qk head dim
-  int v_boxes;                      // big-head kernel: 64-channel boxes of V in this pass (PV MMA N = 64 * v_boxes)
+  int nc;                           // big-head kernel: number of 64-channel boxes of the qk head dim
+  int v_boxes;                      // big-head kernel: 64-channel boxes of V in this pass
+  int dqk_pad;                      // big-head kernel: qk head dim rounded up to 16 (K-steps of the ragged last box)
+  int dv_cols;                      // big-head kernel: accumulator columns of this pass (v channels rounded up to 16)
   float scale_log2;
   int causal, causal_shift;  // key j (local) masked for query n iff j > n + causal_shift
   const uint32_t* pad_bits;  // (B, pad_wpr) bit set = padding key; nullptr if no mask
@@ -1038,22 +1040,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
 
 // --------------------------------------------------------------------------------------------------
-// Big-head kernel: qk head dims up to 512 and v head dims up to 256 per pass (the optical-flow encoder /
-// decoder geometry, 322 and 512 channels per head).  One query tile (128 rows) per CTA.  Q and K stream through
-// shared memory in 128-channel chunks (Q is re-streamed from L2 for every key tile) and S accumulates over the
-// chunks in TMEM; S is double-buffered (columns [0,128) / [128,256)) so Q K^T of tile j+1 overlaps the softmax
-// of tile j; O occupies columns [256, 256 + 64*v_boxes).  A v head dim above 256 is covered by launching the
-// kernel once per 256-channel slice of V (the scores are recomputed).  256 threads: warps 0-3 softmax (one
-// thread per row), warp 4 MMA issuer, warp 5 TMA producer.
+// Big-head kernel: qk head dims up to 512 and up to 384 v channels per pass (the optical-flow encoder / decoder
+// geometry: 322 and 512 channels per head, reference vision/optical_flow/backend.py:22-27,104-109).  One query tile
+// (128 rows) per CTA, 256 threads: warps 0-3 softmax (one thread per row), warp 4 MMA issuer, warp 5 TMA producer.
+//   * Q (128 rows x dqk) is RESIDENT in shared memory for the whole segment: ceil(dqk/64) boxes of 16 KB
+//     (the previous version re-streamed Q from L2 for every key tile).
+//   * K and V stream through ONE ring of 16 KB boxes (128 keys x 64 channels), 14 - #Q boxes slots: per key tile
+//     first the K boxes (K-major B operand of S += Q_box K_box^T, 4 MMAs of K = 16 per box, fewer for the ragged
+//     last box: dqk = 322 costs 21 K-steps, not 24), then the V boxes (MN-major B operand, N = 64 or the ragged
+//     tail, of O[:, box] += P V_box with P read from TMEM).
+//   * TMEM: S in columns [0, 128) (P aliases [0, 64) as in the main kernel), O in [128, 128 + 384): every v channel of
+//     dv <= 384 is produced in ONE pass (the previous version recomputed Q K^T for every 256-channel slice of V).
+//   * S is single-buffered, so per key tile the tensor pipe runs Q K^T, idles while the softmax warps turn S into P
+//     (one query tile per CTA: 1024 MUFU cycles) and runs P V; the in-order pipe makes "S(j) complete" imply
+//     "P V(j-1) complete", which is what the accumulator rescale and the S / P aliasing need.
 // --------------------------------------------------------------------------------------------------
 constexpr int kBigThreads = 256;
-constexpr int kBigItems = 3;
-constexpr int kBigItemBytes = 4 * kBoxBytes;  // 64 KB: [Q chunk 32 KB | K chunk 32 KB] or a V tile of <= 256 channels
-constexpr int kBigSmemBytes = kBigItems * kBigItemBytes + 1024 + 1024;
+constexpr int kBigSlots = 14;            // 16 KB boxes: Q boxes first, the rest is the K/V ring
+constexpr int kBigDv = 384;              // accumulator columns (one pass)
+constexpr int kBigSmemBytes = kBigSlots * kBoxBytes + 1024 + 1024;
 
 struct BigBarriers {
-  uint64_t item_full[kBigItems], item_empty[kBigItems];
-  uint64_t s_full[2], pv_done, o_full, o_empty;  // s_full per S buffer: a barrier must never run a full phase ahead of its waiter
+  uint64_t box_full[kBigSlots], box_empty[kBigSlots];
+  uint64_t q_full, q_empty, s_full, o_full, o_empty;
   uint32_t tmem_base;
 };
 
@@ -1063,26 +1072,29 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                    const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  BigBarriers& bb = *reinterpret_cast<BigBarriers*>(smem + kBigItems * kBigItemBytes);
-  // the shared softmax helpers address barriers through the common struct; alias the fields they touch
-  Barriers& bar = *reinterpret_cast<Barriers*>(smem + kBigItems * kBigItemBytes + 512);
+  BigBarriers& bb = *reinterpret_cast<BigBarriers*>(smem + kBigSlots * kBoxBytes);
+  // the shared softmax helpers address p_full through the common struct; alias the fields they touch
+  Barriers& bar = *reinterpret_cast<Barriers*>(smem + kBigSlots * kBoxBytes + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int seg_lo = p.cta_seg_begin[blockIdx.x];
   const int seg_hi = p.cta_seg_begin[blockIdx.x + 1];
   constexpr int kMma = 4, kTma = 5;
+  const int nqb = p.nc;                   // Q / K boxes (64 channels each)
+  const int nvb = p.v_boxes;              // V boxes of this pass
+  const int ring = kBigSlots - nqb;       // ring slots
+  uint8_t* ring_base = smem + nqb * kBoxBytes;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kBigItems; ++i) {
-      mbar_init(&bb.item_full[i], 1);
-      mbar_init(&bb.item_empty[i], 1);
+    for (int i = 0; i < kBigSlots; ++i) {
+      mbar_init(&bb.box_full[i], 1);
+      mbar_init(&bb.box_empty[i], 1);
     }
-    mbar_init(&bb.s_full[0], 1);
-    mbar_init(&bb.s_full[1], 1);
-    mbar_init(&bar.p_full[0], 4);  // arrive_p_full() targets bar.p_full[c.wg]; c.wg = S buffer index here
-    mbar_init(&bar.p_full[1], 4);
-    mbar_init(&bb.pv_done, 1);
+    mbar_init(&bb.q_full, 1);
+    mbar_init(&bb.q_empty, 1);
+    mbar_init(&bb.s_full, 1);
+    mbar_init(&bar.p_full[0], 4);  // arrive_p_full() targets bar.p_full[c.wg], c.wg = 0 here
     mbar_init(&bb.o_full, 1);
     mbar_init(&bb.o_empty, 4);
     fence_mbar_init();
@@ -1105,8 +1117,8 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // ===== softmax + epilogue: thread = query row =====
     const int row = threadIdx.x;
     const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
-    const uint32_t tO = tmem + lane_field + 256u;
-    uint32_t n_tile = 0, n_o = 0;  // n_tile: key tiles processed by this CTA so far (all segments)
+    const uint32_t tO = tmem + lane_field + 128u;
+    uint32_t n_tile = 0, n_o = 0;  // key tiles / segments processed by this CTA so far
     for (int sg = seg_lo; sg < seg_hi; ++sg) {
       const Segment seg = p.segs[sg];
       const int n = seg.q0 + row;
@@ -1114,143 +1126,131 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       st.m_ref = -INFINITY;
       st.l = 0.f;
       TileCtx c;
-      c.tO = tO; c.row = row;
-      c.pv_bar = &bb.pv_done;
+      c.tS = tmem + lane_field;
+      c.tO = tO;
+      c.row = row;
+      c.wg = 0;
+      c.pv_bar = nullptr;  // S(j) complete implies P V(j-1) complete (single S buffer, in-order tensor pipe)
+      c.pv_parity = 0;
       c.cshift = n + p.causal_shift;
       c.trace_on = false;
       c.scale_log2 = p.scale_log2;
       for (int t = seg.t0; t < seg.t1; ++t) {
-        const int j = t - seg.t0;
-        const uint32_t buf = n_tile & 1;  // S buffer (and its barriers) alternate over ALL tiles of the CTA
-        c.wg = (int)buf;
-        c.tS = tmem + lane_field + buf * 128u;
         c.j0 = t * kTileN;
-        c.tt = j;
-        c.first_tile = (j == 0);
-        c.pv_parity = (n_tile + 1) & 1;  // phase of the previous tile's PV on pv_done
+        c.tt = t - seg.t0;
+        c.first_tile = (t == seg.t0);
         c.mw = make_uint4(0, 0, 0, 0);
         if (p.pad_bits != nullptr)
           c.mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
         const bool masked_tile =
             __any_sync(0xffffffffu, (c.j0 + kTileN > p.M) || ((c.mw.x | c.mw.y | c.mw.z | c.mw.w) != 0u) ||
                                         (p.causal && (c.j0 + kTileN - 1 > c.cshift)));
-        mbar_wait(&bb.s_full[buf], (n_tile >> 1) & 1, 12);
+        mbar_wait(&bb.s_full, n_tile & 1, 12);
         tc_fence_after_sync();
         if (masked_tile) {
-          softmax_tile<256, BF16, true>(p, bar, c, st);
+          softmax_tile<kBigDv, BF16, true>(p, bar, c, st);
         } else if (p.optimistic && !c.first_tile) {
-          if (!softmax_tile_optimistic<256, BF16, 0>(p, bar, c, st)) softmax_tile<256, BF16, false>(p, bar, c, st);
+          if (!softmax_tile_optimistic<kBigDv, BF16, 0>(p, bar, c, st)) softmax_tile<kBigDv, BF16, false>(p, bar, c, st);
         } else {
-          softmax_tile<256, BF16, false>(p, bar, c, st);
+          softmax_tile<kBigDv, BF16, false>(p, bar, c, st);
         }
         ++n_tile;
       }
       mbar_wait(&bb.o_full, n_o & 1, 13);
       ++n_o;
       tc_fence_after_sync();
-      epilogue_row<256, BF16, false>(p, seg, tO, n, row, st.l, st.m_ref);
+      epilogue_row<kBigDv, BF16, false>(p, seg, tO, n, row, st.l, st.m_ref);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bb.o_empty);
     }
   } else if (warp == kTma) {
-    // ===== TMA producer; item order = consumption order: QK(0), QK(1), V(0), QK(2), V(1), ... =====
+    // ===== TMA producer: Q boxes once per segment; per key tile the K boxes, then the V boxes, through the ring =====
     const bool leader = elect_one();
-    uint32_t it = 0;
-    auto load_qk = [&](const Segment& seg, int t) {
-      const int bq = p.q_bcast ? 0 : seg.b;
-      for (int ch = 0; ch < p.nc; ++ch) {
-        const uint32_t slot = it % kBigItems, par = (it / kBigItems) & 1;
-        mbar_wait(&bb.item_empty[slot], par ^ 1, 2);
-        if (leader) {
-          uint8_t* base = smem + slot * kBigItemBytes;
-          mbar_arrive_expect_tx(&bb.item_full[slot], (uint32_t)kBigItemBytes);
-          tma_load_4d(base, &tmap_q, &bb.item_full[slot], ch * 128, seg.q0, seg.h, bq);
-          tma_load_4d(base + kBoxBytes, &tmap_q, &bb.item_full[slot], ch * 128 + 64, seg.q0, seg.h, bq);
-          tma_load_4d(base + 2 * kBoxBytes, &tmap_k, &bb.item_full[slot], ch * 128, t * kTileN, seg.h, seg.b);
-          tma_load_4d(base + 3 * kBoxBytes, &tmap_k, &bb.item_full[slot], ch * 128 + 64, t * kTileN, seg.h, seg.b);
-        }
-        ++it;
-      }
-    };
-    auto load_v = [&](const Segment& seg, int t) {
-      const uint32_t slot = it % kBigItems, par = (it / kBigItems) & 1;
-      mbar_wait(&bb.item_empty[slot], par ^ 1, 3);
-      if (leader) {
-        uint8_t* base = smem + slot * kBigItemBytes;
-        mbar_arrive_expect_tx(&bb.item_full[slot], (uint32_t)(p.v_boxes * kBoxBytes));
-        for (int bx = 0; bx < p.v_boxes; ++bx)
-          tma_load_4d(base + bx * kBoxBytes, &tmap_v, &bb.item_full[slot], bx * 64, t * kTileN, seg.h, seg.b);
-      }
-      ++it;
-    };
+    uint32_t it = 0, n_q = 0;
     for (int sg = seg_lo; sg < seg_hi; ++sg) {
       const Segment seg = p.segs[sg];
-      load_qk(seg, seg.t0);
+      const int bq = p.q_bcast ? 0 : seg.b;
+      mbar_wait(&bb.q_empty, (n_q & 1) ^ 1, 1);
+      ++n_q;
+      if (leader) {
+        mbar_arrive_expect_tx(&bb.q_full, (uint32_t)(nqb * kBoxBytes));
+        for (int bx = 0; bx < nqb; ++bx)
+          tma_load_4d(smem + bx * kBoxBytes, &tmap_q, &bb.q_full, bx * 64, seg.q0, seg.h, bq);
+      }
       for (int t = seg.t0; t < seg.t1; ++t) {
-        if (t + 1 < seg.t1) load_qk(seg, t + 1);
-        load_v(seg, t);
+        for (int bx = 0; bx < nqb + nvb; ++bx, ++it) {
+          const uint32_t slot = it % ring, par = (it / ring) & 1;
+          mbar_wait(&bb.box_empty[slot], par ^ 1, 2);
+          if (leader) {
+            mbar_arrive_expect_tx(&bb.box_full[slot], (uint32_t)kBoxBytes);
+            if (bx < nqb)
+              tma_load_4d(ring_base + slot * kBoxBytes, &tmap_k, &bb.box_full[slot], bx * 64, t * kTileN, seg.h, seg.b);
+            else
+              tma_load_4d(ring_base + slot * kBoxBytes, &tmap_v, &bb.box_full[slot], (bx - nqb) * 64, t * kTileN, seg.h,
+                          seg.b);
+          }
+        }
       }
     }
   } else if (warp == kMma) {
     // ===== MMA issuer =====
     const bool leader = elect_one();
     constexpr uint32_t idesc_qk = make_idesc(kTileM, kTileN, BF16, false);
-    const uint32_t idesc_pv = make_idesc(kTileM, 64 * p.v_boxes, BF16, true);
-    const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);          // K-major operands (Q / K chunks)
-    const uint64_t dv0 = make_smem_desc(smem_u32(smem), kBoxBytes, 1024);  // MN-major V tile
-    uint32_t it = 0, n_qk = 0, n_pvi = 0, n_oe = 0;  // n_qk / n_pvi: tiles whose QK^T / PV have been issued (all segments)
+    const uint64_t dq0 = make_smem_desc(smem_u32(smem), 16, 1024);               // K-major Q boxes
+    const uint64_t dk0 = make_smem_desc(smem_u32(ring_base), 16, 1024);          // K-major K boxes
+    const uint64_t dv0 = make_smem_desc(smem_u32(ring_base), kBoxBytes, 1024);   // MN-major V boxes
+    uint32_t it = 0, n_q = 0, n_p = 0, n_oe = 0;
     auto commit = [&](uint64_t* b) {
       if (leader) tc_commit(b);
-    };
-    auto issue_qk = [&]() {  // S[n_qk & 1] = Q K^T of the next tile, accumulated over the channel chunks
-      const uint32_t buf = n_qk & 1;
-      for (int ch = 0; ch < p.nc; ++ch) {
-        const uint32_t slot = it % kBigItems;
-        mbar_wait(&bb.item_full[slot], (it / kBigItems) & 1, 5);
-        ++it;
-        tc_fence_after_sync();
-        if (leader) {
-          const uint64_t da = d0 + (uint64_t)((slot * kBigItemBytes) >> 4);
-          const uint64_t db = da + (uint64_t)((2 * kBoxBytes) >> 4);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-            mma_ss(tmem + buf * 128, da + off, db + off, idesc_qk, (ch > 0 || kk > 0) ? 1u : 0u);
-          }
-        }
-        commit(&bb.item_empty[slot]);
-      }
-      commit(&bb.s_full[buf]);
-      ++n_qk;
     };
     for (int sg = seg_lo; sg < seg_hi; ++sg) {
       const Segment seg = p.segs[sg];
       const int nt = seg.t1 - seg.t0;
-      issue_qk();
+      mbar_wait(&bb.q_full, n_q & 1, 4);
+      ++n_q;
       for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) issue_qk();
-        const uint32_t buf = n_pvi & 1;
-        const uint32_t slot = it % kBigItems;
-        mbar_wait(&bb.item_full[slot], (it / kBigItems) & 1, 6);
-        ++it;
+        // S = Q K^T over the channel boxes
+        for (int bx = 0; bx < nqb; ++bx, ++it) {
+          const uint32_t slot = it % ring;
+          mbar_wait(&bb.box_full[slot], (it / ring) & 1, 5);
+          tc_fence_after_sync();
+          if (leader) {
+            const int ksteps = min(4, (p.dqk_pad - bx * 64 + 15) / 16);
+            const uint64_t da = dq0 + (uint64_t)((bx * kBoxBytes) >> 4);
+            const uint64_t db = dk0 + (uint64_t)((slot * kBoxBytes) >> 4);
+            for (int kk = 0; kk < ksteps; ++kk)
+              mma_ss(tmem, da + (uint64_t)((kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), idesc_qk,
+                     (bx > 0 || kk > 0) ? 1u : 0u);
+          }
+          commit(&bb.box_empty[slot]);
+        }
+        commit(&bb.s_full);
         if (j == 0) {
           mbar_wait(&bb.o_empty, (n_oe & 1) ^ 1, 7);
           ++n_oe;
         }
-        mbar_wait(&bar.p_full[buf], (n_pvi >> 1) & 1, 8);
+        mbar_wait(&bar.p_full[0], n_p & 1, 8);
+        ++n_p;
         tc_fence_after_sync();
-        if (leader) {
-          const uint64_t db = dv0 + (uint64_t)((slot * kBigItemBytes) >> 4);
+        // O[:, box] += P V_box
+        for (int bx = 0; bx < nvb; ++bx, ++it) {
+          const uint32_t slot = it % ring;
+          mbar_wait(&bb.box_full[slot], (it / ring) & 1, 6);
+          tc_fence_after_sync();
+          if (leader) {
+            const int ncols = min(64, p.dv_cols - bx * 64);
+            const uint32_t idesc_pv = make_idesc(kTileM, ncols, BF16, true);
+            const uint64_t db = dv0 + (uint64_t)((slot * kBoxBytes) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < kTileN / 16; ++kk)
-            mma_ts(tmem + 256, tmem + buf * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
-                   (j > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < kTileN / 16; ++kk)
+              mma_ts(tmem + 128 + bx * 64, tmem + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+                     (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          commit(&bb.box_empty[slot]);
         }
-        commit(&bb.item_empty[slot]);
-        commit(&bb.pv_done);
-        ++n_pvi;
       }
+      commit(&bb.q_empty);
       commit(&bb.o_full);
     }
   }
@@ -1622,7 +1622,7 @@ int launch_big(const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk, con
   count_launch();
   if (pl.num_units > 0) {
     dim3 grid(pl.num_units, p.slot_rows / 8);
-    tc_combine_kernel<256, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
+    tc_combine_kernel<kBigDv, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
     PCV_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -1698,7 +1698,7 @@ int attn_tc_workspace_bytes(const pcv_attn_params& p, size_t* bytes) {
   const Mode mode = choose_mode(p);
   int rc = get_plan(p.B, p.H, p.N, p.M, mode, &pl);
   if (rc != PCV_OK) return rc;
-  size_t b = slots_bytes(*pl, mode.big ? 256 : pad64(p.dv), mode.slot_rows);
+  size_t b = slots_bytes(*pl, mode.big ? kBigDv : pad64(p.dv), mode.slot_rows);
   b = (b + 255) / 256 * 256;
   if (p.pad_mask != nullptr) b += sizeof(uint32_t) * (size_t)p.B * ((p.M + kTileN - 1) / kTileN * 4);
   *bytes = b;
@@ -1790,7 +1790,7 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream, const pcv_shar
   }
   char* ws = reinterpret_cast<char*>(a.workspace);
   const size_t nrows = (size_t)pl->num_slots * mode.slot_rows;
-  const int slot_dv = mode.big ? 256 : DV;
+  const int slot_dv = mode.big ? kBigDv : DV;
   p.slot_o = reinterpret_cast<float*>(ws);
   p.slot_m = p.slot_o + nrows * slot_dv;
   p.slot_l = p.slot_m + nrows;
@@ -1824,12 +1824,14 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream, const pcv_shar
 
   const bool bf = a.dtype == PCV_BF16;
   if (mode.big) {
-    // one launch per 256-channel slice of V (the scores are recomputed for every slice)
-    p.nc = (a.dqk + 127) / 128;
-    for (int off = 0; off < a.dv; off += 256) {
+    // one launch per 384-channel slice of V (the scores are recomputed per slice; dv <= 384 is a single pass)
+    p.nc = (a.dqk + 63) / 64;
+    p.dqk_pad = (a.dqk + 15) / 16 * 16;
+    for (int off = 0; off < a.dv; off += kBigDv) {
       p.dv_off = off;
-      p.dv_pass = std::min(256, a.dv - off);
+      p.dv_pass = std::min(kBigDv, a.dv - off);
       p.v_boxes = (p.dv_pass + 63) / 64;
+      p.dv_cols = (p.dv_pass + 15) / 16 * 16;
       const char* vbase = reinterpret_cast<const char*>(a.v) + 2 * (size_t)off;
       rc = make_tmap(&tv, vbase, a.dtype, p.dv_pass, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
       if (rc != PCV_OK) return rc;

@@ -40,9 +40,11 @@ using namespace sm100;
 constexpr int kBM = 128;   // accumulator rows per CTA (TMEM lanes)
 constexpr int kBN = 256;   // output columns per tile (UMMA N)
 constexpr int kBK = 64;    // channels per pipeline stage (one 128-byte swizzle atom of 16-bit elements)
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;        // TMA warp, MMA warp, 4 epilogue warps
+constexpr int kGemmThreadsFused = 320;   // + 4 statistics warps (LayerNorm row statistics computed from the staged A tiles)
 constexpr int kEpiWarp0 = 2;
 constexpr int kEpiThreads = 128;
+constexpr int kStatWarp0 = 6;
 constexpr int kStoreBoxCols = 64;
 constexpr int kStoreBoxBytes = kBM * kStoreBoxCols * 2;  // 16 KB
 
@@ -54,13 +56,16 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = CG == 1 ? 4 : 6;
   static constexpr int kRingBytes = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kRingBytes + 2 * kStoreBoxBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kTailBytes = 2048;  // barriers (512 B) + row statistics of the current row block (128 x float2)
+  static constexpr int kSmemBytes = kRingBytes + 2 * kStoreBoxBytes + kTailBytes + 1024 /*alignment slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 struct GemmBarriers {
   uint64_t full[8], empty[8];
   uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t stats_full, stats_empty;
+  uint64_t landed[8];  // pair mode: "stage s holds valid data" for the statistics warps of BOTH CTAs (see the MMA issuer)
   uint32_t tmem_base;
 };
 
@@ -72,7 +77,30 @@ struct GemmParams {
   int num_kb;            // ceil(C / 64)
   int tiles_n;           // ceil(n_total / 256)
   int64_t num_tiles;     // row blocks (of 128*CG rows) x tiles_n
+  int64_t m_blocks;      // row blocks
+  int C;                 // input channels
+  float eps;             // LayerNorm epsilon of the in-kernel statistics
 };
+
+// Tile order.  Separate statistics pass (FUSE = false): column tile fastest over the whole grid, so the 8 column
+// tiles of a row block run concurrently on 8 workers and meet in L2.  In-kernel statistics (FUSE = true): a worker
+// takes whole row blocks and walks their column tiles itself — the statistics are computed once, during the first
+// column tile, from the A tiles that are staged in shared memory anyway, and reused for the other tiles; the worker
+// re-reads its own A tile from L2 (148 x 256 KB live in L2), x still crosses HBM once and NOT a second time for a
+// statistics kernel.
+template <bool FUSE>
+__device__ __forceinline__ bool tile_of(const GemmParams& p, int64_t worker, int64_t workers, int64_t i, int64_t* m_blk,
+                                        int* n_blk) {
+  if (FUSE) {
+    *m_blk = worker + (i / p.tiles_n) * workers;
+    *n_blk = (int)(i % p.tiles_n);
+    return *m_blk < p.m_blocks;
+  }
+  const int64_t t = worker + i * workers;
+  *m_blk = t / p.tiles_n;
+  *n_blk = (int)(t % p.tiles_n);
+  return t < p.num_tiles;
+}
 
 __device__ __forceinline__ uint32_t pack_pair(float lo, float hi, bool bf16) {
   uint32_t r;
@@ -83,8 +111,8 @@ __device__ __forceinline__ uint32_t pack_pair(float lo, float hi, bool bf16) {
   return r;
 }
 
-template <bool BF16, int CG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <bool BF16, int CG, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? kGemmThreadsFused : kGemmThreads, 1)
 kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
               const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
               const GemmParams p) {
@@ -94,6 +122,7 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   uint8_t* ring = smem;
   uint8_t* staging = smem + C::kRingBytes;
   GemmBarriers& bar = *reinterpret_cast<GemmBarriers*>(smem + C::kRingBytes + 2 * kStoreBoxBytes);
+  float2* row_stats = reinterpret_cast<float2*>(smem + C::kRingBytes + 2 * kStoreBoxBytes + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,8 +138,12 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
       // mbarrier.arrive.release.cluster per stage compiles to MEMBAR + ERRBAR, which made the peer's producer wait for
       // its own outstanding TMA loads before issuing the next one (measured: 2.6x slower, profiles/r02_kvproj_pair_membar.md).
       mbar_init(&bar.full[i], 1);
-      mbar_init(&bar.empty[i], 1);   // tcgen05.commit (multicast to both CTAs of a pair)
+      // tcgen05.commit (multicast to both CTAs of a pair) + one arrive per statistics warp of this CTA
+      mbar_init(&bar.empty[i], FUSE ? 5 : 1);
     }
+    mbar_init(&bar.stats_full, 4);
+    mbar_init(&bar.stats_empty, 4);
+    for (int i = 0; i < C::kStages; ++i) mbar_init(&bar.landed[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar.tmem_full[i], 1);
       mbar_init(&bar.tmem_empty[i], 4 * CG);  // one arrive per epilogue warp (of both CTAs)
@@ -143,9 +176,9 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     // ===== TMA producer (every CTA: its 128 rows of x, its share of the W' rows) =====
     const bool leader_lane = elect_one();
     uint32_t it = 0;
-    for (int64_t t = worker; t < p.num_tiles; t += workers) {
-      const int64_t m_blk = t / p.tiles_n;
-      const int n_blk = (int)(t % p.tiles_n);
+    int64_t m_blk;
+    int n_blk;
+    for (int64_t ti = 0; tile_of<FUSE>(p, worker, workers, ti, &m_blk, &n_blk); ++ti) {
       const int row0 = (int)(m_blk * (kBM * CG) + rank * kBM);
       const int wrow0 = n_blk * kBN + (int)rank * C::kBRows;
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
@@ -174,7 +207,9 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     const uint64_t da0 = make_smem_desc(smem_u32(ring), 16, 1024);
     const uint64_t db0 = make_smem_desc(smem_u32(ring + C::kABytes), 16, 1024);
     uint32_t it = 0, tc = 0;
-    for (int64_t t = worker; t < p.num_tiles; t += workers, ++tc) {
+    int64_t m_blk;
+    int n_blk;
+    for (int64_t ti = 0; tile_of<FUSE>(p, worker, workers, ti, &m_blk, &n_blk); ++ti, ++tc) {
       const uint32_t acc = tc & 1;
       mbar_wait(&bar.tmem_empty[acc], ((tc >> 1) & 1) ^ 1, 21);
       tc_fence_after_sync();
@@ -192,10 +227,16 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             else
               mma_ss_pair(tmem + acc * kBN, da0 + off, db0 + off, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
           }
-          if (CG == 1)
+          if (CG == 1) {
             tc_commit(&bar.empty[s]);
-          else
+          } else {
             tc_commit_pair(&bar.empty[s], 3);
+            // TMA bytes of a pair are signalled on the LEADER's full barrier only, so the peer's statistics warps cannot
+            // wait for it; a second multicast commit tells both CTAs "the MMAs of stage s are done" — which implies
+            // that its data had landed — while the stage cannot be recycled before the statistics warps have arrived
+            // on their CTA's empty barrier
+            if (FUSE) tc_commit_pair(&bar.landed[s], 3);
+          }
         }
       }
       if (leader_lane) {
@@ -205,7 +246,7 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
           tc_commit_pair(&bar.tmem_full[acc], 3);
       }
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
     // ===== epilogue: thread = accumulator row (TMEM lane 32*(warp%4) + lane) =====
     const int quarter = warp & 3;
     const int r_in_tile = quarter * 32 + lane;
@@ -214,14 +255,25 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     const bool store_thread = (threadIdx.x == kEpiWarp0 * 32);
     const uint32_t tmem_empty_addr =
         CG == 2 ? mapa_cluster(smem_u32(&bar.tmem_empty[0]), 0) : smem_u32(&bar.tmem_empty[0]);
-    uint32_t tc = 0, g = 0;  // tiles / store boxes processed by this CTA
-    for (int64_t t = worker; t < p.num_tiles; t += workers, ++tc) {
-      const int64_t m_blk = t / p.tiles_n;
-      const int n_blk = (int)(t % p.tiles_n);
+    uint32_t tc = 0, g = 0, mb = 0;  // tiles / store boxes / row blocks processed by this CTA
+    int64_t m_blk;
+    int n_blk;
+    float a = 1.f, bb = 0.f;
+    for (int64_t ti = 0; tile_of<FUSE>(p, worker, workers, ti, &m_blk, &n_blk); ++ti, ++tc) {
       const int64_t row0 = m_blk * (kBM * CG) + rank * kBM;
       const int64_t row = row0 + r_in_tile;
-      float a = 1.f, bb = 0.f;
-      if (p.stats != nullptr) {
+      if (FUSE) {
+        if (n_blk == 0) {
+          // the statistics warps publish (mean, rstd) of this row block once its first column tile has been staged
+          mbar_wait(&bar.stats_full, mb & 1, 24);
+          ++mb;
+          const float2 ms = row_stats[r_in_tile];
+          a = ms.y;
+          bb = -ms.y * ms.x;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar.stats_empty);
+        }
+      } else if (p.stats != nullptr) {
         float2 ms = make_float2(0.f, 0.f);
         if (row < p.rows) ms = __ldg(p.stats + row);
         a = ms.y;
@@ -281,6 +333,66 @@ kvproj_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
       }
     }
     if (store_thread) bulk_wait_group<0>();
+  } else if (FUSE && warp >= kStatWarp0) {
+    // ===== LayerNorm row statistics from the staged A tiles (thread = row of this CTA's 128-row tile) =====
+    // One pass, shifted by the row's first element (pivot): mean = p + S1/C, var = S2/C - (S1/C)^2 with S1 = sum(x-p),
+    // S2 = sum((x-p)^2) — |mean - p| is of the order of sigma, so the subtraction does not cancel however large
+    // |mean| / sigma is.  A row's 128 bytes of a stage are read as 8 x 16 bytes in swizzled order (chunk j of row r
+    // lives at chunk j ^ (r & 7)): conflict-free, and a sum does not care about the order.
+    const int r = (warp - kStatWarp0) * 32 + lane;
+    uint32_t it = 0, mb = 0;
+    int64_t m_blk;
+    int n_blk;
+    for (int64_t ti = 0; tile_of<FUSE>(p, worker, workers, ti, &m_blk, &n_blk); ++ti) {
+      float pivot = 0.f, s1 = 0.f, s2 = 0.f;
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const uint32_t s = it % C::kStages, par = (it / C::kStages) & 1;
+        if (CG == 1)
+          mbar_wait(&bar.full[s], par, 25);
+        else
+          mbar_wait(&bar.landed[s], par, 25);
+        if (n_blk == 0) {
+          const uint8_t* rowp = ring + s * C::kStageBytes + r * 128;
+          const int chunks = min(8, (p.C - kb * kBK) / 8);  // ragged last stage: TMA zero fill is not data
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < chunks) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((j ^ (r & 7)) << 4));
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float lo, hi;
+                if (BF16) {
+                  lo = __uint_as_float(w[q] << 16);
+                  hi = __uint_as_float(w[q] & 0xffff0000u);
+                } else {
+                  const __half2 h2 = *reinterpret_cast<const __half2*>(&w[q]);
+                  lo = __low2float(h2);
+                  hi = __high2float(h2);
+                }
+                if (kb == 0 && j == 0 && q == 0) pivot = lo;
+                const float d0 = lo - pivot, d1 = hi - pivot;
+                s1 += d0 + d1;
+                s2 = fmaf(d0, d0, s2);
+                s2 = fmaf(d1, d1, s2);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar.empty[s]);  // release: the shared-memory reads above are done
+      }
+      if (n_blk == 0) {
+        mbar_wait(&bar.stats_empty, (mb & 1) ^ 1, 26);  // the epilogue has taken the previous row block's statistics
+        ++mb;
+        const float inv_c = 1.f / (float)p.C;
+        const float d = s1 * inv_c;
+        const float var = fmaxf(fmaf(-d, d, s2 * inv_c), 0.f);
+        row_stats[r] = make_float2(pivot + d, 1.f / sqrtf(var + p.eps));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar.stats_full);
+      }
+    }
   }
 
   tc_fence_before_sync();
@@ -453,11 +565,11 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, int64_t inner, in
   return PCV_OK;
 }
 
-template <bool BF16, int CG>
+template <bool BF16, int CG, bool FUSE>
 int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tk, const CUtensorMap& tv,
                 const GemmParams& gp, int sms, cudaStream_t stream) {
   using C = GemmCfg<CG>;
-  auto kern = kvproj_kernel<BF16, CG>;
+  auto kern = kvproj_kernel<BF16, CG, FUSE>;
   static std::mutex mu;
   static bool attr_set[64] = {};
   int dev = 0;
@@ -470,7 +582,7 @@ int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap&
     }
   }
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(FUSE ? kGemmThreadsFused : kGemmThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -497,7 +609,7 @@ int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap&
     }
     if (getenv("PCV_KVPROJ_VERBOSE")) fprintf(stderr, "[pcv] kvproj: %lld co-resident CTA pairs on %d SMs\n", (long long)max_workers, sms);
   }
-  const int workers = (int)std::min<int64_t>(max_workers, gp.num_tiles);
+  const int workers = (int)std::min<int64_t>(max_workers, FUSE ? gp.m_blocks : gp.num_tiles);
   cfg.gridDim = dim3((unsigned)(workers * CG));
   prof_mark_begin(stream);
   PCV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tk, tv, gp));
@@ -560,7 +672,11 @@ int launch_kv_project(const pcv_kvproj_params& p, cudaStream_t stream) {
   gp.num_kb = (p.C + kBK - 1) / kBK;
   gp.tiles_n = (n_total + kBN - 1) / kBN;
   const int64_t rows_per_tile = (int64_t)kBM * cg;
-  gp.num_tiles = ((p.rows + rows_per_tile - 1) / rows_per_tile) * gp.tiles_n;
+  gp.m_blocks = (p.rows + rows_per_tile - 1) / rows_per_tile;
+  gp.num_tiles = gp.m_blocks * gp.tiles_n;
+  gp.C = p.C;
+  gp.eps = p.ln_eps;
+  const bool fuse = p.row_stats == nullptr && p.ln_eps > 0.f;
 
   CUtensorMap tx, tw, tk, tv;
   int rc = make_tmap_2d(&tx, p.x, p.dtype, p.C, p.rows, p.x_stride_row, kBM);
@@ -576,8 +692,22 @@ int launch_kv_project(const pcv_kvproj_params& p, cudaStream_t stream) {
   if (rc != PCV_OK) return rc;
 
   const bool bf = p.dtype == PCV_BF16;
-  if (cg == 2) return bf ? launch_gemm<true, 2>(tx, tw, tk, tv, gp, sms, stream) : launch_gemm<false, 2>(tx, tw, tk, tv, gp, sms, stream);
-  return bf ? launch_gemm<true, 1>(tx, tw, tk, tv, gp, sms, stream) : launch_gemm<false, 1>(tx, tw, tk, tv, gp, sms, stream);
+#define PCV_GEMM_CASE(B, G, F) return launch_gemm<B, G, F>(tx, tw, tk, tv, gp, sms, stream)
+  if (cg == 2) {
+    if (fuse) {
+      if (bf) PCV_GEMM_CASE(true, 2, true);
+      PCV_GEMM_CASE(false, 2, true);
+    }
+    if (bf) PCV_GEMM_CASE(true, 2, false);
+    PCV_GEMM_CASE(false, 2, false);
+  }
+  if (fuse) {
+    if (bf) PCV_GEMM_CASE(true, 1, true);
+    PCV_GEMM_CASE(false, 1, true);
+  }
+  if (bf) PCV_GEMM_CASE(true, 1, false);
+  PCV_GEMM_CASE(false, 1, false);
+#undef PCV_GEMM_CASE
 }
 
 }  // namespace pcv

@@ -122,9 +122,18 @@ def attend(mha, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_mask=None
         k, v = ops.kv_append(kv_cache[0], kv_cache[1], k, v)
         kv_cache = (k, v)
 
-    if rot_pos_emb_q is not None:
-        q = _rotate_rows(rot_pos_emb_q, q, mha.num_heads)
-    k_att = k if rot_pos_emb_k is None else _rotate_rows(rot_pos_emb_k, k, mha.num_heads)
+    k_att = None
+    if (kv_cache is not None and rot_pos_emb_q is not None and rot_pos_emb_k is not None
+            and getattr(rot_pos_emb_k, "inv_freq", None) is not None and bool(rot_pos_emb_k.right_align)
+            and bool(rot_pos_emb_q.right_align) and not (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad))):
+        # decode path: keys are rotated once, when they enter the cache (ops.rotated_cache_keys)
+        hit = ops.rotated_cache_keys(k, q, mha.num_heads, rot_pos_emb_k.inv_freq)
+        if hit is not None:
+            q, k_att = hit
+    if k_att is None:
+        if rot_pos_emb_q is not None:
+            q = _rotate_rows(rot_pos_emb_q, q, mha.num_heads)
+        k_att = k if rot_pos_emb_k is None else _rotate_rows(rot_pos_emb_k, k, mha.num_heads)
 
     o = ops.attention(q, k_att, v, mha.num_heads, mha.dp_scale, pad_mask=pad_mask,
                       causal=mha.causal_attention, impl=getattr(mha, "kernel_impl", "auto"))
@@ -200,6 +209,21 @@ def project_kv(cross_attn, x_kv: torch.Tensor):
     w_cat, col_st = _fold_cache(cross_attn, "_pcv_kv_fold", norm if norm.weight is not None else None,
                                 [attn.k_proj, attn.v_proj], x_kv.dtype)
     return ops.kv_project(x_kv, w_cat, col_st, n_k, n_v, eps=norm.eps)
+
+
+def project_qkv(self_attn, x: torch.Tensor):
+    """``q_proj(norm(x)), k_proj(norm(x)), v_proj(norm(x))`` of a SelfAttention (reference modules.py:276, :113-115) as
+    ONE LayerNorm-folded tcgen05 GEMM over [Wq; Wk; Wv] (``ops.kv_project`` with q as its first output and [k | v] as
+    the second: k and v are column ranges of one buffer, the attention kernel takes them by stride).  Returns None when
+    the fused path does not apply (autograd, fp32, autocast, tiny inputs): the caller then runs the library path."""
+    attn, norm = self_attn.attention, self_attn.norm
+    n_q, n_k, n_v = attn.q_proj.out_features, attn.k_proj.out_features, attn.v_proj.out_features
+    if not (_fusable(x, [attn.q_proj, attn.k_proj, attn.v_proj], norm) and ops.kv_project_supported(x, n_q, n_k + n_v)):
+        return None
+    w_cat, col_st = _fold_cache(self_attn, "_pcv_qkv_fold", norm if norm.weight is not None else None,
+                                [attn.q_proj, attn.k_proj, attn.v_proj], x.dtype)
+    q, kv = ops.kv_project(x, w_cat, col_st, n_q, n_k + n_v, eps=norm.eps)
+    return q, kv[..., :n_k], kv[..., n_k:]
 
 
 class CrossAttention(nn.Module):
@@ -293,6 +317,9 @@ class SelfAttention(nn.Module):
         rot_pos_emb: Optional[RotaryPositionEmbedding] = None,
         kv_cache: Optional[KVCache] = None,
     ):
+        qkv = project_qkv(self, x)
+        if qkv is not None:
+            return attend(self.attention, qkv[0], qkv[1], qkv[2], pad_mask, rot_pos_emb, rot_pos_emb, kv_cache)
         x = self.norm(x)
         return self.attention(x, x, pad_mask=pad_mask, rot_pos_emb_q=rot_pos_emb, rot_pos_emb_k=rot_pos_emb,
                               kv_cache=kv_cache)
@@ -738,12 +765,14 @@ class PerceiverAR(nn.Module):
         else:
             ca_cache, sa_cache, new_cache = kv_cache[0], list(kv_cache[1:]), []
 
+        # frequency table of the adapter: lets cached decoding rotate new keys only (ops.rotated_cache_keys)
+        inv_freq = getattr(getattr(self.input_adapter, "frq_pos_encoding", None), "inv_freq", None)
         ca_out = self.cross_attention(
             x_latent,
             x_kv_prefix=x_prefix,
             pad_mask=pad_mask,
-            rot_pos_emb_q=RotaryPositionEmbedding(frq_latent, right_align=True),
-            rot_pos_emb_k=RotaryPositionEmbedding(frq_keys, right_align=True),
+            rot_pos_emb_q=RotaryPositionEmbedding(frq_latent, right_align=True, inv_freq=inv_freq),
+            rot_pos_emb_k=RotaryPositionEmbedding(frq_keys, right_align=True, inv_freq=inv_freq),
             kv_cache=ca_cache,
         )
         if new_cache is not None:
@@ -751,7 +780,7 @@ class PerceiverAR(nn.Module):
 
         sa_out = self.self_attention(
             ca_out.last_hidden_state,
-            rot_pos_emb=RotaryPositionEmbedding(frq_latent, right_align=True),
+            rot_pos_emb=RotaryPositionEmbedding(frq_latent, right_align=True, inv_freq=inv_freq),
             kv_cache=sa_cache,
         )
         if new_cache is not None:

@@ -23,7 +23,7 @@ from ._lib import (AttnParams, CombineParams, KvAppendParams, KvProjParams, LnSt
 
 __all__ = [
     "attention", "attention_partial", "attention_sharded_fused", "combine_partials", "merge_partials", "rescale_partial_", "rotary", "kv_append",
-    "device_info", "tcgen05_supported", "ln_stats", "fold_ln_linear", "kv_project", "kv_project_supported",
+    "device_info", "tcgen05_supported", "rotated_cache_keys", "ln_stats", "fold_ln_linear", "kv_project", "kv_project_supported",
 ]
 
 
@@ -173,37 +173,92 @@ def _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl):
     return out if out.dtype == out_dtype else out.to(out_dtype)
 
 
+#: Budget of the backward shim: the largest fp32 score block (B, H, N, chunk) it materialises at a time.
+backward_config = {"max_score_bytes": 1 << 30}
+
+
 class _FusedAttention(torch.autograd.Function):
-    """Forward = the fused CUDA kernel.  Backward = TRAINING-SUPPORT SHIM, not a kernel:
-    it recomputes softmax(QK^T)V with plain torch ops on the same device so that the reference's
-    Lightning wrappers can still call ``loss.backward()`` (SURVEY.md §7.3 "Training"); a fused
-    backward is listed under §8(f) rank 2.  The forward never routes through it."""
+    """Forward = the fused CUDA kernel (partial-state mode, so the row max and denominator are kept).
+    Backward = TRAINING-SUPPORT SHIM, not a kernel: the flash-attention backward recurrence in plain torch ops,
+    chunked over the key axis from the saved softmax statistics, so that the reference's Lightning wrappers can call
+    ``loss.backward()`` (SURVEY.md §7.3 "Training") at any M without ever holding the (B, H, N, M) score tensor
+    (8.6 GB at the north-star shape): memory is bounded by ``backward_config["max_score_bytes"]``.  A fused backward
+    kernel is SURVEY.md §8(f) rank 2.  The inference forward never routes through this class."""
 
     @staticmethod
     def forward(ctx, q, k, v, num_heads, scale, pad_mask, causal, impl):
-        ctx.save_for_backward(q, k, v, pad_mask)
+        dv_true = _head_dim(v, num_heads)
+        if _head_dim(q, num_heads) % 8 or dv_true % 8 or impl == "decode":
+            # head dims the partial-state kernels do not take without padding: plain forward, statistics recomputed
+            out = _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl)
+            ctx.save_for_backward(q, k, v, pad_mask, out, None, None)
+        else:
+            po, pm, pl = attention_partial(q, k, v, num_heads, scale, pad_mask=pad_mask, causal=causal, impl=impl)
+            out = combine_partials(po[None], pm[None], pl[None], _compute_dtype(q.dtype))
+            out = out if out.dtype == q.dtype else out.to(q.dtype)
+            ctx.save_for_backward(q, k, v, pad_mask, out, pm, pl)
         ctx.meta = (num_heads, scale, causal)
-        return _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl)
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        q, k, v, pad_mask = ctx.saved_tensors
+        q, k, v, pad_mask, out, pm, pl = ctx.saved_tensors
         H, scale, causal = ctx.meta
-        with torch.enable_grad():
-            qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
-            B, M = kf.shape[0], kf.shape[1]
-            N = qf.shape[1]
-            qh = qf.expand(B, -1, -1).reshape(B, N, H, -1).transpose(1, 2)
-            kh = kf.reshape(B, M, H, -1).transpose(1, 2)
-            vh = vf.reshape(B, M, H, -1).transpose(1, 2)
-            s = torch.matmul(qh * scale, kh.transpose(-1, -2))
-            neg = -torch.finfo(s.dtype).max
+        B, M = k.shape[0], k.shape[1]
+        N = q.shape[1]
+        cdt = _compute_dtype(q.dtype)
+        # the kernel saw operands rounded to the compute dtype: differentiate the same function
+        qh = q.to(cdt).float().expand(B, -1, -1).reshape(B, N, H, -1).transpose(1, 2)      # (B,H,N,dqk)
+        kh = k.to(cdt).float().reshape(B, M, H, -1).transpose(1, 2)                         # (B,H,M,dqk)
+        vh = v.to(cdt).float().reshape(B, M, H, -1).transpose(1, 2)                         # (B,H,M,dv)
+        go = grad_out.float().reshape(B, N, H, -1).transpose(1, 2)                          # (B,H,N,dv)
+        oh = out.float().reshape(B, N, H, -1).transpose(1, 2)
+        t_scale = scale * 1.4426950408889634
+        neg = -torch.finfo(torch.float32).max
+        chunk = max(128, int(backward_config["max_score_bytes"] // (4 * B * H * N)) // 128 * 128)
+
+        def scores(j0, j1):  # log2-domain scores with the reference's finite mask fill, and the fill mask
+            t = torch.matmul(qh, kh[:, :, j0:j1].transpose(-1, -2)) * t_scale
+            filled = None
             if pad_mask is not None:
-                s = s.masked_fill(pad_mask.bool()[:, None, None, :], neg)
+                filled = pad_mask[:, j0:j1].bool()[:, None, None, :].expand(B, 1, N, j1 - j0)
             if causal:
-                s = s.masked_fill(torch.ones(N, M, dtype=torch.bool, device=s.device).triu(M - N + 1), neg)
-            o = torch.matmul(s.softmax(-1), vh).transpose(1, 2).reshape(B, N, -1)
-            gq, gk, gv = torch.autograd.grad(o, (qf, kf, vf), grad_out.float())
+                rows = torch.arange(N, device=t.device)[:, None] + (M - N)
+                cm = (torch.arange(j0, j1, device=t.device)[None, :] > rows)[None, None]
+                filled = cm if filled is None else (filled | cm)
+            if filled is not None:
+                t = t.masked_fill(filled, neg)
+            return t, filled
+
+        if pm is None:  # statistics were not saved: one chunked pass to rebuild them
+            m_run = torch.full((B, H, N), -float("inf"), device=q.device)
+            l_run = torch.zeros(B, H, N, device=q.device)
+            for j0 in range(0, M, chunk):
+                t, _ = scores(j0, min(M, j0 + chunk))
+                m_new = torch.maximum(m_run, t.amax(-1))
+                l_run = l_run * torch.exp2(m_run - m_new) + torch.exp2(t - m_new[..., None]).sum(-1)
+                m_run = m_new
+            pm, pl = m_run, l_run
+        delta = (go * oh).sum(-1)                                                            # (B,H,N)
+        gq = torch.zeros_like(qh)
+        gk = torch.empty_like(kh)
+        gv = torch.empty_like(vh)
+        inv_l = 1.0 / pl
+        for j0 in range(0, M, chunk):
+            j1 = min(M, j0 + chunk)
+            t, filled = scores(j0, j1)
+            p = torch.exp2(t - pm[..., None]) * inv_l[..., None]                             # (B,H,N,c) probabilities
+            gv[:, :, j0:j1] = torch.matmul(p.transpose(-1, -2), go)
+            ds = p * (torch.matmul(go, vh[:, :, j0:j1].transpose(-1, -2)) - delta[..., None])
+            if filled is not None:
+                ds = ds.masked_fill(filled, 0.0)  # a filled score is a constant (masked_fill_): no gradient through it
+            gq += torch.matmul(ds, kh[:, :, j0:j1])
+            gk[:, :, j0:j1] = torch.matmul(ds.transpose(-1, -2), qh)
+        gq = (gq * scale).transpose(1, 2).reshape(B, N, -1)
+        if q.shape[0] == 1 and B > 1:
+            gq = gq.sum(0, keepdim=True)
+        gk = (gk * scale).transpose(1, 2).reshape(B, M, -1)
+        gv = gv.transpose(1, 2).reshape(B, M, -1)
         return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), None, None, None, None, None
 
 
@@ -329,7 +384,8 @@ def rescale_partial_(part_o: torch.Tensor, part_m: torch.Tensor, part_l: torch.T
         check(_lib.lib().pcv_partial_rescale(C.byref(p), _stream()), "pcv_partial_rescale")
 
 
-def _rotary_forward(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: bool) -> torch.Tensor:
+def _rotary_forward(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right_align: bool,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _require_cuda(x, angles)
     out_dtype = x.dtype
     cdt = _compute_dtype(x.dtype)
@@ -337,9 +393,14 @@ def _rotary_forward(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right
     B, n, Cx = x.shape
     d = Cx // num_heads
     Ba, n_angles, f = angles.shape
-    y = torch.empty(B, n, Cx, dtype=cdt, device=x.device)
+    if out is not None:
+        if out.shape != x.shape or out.dtype != cdt or out.stride(2) != 1:
+            raise ValueError("rotary: `out` must match x in shape and compute dtype with unit channel stride")
+        y = out
+    else:
+        y = torch.empty(B, n, Cx, dtype=cdt, device=x.device)
     if n == 0:
-        return y.to(out_dtype)
+        return y if out is not None else y.to(out_dtype)
     p = RotaryParams()
     p.x, p.y, p.angles = x.data_ptr(), y.data_ptr(), angles.data_ptr()
     p.x_stride_b, p.x_stride_n, p.x_stride_h = x.stride(0), x.stride(1), d
@@ -352,6 +413,8 @@ def _rotary_forward(x: torch.Tensor, num_heads: int, angles: torch.Tensor, right
     p.dtype = _pcv_dtype(cdt)
     with torch.cuda.device(x.device):
         check(_lib.lib().pcv_rotary_apply(C.byref(p), _stream()), "pcv_rotary_apply")
+    if out is not None:
+        return y
     return y if cdt == out_dtype else y.to(out_dtype)
 
 
@@ -412,13 +475,14 @@ class _KvArena:
     an attribute OF the buffer and refers back to it only weakly, so a superseded buffer is released by reference
     counting as soon as the last cache view of it is dropped (no tensor <-> arena cycle waiting for the cyclic GC)."""
 
-    __slots__ = ("buf_ref", "used")
+    __slots__ = ("buf_ref", "used", "rot")
 
     def __init__(self, buf: torch.Tensor):
         import weakref
 
         self.buf_ref = weakref.ref(buf)
         self.used = 0
+        self.rot = None  # rotated shadow of a K arena: dict(buf, lo, hi, key), see rotated_cache_keys
 
 
 _ARENA_ATTR = "_pcv_kv_arena"
@@ -534,6 +598,54 @@ def kv_append(k_cache: torch.Tensor, v_cache: torch.Tensor, k_new: torch.Tensor,
     return k_dst, v_dst
 
 
+#: Rotated-key cache of the decode path (``enabled=False``: re-rotate the whole cache every step like the reference).
+rotated_cache_config = {"enabled": True}
+
+
+def _abs_angles(inv_freq: torch.Tensor, row0: int, n: int) -> torch.Tensor:
+    """(1, n, 2*len(inv_freq)) angles of absolute positions row0 .. row0+n-1: position * inv_freq with every frequency
+    repeated twice — exactly FrequencyPositionEncoding.forward (reference position.py:69-71)."""
+    pos = torch.arange(row0, row0 + n, device=inv_freq.device, dtype=inv_freq.dtype)
+    return (pos[None, :, None] * inv_freq[None, None, :]).repeat_interleave(2, dim=-1).float()
+
+
+def rotated_cache_keys(k: torch.Tensor, q: torch.Tensor, num_heads: int, inv_freq: torch.Tensor):
+    """Rotary embedding of a cached decode step WITHOUT re-rotating the cache: returns ``(q_rot, k_rot)`` or None.
+
+    ``k`` (B, L, C) must be a row range of a KV arena (what :func:`kv_append` returns) and the rows of ``q`` (B, N, C)
+    must be the LAST N tokens of ``k`` (true for the Perceiver-AR cross-attention and the causal latent self-attention).
+    Rotary scores depend on position DIFFERENCES only, so instead of the reference's window-relative positions
+    (``positions(b, n, shift)``, which change for every cached key whenever the window slides or the batch rows are
+    padded differently) every key is rotated ONCE, when it is first seen, at the absolute position "its row index in
+    the arena", into a shadow buffer kept beside the arena; q is rotated at the row index of its own token.  For every
+    non-masked (query, key) pair the angle difference equals the reference's (pos_q - pos_k = row_q - row_k; padded
+    rows are masked out), so the scores agree up to rounding, and a decode step rotates N new rows instead of L.
+    Arena rows are write-once (an append that is not at the frontier gets a fresh arena), so shadow rows never go stale."""
+    if not rotated_cache_config["enabled"]:
+        return None
+    hit = _arena_of(k)
+    if hit is None or inv_freq is None or q.shape[1] > k.shape[1] or k.dtype not in (torch.bfloat16, torch.float16):
+        return None
+    arena, start = hit
+    root = k._base if k._base is not None else k
+    L, N = k.shape[1], q.shape[1]
+    inv_freq = inv_freq.to(device=k.device, dtype=torch.float32)
+    key = (inv_freq.data_ptr(), int(inv_freq.numel()), num_heads)
+    rot = arena.rot
+    if rot is None or rot["key"] != key:
+        rot = {"buf": torch.empty_like(root), "lo": 0, "hi": 0, "key": key}
+        arena.rot = rot
+    end = start + L
+    if not (rot["lo"] <= start <= rot["hi"]):   # nothing reusable: rotate the whole range once
+        rot["lo"], rot["hi"] = start, start
+    if rot["hi"] < end:
+        a, b = rot["hi"], end
+        _rotary_forward(root[:, a:b], num_heads, _abs_angles(inv_freq, a, b - a), False, out=rot["buf"][:, a:b])
+        rot["hi"] = end
+    q_rot = _rotary_forward(q, num_heads, _abs_angles(inv_freq, end - N, N), False)
+    return q_rot, rot["buf"][:, start:end]
+
+
 def tcgen05_supported(q, k, v, num_heads: int, pad_mask=None, causal: bool = False) -> bool:
     """True when pcv_attn_fwd would pick the tcgen05 kernel for these operands."""
     q, k, v, _ = _prep(q, k, v)
@@ -598,7 +710,7 @@ def fold_ln_linear(norm_weight, norm_bias, weights, biases, dtype: torch.dtype):
     return w_cat, col_st
 
 
-def _fill_kvproj(x2, w_cat, col_st, n_k, n_v, stats, k_out, v_out, cta_group=0) -> KvProjParams:
+def _fill_kvproj(x2, w_cat, col_st, n_k, n_v, stats, k_out, v_out, cta_group=0, ln_eps=0.0) -> KvProjParams:
     p = KvProjParams()
     p.x, p.w, p.col_st = x2.data_ptr(), w_cat.data_ptr(), col_st.data_ptr()
     p.row_stats = None if stats is None else stats.data_ptr()
@@ -610,6 +722,7 @@ def _fill_kvproj(x2, w_cat, col_st, n_k, n_v, stats, k_out, v_out, cta_group=0) 
     p.rows, p.C, p.n_k, p.n_v = x2.shape[0], x2.shape[1], n_k, n_v
     p.dtype = _pcv_dtype(x2.dtype)
     p.cta_group = cta_group
+    p.ln_eps = float(ln_eps)
     return p
 
 
@@ -621,9 +734,17 @@ def kv_project_supported(x: torch.Tensor, n_k: int, n_v: int) -> bool:
     return C_in % 8 == 0 and n_k % 64 == 0 and n_v % 8 == 0 and (n_k + n_v) > 0
 
 
+#: ``stats``: "separate" = pcv_ln_stats first (two-pass statistics; x is read twice, at the copy bandwidth), "fused" =
+#: statistics computed inside the GEMM kernel from the staged tiles (x crosses HBM once).  Measured equal in time at the
+#: north-star shape (the statistics warps delay the recycling of a ring stage by about what the extra pass costs;
+#: profiles/r02_kvproj_bench.log), so the default is the numerically more conservative two-pass variant.
+kv_project_config = {"stats": "separate"}
+
+
 def kv_project(x: torch.Tensor, w_cat: torch.Tensor, col_st: torch.Tensor, n_k: int, n_v: int,
-               eps: Optional[float] = 1e-5, cta_group: int = 0):
-    """K, V = LN(x) Wk^T + bk, LN(x) Wv^T + bv for x (..., C) through pcv_ln_stats + pcv_kv_project.
+               eps: Optional[float] = 1e-5, cta_group: int = 0, stats: Optional[str] = None):
+    """K, V = LN(x) Wk^T + bk, LN(x) Wv^T + bv for x (..., C) through pcv_kv_project (statistics in-kernel or by
+    pcv_ln_stats, see ``kv_project_config``).
 
     ``w_cat`` / ``col_st`` come from :func:`fold_ln_linear`; ``eps=None`` skips the LayerNorm (plain projection).
     Returns contiguous (..., n_k) and (..., n_v) tensors in x's dtype (``None`` for a width of 0)."""
@@ -634,11 +755,13 @@ def kv_project(x: torch.Tensor, w_cat: torch.Tensor, col_st: torch.Tensor, n_k: 
         raise ValueError("kv_project: col_st must be a contiguous (n_k + n_v, 2) float32 tensor")
     lead = x.shape[:-1]
     x2 = _rows2d(x)
+    mode = kv_project_config["stats"] if stats is None else stats
     with torch.cuda.device(x.device):
-        stats = None if eps is None else ln_stats(x2, eps)
+        st = ln_stats(x2, eps) if (eps is not None and mode != "fused") else None
         k_out = torch.empty(x2.shape[0], n_k, dtype=x.dtype, device=x.device) if n_k else None
         v_out = torch.empty(x2.shape[0], n_v, dtype=x.dtype, device=x.device) if n_v else None
-        p = _fill_kvproj(x2, w_cat, col_st, n_k, n_v, stats, k_out, v_out, cta_group)
+        p = _fill_kvproj(x2, w_cat, col_st, n_k, n_v, st, k_out, v_out, cta_group,
+                         ln_eps=(eps if (eps is not None and mode == "fused") else 0.0))
         check(_lib.lib().pcv_kv_project(C.byref(p), _stream()), "pcv_kv_project")
     k = None if k_out is None else k_out.view(*lead, n_k)
     v = None if v_out is None else v_out.view(*lead, n_v)

@@ -11,7 +11,7 @@ import types
 
 from torch import nn
 
-from .modules import CrossAttention, MultiHeadAttention
+from .modules import CrossAttention, MultiHeadAttention, SelfAttention
 
 _REQUIRED = ("q_proj", "k_proj", "v_proj", "o_proj", "dp_scale", "num_heads", "causal_attention", "dropout")
 
@@ -25,11 +25,17 @@ def _is_reference_cross_attention(module: nn.Module) -> bool:
             and all(hasattr(module, a) for a in ("q_norm", "kv_norm", "attention")))
 
 
+def _is_reference_self_attention(module: nn.Module) -> bool:
+    return (type(module).__name__ == "SelfAttention" and not isinstance(module, SelfAttention)
+            and all(hasattr(module, a) for a in ("norm", "attention")))
+
+
 def patch(model: nn.Module, impl: str = "auto") -> int:
     """Route every MultiHeadAttention under ``model`` through the sm_100a kernels.
 
-    Reference ``CrossAttention`` modules (modules.py:173-230) are rebound as well so that their
-    ``kv_norm`` -> ``k_proj`` / ``v_proj`` chain runs through the fused K/V producer (``modules.project_kv``).
+    Reference ``CrossAttention`` / ``SelfAttention`` modules (modules.py:173-278) are rebound as well so that their
+    LayerNorm -> projection chains run through the LayerNorm-folded tcgen05 GEMM (``modules.project_kv`` /
+    ``modules.project_qkv``).
     Returns the number of attention modules rebound; idempotent."""
     count = 0
     for module in model.modules():
@@ -42,4 +48,6 @@ def patch(model: nn.Module, impl: str = "auto") -> int:
             count += 1
         elif _is_reference_cross_attention(module):
             module.forward = types.MethodType(CrossAttention.forward, module)
+        elif _is_reference_self_attention(module):
+            module.forward = types.MethodType(SelfAttention.forward, module)
     return count

@@ -29,11 +29,15 @@ def positions(b: int, n: int, shift: Optional[torch.Tensor] = None, device=None)
 class RotaryPositionEmbedding:
     """Holds per-position rotation angles; applies them to the leading channels of each head."""
 
-    def __init__(self, frq_pos_enc: torch.Tensor, right_align: bool = False):
+    def __init__(self, frq_pos_enc: torch.Tensor, right_align: bool = False, inv_freq: Optional[torch.Tensor] = None):
         # (b, n, f) angles, stored broadcastable over heads like the reference does
         self.frq_pos_enc = frq_pos_enc.unsqueeze(1)
         self.rotate_dim = frq_pos_enc.shape[-1]
         self.right_align = right_align
+        # optional (not in the reference's signature): the frequency table the angles were built from
+        # (FrequencyPositionEncoding.inv_freq).  With it, cached keys can be rotated ONCE, at an absolute position, when
+        # they are appended (ops.rotated_cache_keys) instead of re-rotating the whole cache every decode step
+        self.inv_freq = inv_freq
 
     def rotate_rows(self, x: torch.Tensor, num_heads: int) -> torch.Tensor:
         """x: (B, n, H*d) pre-head-split projection output -> rotated copy (fast path used by MHA)."""

@@ -54,7 +54,8 @@ SHAPES = [
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("cg", [1, 2], ids=["cta1", "cta2"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
-def test_kv_project_matches_layernorm_linear(shape, cg, dtype):
+@pytest.mark.parametrize("stats", ["fused", "separate"])
+def test_kv_project_matches_layernorm_linear(shape, cg, dtype, stats):
     from perceiver_io_b200 import ops
 
     rows, C, n_k, n_v = shape
@@ -62,7 +63,7 @@ def test_kv_project_matches_layernorm_linear(shape, cg, dtype):
     ws = [wk] + ([wv] if n_v else [])
     bs = [bk] + ([bv] if n_v else [])
     w_cat, col_st = ops.fold_ln_linear(gamma, beta, ws, bs, dtype)
-    k, v = ops.kv_project(x, w_cat, col_st, n_k, n_v, eps=1e-5, cta_group=cg)
+    k, v = ops.kv_project(x, w_cat, col_st, n_k, n_v, eps=1e-5, cta_group=cg, stats=stats)
     rk64, rv64 = _reference(x, gamma, beta, wk, bk, wv if n_v else wk[:0], bv if n_v else None, torch.float64)
     ek, ev = _reference(x, gamma, beta, wk, bk, wv if n_v else wk[:0], bv if n_v else None, dtype)
     assert k.shape == (rows, n_k) and k.dtype == dtype
@@ -100,11 +101,12 @@ def test_large_row_mean_does_not_break_the_folded_cancellation():
     x = (torch.randint(-8, 9, (rows, C), generator=g).float() * 0.25 + 48.0).to(dtype).cuda()
     _, gamma, beta, wk, bk, wv, bv = _case(rows, C, n, n, dtype, seed=4)
     w_cat, col_st = ops.fold_ln_linear(gamma, beta, [wk, wv], [bk, bv], dtype)
-    k, v = ops.kv_project(x, w_cat, col_st, n, n)
     rk64, rv64 = _reference(x, gamma, beta, wk, bk, wv, bv, torch.float64)
     ek, ev = _reference(x, gamma, beta, wk, bk, wv, bv, dtype)
-    _check(k, rk64, ek, "K large mean")
-    _check(v, rv64, ev, "V large mean")
+    for stats in ("fused", "separate"):   # one-pass shifted statistics in the GEMM kernel / two-pass pcv_ln_stats
+        k, v = ops.kv_project(x, w_cat, col_st, n, n, stats=stats)
+        _check(k, rk64, ek, f"K large mean ({stats})")
+        _check(v, rv64, ev, f"V large mean ({stats})")
 
 
 def test_plain_projection_without_layernorm():

@@ -305,3 +305,68 @@ def test_prefix_dropout_matches_reference_given_the_same_random_matrix(monkeypat
     assert torch.equal(seen["x_latent"].cpu(), g["x_latent"])
     assert_close(seen["frq_keys"], g["frq_keys"], 1e-6, "gathered key angles")
     assert_close(out.logits, g["logits"], REL_DEEP, "prefix-dropout logits")
+
+
+def test_rotated_key_cache_matches_rerotation_incl_sliding_window():
+    """Decode path (§8(f)3): keys are rotated once, at an absolute position, when they enter the cache
+    (ops.rotated_cache_keys) instead of re-rotating the whole cache every step like the reference
+    (modules.py:129-130).  Greedy-style loop with left padding, 40 cached steps and the 🤗-side sliding-window
+    truncation of both caches (core/huggingface.py:146-156): logits must agree with the re-rotation path and with
+    the uncached forward over the same window."""
+    import perceiver_io_b200 as P
+    from perceiver_io_b200 import ops
+
+    torch.manual_seed(3)
+    cfg = P.CausalSequenceModelConfig(vocab_size=97, max_seq_len=160, max_latents=48, num_channels=128, num_heads=4,
+                                      num_self_attention_layers=2, num_self_attention_rotary_layers=1,
+                                      cross_attention_dropout=0.0, output_norm=True, abs_pos_emb=False, init_scale=0.1)
+    model = P.CausalSequenceModel(cfg).cuda().bfloat16().eval()
+    B, n0, prefix = 2, 120, 90
+    tokens = torch.randint(0, 97, (B, n0 + 40)).cuda()
+    pad = torch.zeros(B, n0 + 40, dtype=torch.bool, device="cuda")
+    pad[1, :7] = True
+
+    import copy
+
+    model32 = copy.deepcopy(model).float()   # same (bf16-rounded) weights in fp32: only q/k/v are rounded, at the kernel boundary
+
+    def run(shadow, model=model):
+        ops.rotated_cache_config["enabled"] = shadow
+        outs = []
+        try:
+            with torch.no_grad():
+                o = model(tokens[:, :n0], prefix_len=prefix, pad_mask=pad[:, :n0], kv_cache=[])
+                cache, plen = o.kv_cache, prefix
+                for s in range(40):
+                    n = cache[0][0].shape[1] + 1
+                    if n > cfg.max_seq_len:                      # sliding window: drop the oldest cached token
+                        cache = [(cache[0][0][:, 1:], cache[0][1][:, 1:])] + cache[1:]
+                        n -= 1
+                    nlat = cache[1][0].shape[1] + 1
+                    if nlat > cfg.max_latents:                    # a latent moves into the prefix
+                        cache = cache[:1] + [(k[:, 1:], v[:, 1:]) for k, v in cache[1:]]
+                        plen += 1
+                    pm = pad[:, n0 + s + 1 - n: n0 + s + 1]
+                    o = model(tokens[:, n0 + s: n0 + s + 1], prefix_len=plen, pad_mask=pm, kv_cache=cache)
+                    cache = o.kv_cache
+                    outs.append(o.logits[:, 0].float())
+        finally:
+            ops.rotated_cache_config["enabled"] = True
+        return torch.stack(outs)
+
+    a, b, truth = run(True), run(False), run(False, model32)
+    assert torch.isfinite(a).all()
+    scale = truth.abs().max().item()
+    # same function; keys rotated at absolute instead of window-relative angles.  Yardstick: the fp32 model on the
+    # re-rotation path; the shadow path may not be further from it than the bf16 re-rotation path (which rounds the same
+    # tensors at the same places) by more than a factor — the derived-gate idea of gpu_util applied to two bf16 arms
+    err_a, err_b = (a - truth).abs().max().item(), (b - truth).abs().max().item()
+    print(f"[parity] rotated-key cache: shadow err {err_a:.3e}, re-rotation err {err_b:.3e}, max|logit| {scale:.3e}")
+    assert err_a <= 2.0 * err_b + 1e-3 * scale, (err_a, err_b, scale)
+    # the shadow really was used: the K arena of the cross-attention cache carries one
+    ops.rotated_cache_config["enabled"] = True
+    with torch.no_grad():
+        o = model(tokens[:, :n0], prefix_len=prefix, pad_mask=pad[:, :n0], kv_cache=[])
+    k = o.kv_cache[0][0]
+    root = k._base if k._base is not None else k
+    assert getattr(root, "_pcv_kv_arena").rot is not None

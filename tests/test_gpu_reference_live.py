@@ -96,7 +96,7 @@ class _PassThroughInput(core.InputAdapter):
 
 def test_patch_on_reference_perceiver_encoder():
     torch.manual_seed(0)
-    B, M, C, N, D = 2, 3000, 256, 192, 512
+    B, M, C, N, D = 2, 3000, 256, 320, 512
     enc = core.PerceiverEncoder(
         _PassThroughInput(C), num_latents=N, num_latent_channels=D, num_cross_attention_heads=4,
         num_cross_attention_layers=2, first_cross_attention_layer_shared=False, num_self_attention_heads=8,
@@ -110,7 +110,10 @@ def test_patch_on_reference_perceiver_encoder():
     with torch.no_grad():
         r64 = copy.deepcopy(enc).double().cuda()(x.double().cuda(), pad_mask=pad.cuda())
         eager = copy.deepcopy(enc).bfloat16().cuda()(x.cuda(), pad_mask=pad.cuda())
-        ours = _patched_bf16(enc)(x.cuda(), pad_mask=pad.cuda())
+        mine = _patched_bf16(enc)
+        ours = mine(x.cuda(), pad_mask=pad.cuda())
+    folded = [k for m in mine.modules() for k in m.__dict__ if k.startswith("_pcv_") and k.endswith("_fold")]
+    assert "_pcv_qkv_fold" in folded and "_pcv_kv_fold" in folded and "_pcv_o_fold" in folded, folded
     _gate(ours, r64, eager, "reference PerceiverEncoder, patched (2 cross-attention + 4 self-attention layers)")
 
 

@@ -10,6 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from perceiver_io_b200 import _lib, ops  # noqa: E402
 
+ONLY = os.environ.get("PCV_SWEEP_ONLY")  # substring filter
 CASES = [
     # name, B, N, M, H, dqk, dv, causal
     ("mnist enc x-attn (N=32,M=784,dh=131)", 8, 32, 784, 1, 131, 131, False),
@@ -31,11 +32,17 @@ CASES = [
 
 rows = []
 for name, B, N, M, H, dqk, dv, causal in CASES:
+    if ONLY and ONLY not in name:
+        continue
     torch.manual_seed(0)
     q = torch.randn(B, N, H * dqk, device="cuda").bfloat16()
     k = torch.randn(B, M, H * dqk, device="cuda").bfloat16()
     v = torch.randn(B, M, H * dv, device="cuda").bfloat16()
     fam = "tcgen05" if ops.tcgen05_supported(q, k, v, H, causal=causal) else "simt"
+    if N <= 4 and M >= 1024 and dqk % 8 == 0 and dv % 8 == 0 and max(dqk, dv) <= 256:
+        fam = "decode (streaming)"
+    elif fam == "tcgen05" and (dqk > 128 or dv > 256):
+        fam = "tcgen05 big-head"
     reps = 3 if fam == "simt" and N * M > 1e8 else 20
     for _ in range(2):
         ops.attention(q, k, v, H, dqk ** -0.5, causal=causal)

@@ -45,14 +45,14 @@ def gemm_only():
 
 
 kl, vl = lib()
-for cg in (2, 1):
-    k, v = ops.kv_project(x, w_cat, col_st, n, n, eps=1e-5, cta_group=cg)
+for cg, mode in ((2, "fused"), (2, "separate"), (1, "fused"), (1, "separate")):
+    k, v = ops.kv_project(x, w_cat, col_st, n, n, eps=1e-5, cta_group=cg, stats=mode)
     torch.cuda.synchronize()
     dk = (k.float() - kl.float()).abs().max().item()
     dv = (v.float() - vl.float()).abs().max().item()
-    ms = timed(lambda: ops.kv_project(x, w_cat, col_st, n, n, eps=1e-5, cta_group=cg))
+    ms = timed(lambda: ops.kv_project(x, w_cat, col_st, n, n, eps=1e-5, cta_group=cg, stats=mode))
     st = timed(lambda: ops.ln_stats(x, 1e-5))
-    print(f"fused cg={cg}: {ms:.3f} ms total ({flops / ms / 1e9:.0f} TFLOP/s), of which ln_stats {st:.3f} ms "
+    print(f"producer cg={cg} stats={mode}: {ms:.3f} ms total ({flops / ms / 1e9:.0f} TFLOP/s); separate ln_stats pass alone {st:.3f} ms "
           f"({rows * C * 2 / st / 1e6:.0f} GB/s); max|dK| {dk:.3e} max|dV| {dv:.3e} vs library (max|K| {kl.float().abs().max().item():.2f})")
 ms = timed(lib)
 print(f"library LN + 2 x cuBLAS: {ms:.3f} ms ({flops / ms / 1e9:.0f} TFLOP/s)")
