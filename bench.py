@@ -474,7 +474,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--kernel", choices=["auto", "tcgen05", "simt"], default="auto")
+    ap.add_argument("--kernel", choices=["auto", "tcgen05", "tcgen05_pair", "simt"], default="auto")
     ap.add_argument("--kv-layout", choices=["token_major", "head_major"], default="token_major",
                     help="memory layout of the projected K/V: (B,M,H*dh) as nn.Linear writes it, or (B,H,M,dh)")
     ap.add_argument("--merge", choices=["auto", "fused", "peer", "nccl"], default="auto",

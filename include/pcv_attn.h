@@ -53,7 +53,7 @@ enum pcv_impl {
   PCV_IMPL_AUTO = 0,         /* decode kernel for N <= 4 and M >= 1024, tcgen05 kernel when the shape fits, else SIMT */
   PCV_IMPL_TCGEN05 = 1,      /* tcgen05 single-CTA kernel or error */
   PCV_IMPL_SIMT = 2,         /* CUDA-core coverage kernel */
-  PCV_IMPL_TCGEN05_PAIR = 3, /* retired (the cta_group::2 attention kernel is no longer built): always an error */
+  PCV_IMPL_TCGEN05_PAIR = 3, /* cta_group::2 CTA-pair kernel (qk and v head dims <= 128; 512 query rows per unit) or error */
   PCV_IMPL_DECODE = 4        /* streaming kernel for N <= 4 query rows against a long cache (HBM-bound) or error */
 };
 

@@ -9,6 +9,7 @@ Layout (tier scope: SURVEY.md §8 only):
   position.py / adapter.py / utils.py / config.py   the small pieces those modules need
   dist.py      M-sharded cross-attention across the GPUs of one box
   patch.py     swap the attention arithmetic inside an already-built reference model
+  streaming.py host-resident K/V input pipelined against PCIe;  graphs.py  CUDA-graph capture of static-shape forwards
 """
 from .utils import ModuleOutput, Residual, init_parameters, freeze  # noqa: F401
 from .position import positions, RotaryPositionEmbedding, FrequencyPositionEncoding  # noqa: F401

@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("PCV_LIB_PATH") or os.path.join(_HERE, "lib", "libpcv_
 
 PCV_BF16, PCV_F16, PCV_F32 = 0, 1, 2
 PCV_IMPL_AUTO, PCV_IMPL_TCGEN05, PCV_IMPL_SIMT, PCV_IMPL_TCGEN05_PAIR, PCV_IMPL_DECODE = 0, 1, 2, 3, 4
-IMPL_BY_NAME = {"auto": PCV_IMPL_AUTO, "tcgen05": PCV_IMPL_TCGEN05, "simt": PCV_IMPL_SIMT, "decode": PCV_IMPL_DECODE}
+IMPL_BY_NAME = {"auto": PCV_IMPL_AUTO, "tcgen05": PCV_IMPL_TCGEN05, "simt": PCV_IMPL_SIMT, "decode": PCV_IMPL_DECODE,
+                "tcgen05_pair": PCV_IMPL_TCGEN05_PAIR}
 
 EXPORTS = (
     "pcv_abi_version",

@@ -47,6 +47,11 @@ constexpr int kThreads = 384;  // 12 warps: 8 softmax + MMA + TMA + 2 idle (fill
 constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr float kRescaleThreshold = 8.f;  // log2 units
+#ifndef PCV_PAIR_DEFAULT
+#define PCV_PAIR_DEFAULT 0
+#endif
+constexpr bool kPairByDefault = PCV_PAIR_DEFAULT != 0;  // build-time choice after the A/B measurement
+constexpr int kFlagsPerSlot = 16;          // fix-up flags per slot: one per 32-row warp slice of a unit (<= 512 rows)
 // compile-time experiment knob: column pairs (of every 4) of an optimistic tile whose 2^x runs on the FMA pipes
 // (exp2_poly2) instead of MUFU.  0 in the product (measured slower at 1 of 4).
 #ifndef PCV_POLY_QUARTERS
@@ -92,6 +97,7 @@ struct TcParams {
   const int* cta_seg_begin;
   int B, H, N, M, dv;
   int dv_off, dv_pass;              // this launch writes output channels [dv_off, dv_off + dv_pass)
+  int nc128;                        // big-head streaming kernel: number of 128-channel chunks of the qk head dim
   int nc;                           // big-head kernel: number of 64-channel boxes of the qk head dim
   int v_boxes;                      // big-head kernel: 64-channel boxes of V in this pass
   int dqk_pad;                      // big-head kernel: qk head dim rounded up to 16 (K-steps of the ragged last box)
@@ -111,7 +117,7 @@ struct TcParams {
   // the per-warp "rows stored" flags of the other parts and folds their slots into its own accumulator rows while
   // writing the result, so no separate merge kernel (and no extra pass over the state) is needed.
   const UnitRec* units;
-  unsigned long long* slot_flags;   // [slot][8]: == fixup_tag once warp w of that part has stored its 32 rows
+  unsigned long long* slot_flags;   // [slot][16]: == fixup_tag once warp w of that part has stored its 32 rows
   unsigned long long fixup_tag;     // unique per launch (workspace memory is not cleared between launches)
   int rows_per_unit;                // query rows per work unit: 256 (two tiles per CTA) or 128 (wide-dv / big-head)
   int slot_rows;                    // row stride of the partial slots (>= rows_per_unit)
@@ -192,6 +198,7 @@ struct TileCtx;
 __device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c);
 
 struct TileCtx {
+  uint32_t p_full_remote;  // 0: arrive on the local p_full[wg]; else shared::cluster address of the pair leader's p_full[wg]
   uint64_t* pv_bar;      // non-null: barrier (and parity) to wait on before rescaling O — kernels whose S(j) does not imply PV(j-1) done
   uint32_t pv_parity;
   uint32_t tS, tO;    // TMEM addresses (lane field included) of this thread's S / O row
@@ -211,7 +218,10 @@ __device__ __forceinline__ void arrive_p_full(Barriers& bar, const TileCtx& c) {
   // 4 arrivals per tile instead of 128 serialised updates of one shared-memory word
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
-    mbar_arrive(&bar.p_full[c.wg]);
+    if (c.p_full_remote == 0)
+      mbar_arrive(&bar.p_full[c.wg]);
+    else
+      mbar_arrive_cluster_relaxed(c.p_full_remote);  // P is in TMEM (tcgen05.wait::st returned): no memory to release
   }
 }
 
@@ -392,7 +402,7 @@ __device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsign
 
 // wait (bounded) until another CTA's warp has published its 32 slot rows; call with the whole warp converged
 __device__ __forceinline__ void wait_slot_rows(const TcParams& p, int slot, int warp_in_unit) {
-  const unsigned long long* f = p.slot_flags + (int64_t)slot * 8 + warp_in_unit;
+  const unsigned long long* f = p.slot_flags + (int64_t)slot * kFlagsPerSlot + warp_in_unit;
   if ((threadIdx.x & 31) == 0) {
     uint32_t spins = 0;
     uint64_t t0 = 0;
@@ -446,7 +456,7 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const Segment& s
     if (FIXUP) {
       __threadfence();
       __syncwarp();
-      if ((threadIdx.x & 31) == 0) st_release_gpu_u64(p.slot_flags + (int64_t)seg.slot * 8 + (row_in_unit >> 5), p.fixup_tag);
+      if ((threadIdx.x & 31) == 0) st_release_gpu_u64(p.slot_flags + (int64_t)seg.slot * kFlagsPerSlot + (row_in_unit >> 5), p.fixup_tag);
     }
     return;
   }
@@ -532,10 +542,15 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const Segment& s
   }
 }
 
+// pair_rank < 0: single-CTA kernel.  Otherwise this CTA is rank `pair_rank` of a cta_group::2 pair: query tile `wg` of
+// the pair spans 256 rows (128 per CTA) and the p_full / o_empty barriers the MMA issuer waits on live in the leader CTA.
 template <int DQK, int DV, bool BF16>
 __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, int wg, int row, int seg_lo,
-                                             int seg_hi) {
-  const int row_in_unit = wg * kTileM + row;
+                                             int seg_hi, int pair_rank = -1) {
+  const bool pair = pair_rank >= 0;
+  const int row_in_unit = wg * (pair ? 2 * kTileM : kTileM) + (pair ? pair_rank * kTileM : 0) + row;
+  const uint32_t p_full_remote = (pair && pair_rank != 0) ? mapa_cluster(smem_u32(&bar.p_full[wg]), 0) : 0u;
+  const uint32_t o_empty_remote = (pair && pair_rank != 0) ? mapa_cluster(smem_u32(&bar.o_empty[wg]), 0) : 0u;
   const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
   const uint32_t tS = bar.tmem_base + lane_field + (uint32_t)(wg * 128);
   const uint32_t tO = bar.tmem_base + lane_field + 256u + (uint32_t)(wg * 128);
@@ -552,6 +567,7 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     st.l = 0.f;
     TileCtx c;
     c.tS = tS; c.tO = tO; c.wg = wg; c.row = row;
+    c.p_full_remote = p_full_remote;
     c.pv_bar = nullptr;
     c.pv_parity = 0;
     c.cshift = n + p.causal_shift;
@@ -595,7 +611,12 @@ __device__ __forceinline__ void softmax_role(const TcParams& p, Barriers& bar, i
     epilogue_row<DV, BF16, true>(p, seg, tO, n, row_in_unit, l, m_ref);
     tc_fence_before_sync();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&bar.o_empty[wg]);
+    if ((threadIdx.x & 31) == 0) {
+      if (o_empty_remote == 0)
+        mbar_arrive(&bar.o_empty[wg]);
+      else
+        mbar_arrive_cluster_relaxed(o_empty_remote);  // the accumulator rows were read with tcgen05.ld + wait::ld
+    }
   }
 }
 
@@ -1040,6 +1061,472 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
 
 // --------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): one work unit = 512 query rows of one (b, h) on TWO SMs.  Every tcgen05.mma has
+// M = 256 (128 rows from each CTA); each CTA stages its own Q rows, HALF of every K tile (64 keys: N/2 of Q K^T) and
+// HALF of every V tile (64 channels: N/2 of P V), so the SS-mode operand reads of Q K^T drop from 128 to 96 bytes per
+// clock and SM — the shared-memory ceiling the single-CTA kernel's issuing thread blocks on — and the L2 -> SM traffic
+// per SM halves.  Only the leader CTA issues MMAs; tcgen05.commit multicasts to the barriers of both CTAs.
+// Round 1 measured this structure at 0.91 PF (vs 1.25 PF single-CTA) and shelved it; the fused K/V producer's profile
+//  showed why: every cross-CTA `mbarrier.arrive.release.cluster` compiles to MEMBAR.ALL.GPU +
+// ERRBAR + CGAERRBAR, and the kernel issued one per K/V stage from the peer's producer (ERRBAR waits for the thread's
+// outstanding TMA loads: ring depth 1) and one per tile from EVERY softmax warp, on the critical chain.  Here: the peer
+// producer never arrives (the leader's expect_tx covers both CTAs' bytes), the leader's softmax warps arrive locally,
+// the peer's with `mbarrier.arrive.relaxed.cluster` (P is in TMEM once tcgen05.wait::st returns; nothing to release).
+// --------------------------------------------------------------------------------------------------
+template <int DQK>
+struct PairCfg {
+  static constexpr int DV = 128;
+  static constexpr int kQBoxes = DQK / 64;
+  static constexpr int kQTileBytes = kQBoxes * kBoxBytes;        // 128 rows x DQK
+  static constexpr int kQBytes = 2 * kQTileBytes;
+  static constexpr int kKHalfBytes = kQBoxes * (kBoxBytes / 2);  // 64 keys x DQK: kQBoxes boxes of 64 rows
+  static constexpr int kVHalfBytes = kBoxBytes;                  // 128 keys x 64 channels
+  static constexpr int kStageBytes = kKHalfBytes > kVHalfBytes ? kKHalfBytes : kVHalfBytes;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kMaxSmem = 232448 - 1024;
+  static constexpr int kStagesRaw = (kMaxSmem - kQBytes - kBarrierBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kBarrierBytes + 1024;
+  static_assert(kStages >= 3, "ring too shallow");
+};
+
+template <int DQK, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
+  using C = PairCfg<DQK>;
+  constexpr int DV = C::DV;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + C::kQBytes;
+  Barriers& bar = *reinterpret_cast<Barriers*>(smem + C::kQBytes + C::kStages * C::kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair_id = blockIdx.x >> 1;
+  const int seg_lo = p.cta_seg_begin[pair_id];
+  const int seg_hi = p.cta_seg_begin[pair_id + 1];
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar.q_full, 1);    // the leader's arrive.expect_tx announces the bytes of BOTH CTAs; the peer never arrives
+    mbar_init(&bar.q_empty, 1);   // multicast commit
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&bar.kv_full[i], 1);
+      mbar_init(&bar.kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar.s_full[i], 1);
+      mbar_init(&bar.p_full[i], 8);   // one arrive per softmax warp, 4 warps x 2 CTAs
+      mbar_init(&bar.o_full[i], 1);
+      mbar_init(&bar.o_empty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_pair(&bar.tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after_sync();
+
+  if (warp < 8) {
+    reg_alloc<216>();
+    softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi, (int)rank);
+    if (p.tail.enabled) peer_tail<DV, BF16>(p);
+  } else {
+    reg_dealloc<72>();
+  }
+
+  if (warp == kTmaWarp) {
+    // ===== TMA producer (both CTAs): own Q tiles, own half of every K / V tile; bytes counted on the leader =====
+    const bool leader_lane = elect_one();
+    uint32_t it = 0, n_q = 0;
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const int bq = p.q_bcast ? 0 : seg.b;
+      mbar_wait(&bar.q_empty, (n_q & 1) ^ 1, 1);
+      ++n_q;
+      if (leader_lane) {
+        if (rank == 0) mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(2 * seg.ntile * C::kQTileBytes));
+        for (int i = 0; i < seg.ntile; ++i)
+          for (int bx = 0; bx < C::kQBoxes; ++bx)
+            tma_load_4d_pair(q_smem + i * C::kQTileBytes + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64,
+                             seg.q0 + i * 2 * kTileM + (int)rank * kTileM, seg.h, bq);
+      }
+      for (int t = seg.t0; t < seg.t1; ++t) {
+        {
+          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+          mbar_wait(&bar.kv_empty[slot], par ^ 1, 2);
+          if (leader_lane) {
+            if (rank == 0) mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(2 * C::kKHalfBytes));
+#pragma unroll
+            for (int bx = 0; bx < C::kQBoxes; ++bx)  // K half: 64 keys x 64 channels per box
+              tma_load_4d_pair(kv_smem + slot * C::kStageBytes + bx * (kBoxBytes / 2), &tmap_k, &bar.kv_full[slot],
+                               bx * 64, t * kTileN + (int)rank * 64, seg.h, seg.b);
+          }
+          ++it;
+        }
+        {
+          const uint32_t slot = it % C::kStages, par = (it / C::kStages) & 1;
+          mbar_wait(&bar.kv_empty[slot], par ^ 1, 3);
+          if (leader_lane) {
+            if (rank == 0) mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)(2 * C::kVHalfBytes));
+            // V half: all 128 keys, channels [64*rank, 64*rank + 64)
+            tma_load_4d_pair(kv_smem + slot * C::kStageBytes, &tmap_v, &bar.kv_full[slot], (int)rank * 64, t * kTileN,
+                             seg.h, seg.b);
+          }
+          ++it;
+        }
+      }
+    }
+  } else if (warp == kMmaWarp && rank == 0) {
+    // ===== MMA issuer (leader CTA only) =====
+    const bool leader_lane = elect_one();
+    constexpr uint32_t idesc_qk = make_idesc(2 * kTileM, kTileN, BF16, false);
+    constexpr uint32_t idesc_pv = make_idesc(2 * kTileM, DV, BF16, true);
+    const uint32_t tmem = bar.tmem_base;
+    const uint64_t dq0 = make_smem_desc(smem_u32(q_smem), 16, 1024);
+    const uint64_t dk0 = make_smem_desc(smem_u32(kv_smem), 16, 1024);
+    const uint64_t dv0 = make_smem_desc(smem_u32(kv_smem), kBoxBytes, 1024);
+    uint32_t it = 0, n_q = 0, n_p0 = 0, n_p1 = 0, n_oe0 = 0, n_oe1 = 0;
+
+    auto issue_qk = [&](int i, uint32_t k_slot) {
+      if (leader_lane) {
+        const uint64_t da = dq0 + (uint64_t)((i * C::kQTileBytes) >> 4);
+        const uint64_t db = dk0 + (uint64_t)((k_slot * C::kStageBytes) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < DQK / 16; ++kk) {
+          const uint64_t offa = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          const uint64_t offb = (uint64_t)(((kk >> 2) * (kBoxBytes / 2) + (kk & 3) * 32) >> 4);
+          mma_ss_pair(tmem + i * 128, da + offa, db + offb, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+      }
+    };
+    auto issue_pv = [&](int i, uint32_t v_slot, bool accumulate) {
+      if (leader_lane) {
+        const uint64_t db = dv0 + (uint64_t)((v_slot * C::kStageBytes) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < kTileN / 16; ++kk)
+          mma_ts_pair(tmem + 256 + i * 128, tmem + i * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+                      (accumulate || kk > 0) ? 1u : 0u);
+      }
+    };
+    auto commit = [&](uint64_t* b) {
+      if (leader_lane) tc_commit_pair(b, 3);
+    };
+
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const bool two = seg.ntile == 2;
+      const int nt = seg.t1 - seg.t0;
+      mbar_wait(&bar.q_full, n_q & 1, 4);
+      ++n_q;
+
+      uint32_t k_slot = it % C::kStages;
+      mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 5);
+      ++it;
+      tc_fence_after_sync();
+      issue_qk(0, k_slot);
+      commit(&bar.s_full[0]);
+      if (two) {
+        issue_qk(1, k_slot);
+        commit(&bar.s_full[1]);
+      }
+      commit(&bar.kv_empty[k_slot]);
+
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t v_slot = it % C::kStages;
+        mbar_wait(&bar.kv_full[v_slot], (it / C::kStages) & 1, 6);
+        ++it;
+        if (j == 0) {
+          mbar_wait(&bar.o_empty[0], (n_oe0 & 1) ^ 1, 7);
+          ++n_oe0;
+        }
+        mbar_wait(&bar.p_full[0], n_p0 & 1, 8);
+        ++n_p0;
+        tc_fence_after_sync();
+        issue_pv(0, v_slot, j > 0);
+        const bool more = (j + 1 < nt);
+        if (more) {
+          k_slot = it % C::kStages;
+          mbar_wait(&bar.kv_full[k_slot], (it / C::kStages) & 1, 9);
+          ++it;
+          tc_fence_after_sync();
+          issue_qk(0, k_slot);
+          commit(&bar.s_full[0]);
+        }
+        if (two) {
+          if (j == 0) {
+            mbar_wait(&bar.o_empty[1], (n_oe1 & 1) ^ 1, 10);
+            ++n_oe1;
+          }
+          mbar_wait(&bar.p_full[1], n_p1 & 1, 11);
+          ++n_p1;
+          tc_fence_after_sync();
+          issue_pv(1, v_slot, j > 0);
+        }
+        commit(&bar.kv_empty[v_slot]);
+        if (more) {
+          if (two) {
+            issue_qk(1, k_slot);
+            commit(&bar.s_full[1]);
+          }
+          commit(&bar.kv_empty[k_slot]);
+        }
+      }
+      commit(&bar.q_empty);
+      commit(&bar.o_full[0]);
+      if (two) commit(&bar.o_full[1]);
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its pair can still touch its memory / barriers
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(bar.tmem_base, 512);
+  }
+}
+
+
+// --------------------------------------------------------------------------------------------------
+// Big-head STREAMING kernel (round 1's structure, kept for head dims the resident-Q kernel below handles worse:
+// qk head dim > 384 or v head dim > 384, i.e. the optical-flow decoder's 512 / 512): qk head dims up to 512 and v head
+// dims up to 256 per pass (the optical-flow encoder /
+// decoder geometry, 322 and 512 channels per head).  One query tile (128 rows) per CTA.  Q and K stream through
+// shared memory in 128-channel chunks (Q is re-streamed from L2 for every key tile) and S accumulates over the
+// chunks in TMEM; S is double-buffered (columns [0,128) / [128,256)) so Q K^T of tile j+1 overlaps the softmax
+// of tile j; O occupies columns [256, 256 + 64*v_boxes).  A v head dim above 256 is covered by launching the
+// kernel once per 256-channel slice of V (the scores are recomputed).  256 threads: warps 0-3 softmax (one
+// thread per row), warp 4 MMA issuer, warp 5 TMA producer.
+// --------------------------------------------------------------------------------------------------
+constexpr int kBigStreamThreads = 256;
+constexpr int kBigStreamItems = 3;
+constexpr int kBigStreamItemBytes = 4 * kBoxBytes;  // 64 KB: [Q chunk 32 KB | K chunk 32 KB] or a V tile of <= 256 channels
+constexpr int kBigStreamSmemBytes = kBigStreamItems * kBigStreamItemBytes + 1024 + 1024;
+
+struct BigStreamBarriers {
+  uint64_t item_full[kBigStreamItems], item_empty[kBigStreamItems];
+  uint64_t s_full[2], pv_done, o_full, o_empty;  // s_full per S buffer: a barrier must never run a full phase ahead of its waiter
+  uint32_t tmem_base;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(kBigStreamThreads, 1)
+attn_tc_bigstream_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  BigStreamBarriers& bb = *reinterpret_cast<BigStreamBarriers*>(smem + kBigStreamItems * kBigStreamItemBytes);
+  // the shared softmax helpers address barriers through the common struct; alias the fields they touch
+  Barriers& bar = *reinterpret_cast<Barriers*>(smem + kBigStreamItems * kBigStreamItemBytes + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seg_lo = p.cta_seg_begin[blockIdx.x];
+  const int seg_hi = p.cta_seg_begin[blockIdx.x + 1];
+  constexpr int kMma = 4, kTma = 5;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBigStreamItems; ++i) {
+      mbar_init(&bb.item_full[i], 1);
+      mbar_init(&bb.item_empty[i], 1);
+    }
+    mbar_init(&bb.s_full[0], 1);
+    mbar_init(&bb.s_full[1], 1);
+    mbar_init(&bar.p_full[0], 4);  // arrive_p_full() targets bar.p_full[c.wg]; c.wg = S buffer index here
+    mbar_init(&bar.p_full[1], 4);
+    mbar_init(&bb.pv_done, 1);
+    mbar_init(&bb.o_full, 1);
+    mbar_init(&bb.o_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == kMma) {
+    tmem_alloc(&bb.tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == kTma && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bb.tmem_base;
+
+  if (warp < 4) {
+    // ===== softmax + epilogue: thread = query row =====
+    const int row = threadIdx.x;
+    const uint32_t lane_field = (uint32_t)((row >> 5) * 32) << 16;
+    const uint32_t tO = tmem + lane_field + 256u;
+    uint32_t n_tile = 0, n_o = 0;  // n_tile: key tiles processed by this CTA so far (all segments)
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const int n = seg.q0 + row;
+      RowState st;
+      st.m_ref = -INFINITY;
+      st.l = 0.f;
+      TileCtx c;
+      c.tO = tO; c.row = row;
+      c.p_full_remote = 0;
+      c.pv_bar = &bb.pv_done;
+      c.cshift = n + p.causal_shift;
+      c.trace_on = false;
+      c.scale_log2 = p.scale_log2;
+      for (int t = seg.t0; t < seg.t1; ++t) {
+        const int j = t - seg.t0;
+        const uint32_t buf = n_tile & 1;  // S buffer (and its barriers) alternate over ALL tiles of the CTA
+        c.wg = (int)buf;
+        c.tS = tmem + lane_field + buf * 128u;
+        c.j0 = t * kTileN;
+        c.tt = j;
+        c.first_tile = (j == 0);
+        c.pv_parity = (n_tile + 1) & 1;  // phase of the previous tile's PV on pv_done
+        c.mw = make_uint4(0, 0, 0, 0);
+        if (p.pad_bits != nullptr)
+          c.mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)seg.b * p.pad_wpr + (size_t)t * 4);
+        const bool masked_tile =
+            __any_sync(0xffffffffu, (c.j0 + kTileN > p.M) || ((c.mw.x | c.mw.y | c.mw.z | c.mw.w) != 0u) ||
+                                        (p.causal && (c.j0 + kTileN - 1 > c.cshift)));
+        mbar_wait(&bb.s_full[buf], (n_tile >> 1) & 1, 12);
+        tc_fence_after_sync();
+        if (masked_tile) {
+          softmax_tile<256, BF16, true>(p, bar, c, st);
+        } else if (p.optimistic && !c.first_tile) {
+          if (!softmax_tile_optimistic<256, BF16, 0>(p, bar, c, st)) softmax_tile<256, BF16, false>(p, bar, c, st);
+        } else {
+          softmax_tile<256, BF16, false>(p, bar, c, st);
+        }
+        ++n_tile;
+      }
+      mbar_wait(&bb.o_full, n_o & 1, 13);
+      ++n_o;
+      tc_fence_after_sync();
+      epilogue_row<256, BF16, false>(p, seg, tO, n, row, st.l, st.m_ref);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bb.o_empty);
+    }
+  } else if (warp == kTma) {
+    // ===== TMA producer; item order = consumption order: QK(0), QK(1), V(0), QK(2), V(1), ... =====
+    const bool leader = elect_one();
+    uint32_t it = 0;
+    auto load_qk = [&](const Segment& seg, int t) {
+      const int bq = p.q_bcast ? 0 : seg.b;
+      for (int ch = 0; ch < p.nc128; ++ch) {
+        const uint32_t slot = it % kBigStreamItems, par = (it / kBigStreamItems) & 1;
+        mbar_wait(&bb.item_empty[slot], par ^ 1, 2);
+        if (leader) {
+          uint8_t* base = smem + slot * kBigStreamItemBytes;
+          mbar_arrive_expect_tx(&bb.item_full[slot], (uint32_t)kBigStreamItemBytes);
+          tma_load_4d(base, &tmap_q, &bb.item_full[slot], ch * 128, seg.q0, seg.h, bq);
+          tma_load_4d(base + kBoxBytes, &tmap_q, &bb.item_full[slot], ch * 128 + 64, seg.q0, seg.h, bq);
+          tma_load_4d(base + 2 * kBoxBytes, &tmap_k, &bb.item_full[slot], ch * 128, t * kTileN, seg.h, seg.b);
+          tma_load_4d(base + 3 * kBoxBytes, &tmap_k, &bb.item_full[slot], ch * 128 + 64, t * kTileN, seg.h, seg.b);
+        }
+        ++it;
+      }
+    };
+    auto load_v = [&](const Segment& seg, int t) {
+      const uint32_t slot = it % kBigStreamItems, par = (it / kBigStreamItems) & 1;
+      mbar_wait(&bb.item_empty[slot], par ^ 1, 3);
+      if (leader) {
+        uint8_t* base = smem + slot * kBigStreamItemBytes;
+        mbar_arrive_expect_tx(&bb.item_full[slot], (uint32_t)(p.v_boxes * kBoxBytes));
+        for (int bx = 0; bx < p.v_boxes; ++bx)
+          tma_load_4d(base + bx * kBoxBytes, &tmap_v, &bb.item_full[slot], bx * 64, t * kTileN, seg.h, seg.b);
+      }
+      ++it;
+    };
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      load_qk(seg, seg.t0);
+      for (int t = seg.t0; t < seg.t1; ++t) {
+        if (t + 1 < seg.t1) load_qk(seg, t + 1);
+        load_v(seg, t);
+      }
+    }
+  } else if (warp == kMma) {
+    // ===== MMA issuer =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_qk = make_idesc(kTileM, kTileN, BF16, false);
+    const uint32_t idesc_pv = make_idesc(kTileM, 64 * p.v_boxes, BF16, true);
+    const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);          // K-major operands (Q / K chunks)
+    const uint64_t dv0 = make_smem_desc(smem_u32(smem), kBoxBytes, 1024);  // MN-major V tile
+    uint32_t it = 0, n_qk = 0, n_pvi = 0, n_oe = 0;  // n_qk / n_pvi: tiles whose QK^T / PV have been issued (all segments)
+    auto commit = [&](uint64_t* b) {
+      if (leader) tc_commit(b);
+    };
+    auto issue_qk = [&]() {  // S[n_qk & 1] = Q K^T of the next tile, accumulated over the channel chunks
+      const uint32_t buf = n_qk & 1;
+      for (int ch = 0; ch < p.nc128; ++ch) {
+        const uint32_t slot = it % kBigStreamItems;
+        mbar_wait(&bb.item_full[slot], (it / kBigStreamItems) & 1, 5);
+        ++it;
+        tc_fence_after_sync();
+        if (leader) {
+          const uint64_t da = d0 + (uint64_t)((slot * kBigStreamItemBytes) >> 4);
+          const uint64_t db = da + (uint64_t)((2 * kBoxBytes) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+            mma_ss(tmem + buf * 128, da + off, db + off, idesc_qk, (ch > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        commit(&bb.item_empty[slot]);
+      }
+      commit(&bb.s_full[buf]);
+      ++n_qk;
+    };
+    for (int sg = seg_lo; sg < seg_hi; ++sg) {
+      const Segment seg = p.segs[sg];
+      const int nt = seg.t1 - seg.t0;
+      issue_qk();
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) issue_qk();
+        const uint32_t buf = n_pvi & 1;
+        const uint32_t slot = it % kBigStreamItems;
+        mbar_wait(&bb.item_full[slot], (it / kBigStreamItems) & 1, 6);
+        ++it;
+        if (j == 0) {
+          mbar_wait(&bb.o_empty, (n_oe & 1) ^ 1, 7);
+          ++n_oe;
+        }
+        mbar_wait(&bar.p_full[buf], (n_pvi >> 1) & 1, 8);
+        tc_fence_after_sync();
+        if (leader) {
+          const uint64_t db = dv0 + (uint64_t)((slot * kBigStreamItemBytes) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < kTileN / 16; ++kk)
+            mma_ts(tmem + 256, tmem + buf * 128 + kk * 8, db + (uint64_t)((kk * 2048) >> 4), idesc_pv,
+                   (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        commit(&bb.item_empty[slot]);
+        commit(&bb.pv_done);
+        ++n_pvi;
+      }
+      commit(&bb.o_full);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMma) {
+    tc_fence_after_sync();
+    tmem_dealloc(bb.tmem_base, 512);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
 // Big-head kernel: qk head dims up to 512 and up to 384 v channels per pass (the optical-flow encoder / decoder
 // geometry: 322 and 512 channels per head, reference vision/optical_flow/backend.py:22-27,104-109).  One query tile
 // (128 rows) per CTA, 256 threads: warps 0-3 softmax (one thread per row), warp 4 MMA issuer, warp 5 TMA producer.
@@ -1130,6 +1617,7 @@ attn_tc_big_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       c.tO = tO;
       c.row = row;
       c.wg = 0;
+      c.p_full_remote = 0;
       c.pv_bar = nullptr;  // S(j) complete implies P V(j-1) complete (single S buffer, in-order tensor pipe)
       c.pv_parity = 0;
       c.cshift = n + p.causal_shift;
@@ -1453,7 +1941,8 @@ constexpr size_t kMaxPlans = 256;
 
 struct Mode {
   int rows_per_unit, rows_per_tile, slot_rows;
-  bool big;  // big-head kernel (qk head dim > 128 or v head dim > 256)
+  bool big;   // big-head kernels (qk head dim > 128 or v head dim > 256)
+  bool pair;  // cta_group::2 kernel: workers are CTA pairs, 512 query rows per unit
 };
 
 void free_plan_tables(Plan& pl) {
@@ -1484,6 +1973,7 @@ int get_plan(int B, int H, int N, int M, const Mode& mode, std::shared_ptr<Plan>
     int rc = ensure_diag(dev);
     if (rc != PCV_OK) return rc;
   }
+  if (mode.pair) sms /= 2;  // workers are CTA pairs
   const int QB = (N + mode.rows_per_unit - 1) / mode.rows_per_unit;
   const int T = (M + kTileN - 1) / kTileN;
   const int last_ntile =
@@ -1560,15 +2050,27 @@ int make_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int ro
 inline int pad64(int d) { return (d + 63) / 64 * 64; }
 
 size_t slots_bytes(const Plan& pl, int DV, int slot_rows) {
-  // [slot][row][DV] numerators, [slot][row] row max, [slot][row] denominators, then [slot][8] 64-bit fix-up flags
-  return sizeof(float) * (size_t)pl.num_slots * slot_rows * (DV + 2) + sizeof(unsigned long long) * (size_t)pl.num_slots * 8;
+  // [slot][row][DV] numerators, [slot][row] row max, [slot][row] denominators, then [slot][16] 64-bit fix-up flags
+  return sizeof(float) * (size_t)pl.num_slots * slot_rows * (DV + 2) + sizeof(unsigned long long) * (size_t)pl.num_slots * kFlagsPerSlot;
+}
+
+// The CTA-pair kernel takes a call when it is asked for (impl = PCV_IMPL_TCGEN05_PAIR) or, with impl = AUTO, when the
+// shape is its home ground: v head dim <= 128 and at least two 256-row query tiles per (b, h), i.e. N > 256.
+bool pair_wanted(const pcv_attn_params& a) {
+  if (pad64(a.dv) > 128 || pad64(a.dqk) > 128) return false;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+  if (sms < 2 || (sms % 2)) return false;
+  if (a.impl == PCV_IMPL_TCGEN05_PAIR) return true;
+  return kPairByDefault && a.impl == PCV_IMPL_AUTO && a.N > kRowsPerUnit;
 }
 
 Mode choose_mode(const pcv_attn_params& a) {
   const int DV = pad64(a.dv);
-  if (pad64(a.dqk) > 128 || DV > 256) return Mode{kTileM, kTileM, kTileM, true};
-  if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false};
-  return Mode{kRowsPerUnit, kTileM, kRowsPerUnit, false};
+  if (pad64(a.dqk) > 128 || DV > 256) return Mode{kTileM, kTileM, kTileM, true, false};
+  if (DV > 128) return Mode{kTileM, kTileM, kRowsPerUnit, false, false};
+  if (pair_wanted(a)) return Mode{4 * kTileM, 2 * kTileM, 4 * kTileM, false, true};
+  return Mode{kRowsPerUnit, kTileM, kRowsPerUnit, false, false};
 }
 
 template <int DQK, int DV, bool BF16>
@@ -1599,6 +2101,68 @@ int launch_cfg(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, 
   PCV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return PCV_OK;  // split units are merged by the fix-up in the kernel's own epilogue: no second launch
+}
+
+template <int DQK, bool BF16>
+int launch_pair(const pcv_attn_params& a, const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk,
+                const CUtensorMap& tv, TcParams& p, cudaStream_t stream) {
+  using C = PairCfg<DQK>;
+  auto kern = attn_tc_pair_kernel<DQK, BF16>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pl.num_ctas);  // num_ctas counts CTA pairs in this mode
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_mark_begin(stream);
+  PCV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, p));
+  prof_mark_end(stream);
+  count_launch();
+  return PCV_OK;  // split units are fixed up inside the kernel
+}
+
+template <bool BF16>
+int launch_bigstream(const Plan& pl, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, TcParams& p,
+                     cudaStream_t stream) {
+  auto kern = attn_tc_bigstream_kernel<BF16>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      PCV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigStreamSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+  }
+  prof_mark_begin(stream);
+  kern<<<pl.num_ctas, kBigStreamThreads, kBigStreamSmemBytes, stream>>>(tq, tk, tv, p);
+  prof_mark_end(stream);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  if (pl.num_units > 0) {
+    dim3 grid(pl.num_units, p.slot_rows / 8);
+    tc_combine_kernel<256, BF16><<<grid, 256, 0, stream>>>(pl.d_units, p);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return PCV_OK;
 }
 
 template <bool BF16>
@@ -1723,8 +2287,8 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream, const pcv_shar
   std::shared_ptr<Plan> pl;
   const int DQK = pad64(a.dqk), DV = pad64(a.dv);
   const Mode mode = choose_mode(a);
-  PCV_REQUIRE(a.impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
-              "the cta_group::2 attention kernel was a measured dead end (0.91 vs 1.25 PFLOP/s) and is no longer built");
+  PCV_REQUIRE(mode.pair || a.impl != PCV_IMPL_TCGEN05_PAIR, PCV_ERR_UNSUPPORTED,
+              "the cta_group::2 kernel needs qk and v head dims <= 128 and an even SM count");
   int rc = get_plan(a.B, a.H, a.N, a.M, mode, &pl);
   if (rc != PCV_OK) return rc;
   size_t need = 0;
@@ -1817,12 +2381,28 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream, const pcv_shar
   const int Bq = a.q_stride_b == 0 ? 1 : a.B;
   rc = make_tmap(&tq, a.q, a.dtype, a.dqk, a.N, a.H, Bq, a.q_stride_n, a.q_stride_h, a.q_stride_b);
   if (rc != PCV_OK) return rc;
-  rc = make_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b);
+  rc = make_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b,
+                 mode.pair ? kTileN / 2 : kTileN);  // the pair kernel loads 64-key halves of every K tile
   if (rc != PCV_OK) return rc;
   rc = make_tmap(&tv, a.v, a.dtype, a.dv, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
   if (rc != PCV_OK) return rc;
 
   const bool bf = a.dtype == PCV_BF16;
+  if (mode.big && (a.dqk > kBigDv || a.dv > kBigDv)) {
+    // widest heads (optical-flow decoder 512 / 512): streaming kernel, one launch per 256-channel slice of V
+    p.nc128 = (a.dqk + 127) / 128;
+    for (int off = 0; off < a.dv; off += 256) {
+      p.dv_off = off;
+      p.dv_pass = std::min(256, a.dv - off);
+      p.v_boxes = (p.dv_pass + 63) / 64;
+      const char* vbase = reinterpret_cast<const char*>(a.v) + 2 * (size_t)off;
+      rc = make_tmap(&tv, vbase, a.dtype, p.dv_pass, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
+      if (rc != PCV_OK) return rc;
+      rc = bf ? launch_bigstream<true>(*pl, tq, tk, tv, p, stream) : launch_bigstream<false>(*pl, tq, tk, tv, p, stream);
+      if (rc != PCV_OK) return rc;
+    }
+    return PCV_OK;
+  }
   if (mode.big) {
     // one launch per 384-channel slice of V (the scores are recomputed per slice; dv <= 384 is a single pass)
     p.nc = (a.dqk + 63) / 64;
@@ -1839,6 +2419,11 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream, const pcv_shar
       if (rc != PCV_OK) return rc;
     }
     return PCV_OK;
+  }
+  if (mode.pair) {
+    if (DQK == 128)
+      return bf ? launch_pair<128, true>(a, *pl, tq, tk, tv, p, stream) : launch_pair<128, false>(a, *pl, tq, tk, tv, p, stream);
+    return bf ? launch_pair<64, true>(a, *pl, tq, tk, tv, p, stream) : launch_pair<64, false>(a, *pl, tq, tk, tv, p, stream);
   }
 #define PCV_TC_CASE(DQ, DVV)                                                                          \
   if (DQK == DQ && DV == DVV)                                                                         \

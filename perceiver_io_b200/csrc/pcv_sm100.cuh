@@ -112,6 +112,12 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_smem_addr, uint3
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// same without release semantics: a bare arrive (the release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR +
+// CGAERRBAR in front of the arrive); for hand-offs whose payload is not in memory (TMEM written by tcgen05.st and
+// completed with tcgen05.wait::st, or registers)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared address: "same offset in the pair's leader"
 
 // ---- TMA ------------------------------------------------------------------------------------

@@ -370,3 +370,21 @@ def test_rotated_key_cache_matches_rerotation_incl_sliding_window():
     k = o.kv_cache[0][0]
     root = k._base if k._base is not None else k
     assert getattr(root, "_pcv_kv_arena").rot is not None
+
+
+def test_cuda_graph_replay_of_the_latent_stack_equals_eager():
+    """perceiver_io_b200.graphs: a 6-layer SelfAttentionBlock (bf16, fused QKV projection + attention + o_proj + MLP)
+    recorded once and replayed must give bit-identical outputs to the eager forward, for new inputs as well."""
+    import perceiver_io_b200 as P
+    from perceiver_io_b200.graphs import graph_latent_block
+
+    torch.manual_seed(0)
+    block = P.SelfAttentionBlock(num_layers=6, num_heads=8, num_channels=512, widening_factor=2).cuda().bfloat16().eval()
+    x0 = torch.randn(4, 256, 512, device="cuda").bfloat16()
+    fast = graph_latent_block(block, x0)
+    for seed in (1, 2):
+        x = torch.randn(4, 256, 512, device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed)).bfloat16()
+        with torch.no_grad():
+            ref = block(x).last_hidden_state
+        out = fast(x)
+        assert torch.equal(out, ref), (out.float() - ref.float()).abs().max().item()

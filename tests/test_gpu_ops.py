@@ -346,3 +346,24 @@ def test_decode_kernel_matches_oracle(shape, dtype):
     part2 = ops.attention_partial(q, k[:, M // 2:], v[:, M // 2:], H, scale, pad_mask=pad.cuda()[:, M // 2:], m_total=M, m_offset=M // 2)
     merged = ops.combine_partials(torch.stack([part[0], part2[0]]), torch.stack([part[1], part2[1]]), torch.stack([part[2], part2[2]]), dtype)
     assert_parity(merged, q, k, v, H, scale, pad, False, what=f"decode {shape} two key shards merged")
+
+
+@pytest.mark.parametrize("shape", [(2, 300, 700, 2, 128, 128), (1, 512, 2048, 4, 64, 128), (3, 400, 900, 2, 96, 96),
+                                   (2, 1024, 4096, 2, 128, 128)], ids=lambda s: "x".join(map(str, s)))
+def test_cta_pair_kernel_matches_oracle(shape):
+    """cta_group::2 kernel (two SMs per 256-row MMA, relaxed cross-CTA hand-offs, in-kernel fix-up of split units),
+    incl. padding + causal masks, ragged N / M, batch-1 queries and the partial-state output."""
+    from perceiver_io_b200 import ops
+
+    B, N, M, H, dqk, dv = shape
+    q, k, v = _qkv(B, N, M, H, dqk, dv, Bq=1 if B == 3 else None, seed=17, q_gain=2.0)
+    pad = torch.zeros(B, M, dtype=torch.bool)
+    pad[0, : M // 5] = True
+    if B > 2:
+        pad[2, :] = True
+    for causal in (False, True):
+        out = ops.attention(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), causal=causal, impl="tcgen05_pair")
+        assert_parity(out, q, k, v, H, dqk ** -0.5, pad, causal, what=f"pair {shape} causal={causal}")
+    part = ops.attention_partial(q, k, v, H, dqk ** -0.5, pad_mask=pad.cuda(), impl="tcgen05_pair")
+    merged = ops.combine_partials(part[0][None], part[1][None], part[2][None])
+    assert_parity(merged, q, k, v, H, dqk ** -0.5, pad, False, what=f"pair {shape} partial state")
