@@ -2365,6 +2365,12 @@ int launch_attn_tc(const pcv_attn_params& a, cudaStream_t stream, const pcv_shar
     static std::atomic<unsigned long long> launch_seq{0};
     p.fixup_tag = 0x5043560000000000ull ^ (launch_seq.fetch_add(1, std::memory_order_relaxed) + 1);
   }
+  if (pl->num_units > 0 && !mode.big) {
+    // The per-launch tag alone is not enough once a launch is REPLAYED from a CUDA graph (the recorded tag repeats and
+    // the flags of the previous replay would satisfy this one): clear the flags in stream order (a memset node under
+    // capture).  num_slots * 128 bytes.
+    PCV_CHECK_CUDA(cudaMemsetAsync(p.slot_flags, 0, sizeof(unsigned long long) * (size_t)pl->num_slots * kFlagsPerSlot, stream));
+  }
   if (a.pad_mask != nullptr) {
     size_t off = (slots_bytes(*pl, slot_dv, mode.slot_rows) + 255) / 256 * 256;
     uint32_t* bits = reinterpret_cast<uint32_t*>(ws + off);

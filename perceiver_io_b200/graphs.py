@@ -60,5 +60,16 @@ class GraphedForward:
 
 
 def graph_latent_block(block, example_latents: torch.Tensor, **kwargs) -> Callable[[torch.Tensor], torch.Tensor]:
-    """Capture ``block(x, **kwargs).last_hidden_state`` for a SelfAttentionBlock on a fixed latent shape."""
-    return GraphedForward(lambda x: block(x, **kwargs).last_hidden_state, example_latents)
+    """Capture ``block(x, **kwargs).last_hidden_state`` for a SelfAttentionBlock on a fixed latent shape.
+
+    While recording, the row threshold of the self-attention projections is lowered so that the LayerNorm-folded
+    one-GEMM QKV projection and the tcgen05 o_proj are what gets captured (4 kernels per layer instead of 7): inside a
+    graph there is no host-side dispatch cost to trade against."""
+    from . import modules
+
+    old = modules.kv_producer_config["min_rows_latent"]
+    modules.kv_producer_config["min_rows_latent"] = modules.kv_producer_config["min_rows"]
+    try:
+        return GraphedForward(lambda x: block(x, **kwargs).last_hidden_state, example_latents)
+    finally:
+        modules.kv_producer_config["min_rows_latent"] = old

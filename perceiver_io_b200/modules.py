@@ -109,7 +109,7 @@ class MultiHeadAttention(nn.Module):
 
 
 def attend(mha, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_mask=None, rot_pos_emb_q=None,
-           rot_pos_emb_k=None, kv_cache: Optional[KVCache] = None):
+           rot_pos_emb_k=None, kv_cache: Optional[KVCache] = None, min_rows_key: str = "min_rows"):
     """Everything of ``MultiHeadAttention.forward`` after the q/k/v projections (reference modules.py:117-170):
     cache append, rotary, fused attention, ``o_proj``.  ``mha`` is this package's module or a patched reference
     one (only its attributes are used)."""
@@ -137,13 +137,17 @@ def attend(mha, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_mask=None
 
     o = ops.attention(q, k_att, v, mha.num_heads, mha.dp_scale, pad_mask=pad_mask,
                       causal=mha.causal_attention, impl=getattr(mha, "kernel_impl", "auto"))
-    o = fused_linear(mha, "_pcv_o_fold", None, mha.o_proj, o)
+    o = fused_linear(mha, "_pcv_o_fold", None, mha.o_proj, o, min_rows_key)
     return ModuleOutput(last_hidden_state=o, kv_cache=kv_cache)
 
 
 #: Policy of the fused K/V producer (LayerNorm + k_proj + v_proj as one tcgen05 GEMM, ``ops.kv_project``).
 #: ``min_rows``: below this many key rows the two library GEMMs are used (launch-bound either way).
-kv_producer_config = {"enabled": True, "min_rows": 512}
+#: ``min_rows_latent``: threshold of the SELF-attention projections (QKV and o_proj).  In eager mode a small latent array
+#: (B*N of a few thousand rows) is bound by host-side dispatch, where ATen's nn.Linear path is leaner than three ctypes
+#: calls; under a CUDA graph (``graphs.graph_latent_block`` lowers the threshold while recording) the fused path wins
+#: because it launches 4 kernels per layer instead of 7 (tools/latent_stack_bench.py).
+kv_producer_config = {"enabled": True, "min_rows": 512, "min_rows_latent": 4096}
 
 
 def _fold_cache(owner: nn.Module, slot: str, norm: Optional[nn.Module], linears, dtype: torch.dtype):
@@ -164,12 +168,12 @@ def _fold_cache(owner: nn.Module, slot: str, norm: Optional[nn.Module], linears,
     return w_cat, col_st
 
 
-def _fusable(x: torch.Tensor, linears, norm) -> bool:
+def _fusable(x: torch.Tensor, linears, norm, min_rows_key: str = "min_rows") -> bool:
     """Inference on bf16/fp16 CUDA rows with parameters in the same dtype: the case the tcgen05 projection kernel
     (ops.kv_project) covers; autograd, autocast, fp32 and tiny inputs stay on LayerNorm + nn.Linear (library GEMMs)."""
     if not kv_producer_config["enabled"] or not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16):
         return False
-    if x.numel() // max(x.shape[-1], 1) < kv_producer_config["min_rows"] or torch.is_autocast_enabled():
+    if x.numel() // max(x.shape[-1], 1) < kv_producer_config[min_rows_key] or torch.is_autocast_enabled():
         return False
     if norm is not None and not (isinstance(norm, nn.LayerNorm) and len(norm.normalized_shape) == 1
                                  and norm.normalized_shape[0] == x.shape[-1]):
@@ -182,11 +186,12 @@ def _fusable(x: torch.Tensor, linears, norm) -> bool:
     return True
 
 
-def fused_linear(owner: nn.Module, slot: str, norm: Optional[nn.Module], linear: nn.Linear, x: torch.Tensor):
+def fused_linear(owner: nn.Module, slot: str, norm: Optional[nn.Module], linear: nn.Linear, x: torch.Tensor,
+                 min_rows_key: str = "min_rows"):
     """``linear(norm(x))`` (``norm`` may be None) through the tcgen05 projection kernel when it applies — the q_norm ->
     q_proj chain of CrossAttention (reference modules.py:220, :113) and o_proj (:168) — else the library path."""
     n_out = linear.out_features
-    if not (_fusable(x, [linear], norm) and ops.kv_project_supported(x, n_out, 0)):
+    if not (_fusable(x, [linear], norm, min_rows_key) and ops.kv_project_supported(x, n_out, 0)):
         return linear(x if norm is None else norm(x))
     affine = norm if (norm is not None and norm.weight is not None) else None
     w_cat, col_st = _fold_cache(owner, slot, affine, [linear], x.dtype)
@@ -218,7 +223,8 @@ def project_qkv(self_attn, x: torch.Tensor):
     the fused path does not apply (autograd, fp32, autocast, tiny inputs): the caller then runs the library path."""
     attn, norm = self_attn.attention, self_attn.norm
     n_q, n_k, n_v = attn.q_proj.out_features, attn.k_proj.out_features, attn.v_proj.out_features
-    if not (_fusable(x, [attn.q_proj, attn.k_proj, attn.v_proj], norm) and ops.kv_project_supported(x, n_q, n_k + n_v)):
+    if not (_fusable(x, [attn.q_proj, attn.k_proj, attn.v_proj], norm, "min_rows_latent")
+            and ops.kv_project_supported(x, n_q, n_k + n_v)):
         return None
     w_cat, col_st = _fold_cache(self_attn, "_pcv_qkv_fold", norm if norm.weight is not None else None,
                                 [attn.q_proj, attn.k_proj, attn.v_proj], x.dtype)
@@ -319,7 +325,8 @@ class SelfAttention(nn.Module):
     ):
         qkv = project_qkv(self, x)
         if qkv is not None:
-            return attend(self.attention, qkv[0], qkv[1], qkv[2], pad_mask, rot_pos_emb, rot_pos_emb, kv_cache)
+            return attend(self.attention, qkv[0], qkv[1], qkv[2], pad_mask, rot_pos_emb, rot_pos_emb, kv_cache,
+                          min_rows_key="min_rows_latent")
         x = self.norm(x)
         return self.attention(x, x, pad_mask=pad_mask, rot_pos_emb_q=rot_pos_emb, rot_pos_emb_k=rot_pos_emb,
                               kv_cache=kv_cache)

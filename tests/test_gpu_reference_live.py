@@ -110,8 +110,14 @@ def test_patch_on_reference_perceiver_encoder():
     with torch.no_grad():
         r64 = copy.deepcopy(enc).double().cuda()(x.double().cuda(), pad_mask=pad.cuda())
         eager = copy.deepcopy(enc).bfloat16().cuda()(x.cuda(), pad_mask=pad.cuda())
+        from perceiver_io_b200 import modules
+
         mine = _patched_bf16(enc)
-        ours = mine(x.cuda(), pad_mask=pad.cuda())
+        modules.kv_producer_config["min_rows_latent"] = 512   # exercise the one-GEMM QKV projection on the 640 latent rows
+        try:
+            ours = mine(x.cuda(), pad_mask=pad.cuda())
+        finally:
+            modules.kv_producer_config["min_rows_latent"] = 4096
     folded = [k for m in mine.modules() for k in m.__dict__ if k.startswith("_pcv_") and k.endswith("_fold")]
     assert "_pcv_qkv_fold" in folded and "_pcv_kv_fold" in folded and "_pcv_o_fold" in folded, folded
     _gate(ours, r64, eager, "reference PerceiverEncoder, patched (2 cross-attention + 4 self-attention layers)")

@@ -38,9 +38,11 @@ with torch.no_grad():
     modules.kv_producer_config["enabled"] = False
     res["library_projections_ms"] = round(timed(lambda: block(x)), 4)
     modules.kv_producer_config["enabled"] = True
+    modules.kv_producer_config["min_rows_latent"] = 512
     l0 = _lib.launch_count()
     res["fused_projections_ms"] = round(timed(lambda: block(x)), 4)
     res["library_kernels_per_forward"] = (_lib.launch_count() - l0) // 23
+modules.kv_producer_config["min_rows_latent"] = 4096
 fast = graph_latent_block(block, x)
 res["cuda_graph_ms"] = round(timed(lambda: fast(x)), 4)
 print(json.dumps(res))
