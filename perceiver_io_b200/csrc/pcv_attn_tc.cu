@@ -52,10 +52,11 @@ constexpr float kRescaleThreshold = 8.f;  // log2 units
 #endif
 constexpr bool kPairByDefault = PCV_PAIR_DEFAULT != 0;  // build-time choice after the A/B measurement
 constexpr int kFlagsPerSlot = 16;          // fix-up flags per slot: one per 32-row warp slice of a unit (<= 512 rows)
-// compile-time experiment knob: column pairs (of every 4) of an optimistic tile whose 2^x runs on the FMA pipes
-// (exp2_poly2) instead of MUFU.  0 in the product (measured slower at 1 of 4).
+// Column pairs (of every 8) of an optimistic tile whose 2^x runs on the FMA / ALU pipes (exp2_poly2_fast: cubic, relative
+// error 1e-4, far below the bf16 rounding of P) instead of the MUFU pipe, which is co-critical with the tensor pipe in
+// this kernel.  Same-box A/B at the north-star shape: 0/8 1234, 2/8 1273, 4/8 1225 TFLOP/s.
 #ifndef PCV_POLY_QUARTERS
-#define PCV_POLY_QUARTERS 0
+#define PCV_POLY_QUARTERS 2
 #endif
 constexpr int kPolyQuarter = PCV_POLY_QUARTERS;
 
@@ -366,8 +367,8 @@ __device__ __forceinline__ bool softmax_tile_optimistic(const TcParams& p, Barri
     _Pragma("unroll") for (int i = 0; i < 32; i += 2) {                                           \
       const float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);                \
       const float2 x = fma2(make_float2(s0, s1), mul2, negm2);                                    \
-      /* POLY4 of every 4 column pairs go through the FMA-pipe exp2 (compile-time pattern) */     \
-      const float2 e = (((i >> 1) & 3) < POLY4) ? exp2_poly2(x) : make_float2(ex2(x.x), ex2(x.y)); \
+      /* POLY4 of every 8 column pairs go through the FMA-pipe exp2 (compile-time pattern) */     \
+      const float2 e = (((i >> 1) & 7) < POLY4) ? exp2_poly2_fast(x) : make_float2(ex2(x.x), ex2(x.y)); \
       sum2 = add2(sum2, e);                                                                       \
       dst[(off) + (i >> 1)] = pack2(e.x, e.y, BF16);                                              \
     }                                                                                             \

@@ -383,6 +383,24 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return r;
 }
 
+// Leaner variant for the optimistic softmax tile (experiment knob PCV_POLY_QUARTERS): only the lower clamp (an
+// overflowing exponent yields inf, which fails the caller's row-sum range check and sends the tile to the classic
+// path), cubic fit with relative error 1.0e-4, exponent inserted with one shift-add per element.
+__device__ __forceinline__ float2 exp2_poly2_fast(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 xr = add2(x, magic);
+  const float2 xf = sub2(x, sub2(xr, magic));
+  float2 pf = fma2(xf, make_float2(0.05592204f, 0.05592204f), make_float2(0.24264008f, 0.24264008f));
+  pf = fma2(pf, xf, make_float2(0.69312103f, 0.69312103f));
+  pf = fma2(pf, xf, make_float2(0.99992448f, 0.99992448f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pf.x) + (__float_as_int(xr.x) << 23));
+  r.y = __int_as_float(__float_as_int(pf.y) + (__float_as_int(xr.y) << 23));
+  return r;
+}
+
 // plain 2-input max the compiler cannot re-fuse into FMNMX3
 __device__ __forceinline__ float max2(float a, float b) {
   float d;
