@@ -289,11 +289,10 @@ size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 template <typename T, int LPK>
 int launch_nq(const DecParams& p, cudaStream_t stream) {
   dim3 grid((unsigned)((int64_t)p.nsplit * p.a.B * p.a.H));
-  switch (p.a.N) {
-    case 1: attn_decode_kernel<T, LPK, 1><<<grid, kDecThreads, 0, stream>>>(p); break;
-    case 2: attn_decode_kernel<T, LPK, 2><<<grid, kDecThreads, 0, stream>>>(p); break;
-    default: attn_decode_kernel<T, LPK, 4><<<grid, kDecThreads, 0, stream>>>(p); break;
-  }
+  if (p.a.N == 1)
+    attn_decode_kernel<T, LPK, 1><<<grid, kDecThreads, 0, stream>>>(p);
+  else  // 2-4 query rows share the four-row instantiation (rows beyond N are zero queries whose results are dropped)
+    attn_decode_kernel<T, LPK, 4><<<grid, kDecThreads, 0, stream>>>(p);
   PCV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return PCV_OK;
@@ -301,9 +300,9 @@ int launch_nq(const DecParams& p, cudaStream_t stream) {
 
 template <typename T>
 int launch_lpk(const DecParams& p, int lpk, cudaStream_t stream) {
-  switch (lpk) {
-    case 1: return launch_nq<T, 1>(p, stream);
-    case 2: return launch_nq<T, 2>(p, stream);
+  switch (lpk) {  // rows of up to 32 channels use the 4-lane instantiation with idle lanes
+    case 1:
+    case 2:
     case 4: return launch_nq<T, 4>(p, stream);
     case 8: return launch_nq<T, 8>(p, stream);
     case 16: return launch_nq<T, 16>(p, stream);
@@ -340,7 +339,7 @@ bool attn_decode_supported(const pcv_attn_params& a, const char** why) {
 int attn_decode_workspace_bytes(const pcv_attn_params& a, size_t* bytes) {
   int nsplit = 1, kps = a.M;
   choose_split(a, &nsplit, &kps);
-  const int nq = a.N <= 1 ? 1 : (a.N <= 2 ? 2 : 4);
+  const int nq = a.N <= 1 ? 1 : 4;
   const size_t rows = (size_t)a.B * a.H * nsplit * nq;
   *bytes = align256(rows * a.dv * 4) + 2 * align256(rows * 4) + align256((size_t)a.B * a.H * 4);
   return PCV_OK;
@@ -354,7 +353,7 @@ int launch_attn_decode(const pcv_attn_params& a, cudaStream_t stream) {
   DecParams p{};
   p.a = a;
   choose_split(a, &p.nsplit, &p.keys_per_split);
-  const int nq = a.N <= 1 ? 1 : (a.N <= 2 ? 2 : 4);
+  const int nq = a.N <= 1 ? 1 : 4;
   const size_t rows = (size_t)a.B * a.H * p.nsplit * nq;
   char* ws = reinterpret_cast<char*>(a.workspace);
   p.ws_o = reinterpret_cast<float*>(ws);

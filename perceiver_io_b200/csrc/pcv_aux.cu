@@ -93,9 +93,10 @@ __global__ void __launch_bounds__(256) combine_peers_kernel(const pcv_peer_combi
 #pragma unroll
     for (int g = 0; g < PCV_MAX_PEERS; ++g) {
       if (g < G) {
-        mg[g] = __ldg(p.part_m[g] + r);
-        lg[g] = __ldg(p.part_l[g] + r);
-        x[g] = active ? __ldg(reinterpret_cast<const float4*>(p.part_o[g] + r * p.dv + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // L2-only loads (no read-only / L1 path): the rows were written by OTHER GPUs into peer-mapped memory
+        mg[g] = __ldcg(p.part_m[g] + r);
+        lg[g] = __ldcg(p.part_l[g] + r);
+        x[g] = active ? __ldcg(reinterpret_cast<const float4*>(p.part_o[g] + r * p.dv + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
         mg[g] = -INFINITY;
         lg[g] = 0.f;

@@ -629,12 +629,15 @@ def rotated_cache_keys(k: torch.Tensor, q: torch.Tensor, num_heads: int, inv_fre
     arena, start = hit
     root = k._base if k._base is not None else k
     L, N = k.shape[1], q.shape[1]
-    inv_freq = inv_freq.to(device=k.device, dtype=torch.float32)
-    key = (inv_freq.data_ptr(), int(inv_freq.numel()), num_heads)
+    # identity of the frequency table as the caller holds it (a bf16 model's buffer is converted below: the converted
+    # copy is kept with the shadow, otherwise every step would see a "new" table and re-rotate the whole cache)
+    key = (inv_freq.data_ptr(), inv_freq.dtype, int(inv_freq.numel()), num_heads, inv_freq._version)
     rot = arena.rot
     if rot is None or rot["key"] != key:
-        rot = {"buf": torch.empty_like(root), "lo": 0, "hi": 0, "key": key}
+        rot = {"buf": torch.empty_like(root), "lo": 0, "hi": 0, "key": key,
+               "inv_freq": inv_freq.detach().to(device=k.device, dtype=torch.float32)}
         arena.rot = rot
+    inv_freq = rot["inv_freq"]
     end = start + L
     if not (rot["lo"] <= start <= rot["hi"]):   # nothing reusable: rotate the whole range once
         rot["lo"], rot["hi"] = start, start
