@@ -202,6 +202,10 @@ def sharded_attention(q: torch.Tensor, k_shard: torch.Tensor, v_shard: torch.Ten
     merge_requested = merge
     if merge == "auto":
         merge = "fused" if (kernels is None and not PeerMerger.disabled and _peer_merge_possible(k_shard, world_now)) else "nccl"
+        if merge == "fused" and q.shape[1] <= 4:
+            # decode step (a handful of query rows against a sharded cache): the streaming decode kernel produces the
+            # partial state, the 33 KB-per-rank merge goes through the peer kernel
+            merge = "peer"
     if merge in ("peer", "fused") and world_now > 1:
         from . import ops
 

@@ -52,6 +52,20 @@ for (B, N, M, H, d, causal) in [(2, 200, 5000, 4, 64, False), (2, 512, 16384, 8,
     if rank == 0:
         print(f"shape {(B, N, M, H, d, causal)}: sharded vs single max err {err:.3e} (bound {bound:.3e}), identical on all ranks: {same}")
     ok = ok and err <= bound and same
+# decode step against a sharded cache: one query row, partial states from the streaming decode kernel
+for (B, N, M, H, d) in [(4, 1, 16384, 8, 128), (2, 2, 8192, 4, 64)]:
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(B, N, H * d, generator=g).bfloat16().to(dev)
+    k = torch.randn(B, M, H * d, generator=g).bfloat16().to(dev)
+    v = torch.randn(B, M, H * d, generator=g).bfloat16().to(dev)
+    m0, m1 = shard_bounds(M, world, rank)
+    out = sharded_attention(q, k[:, m0:m1], v[:, m0:m1], H, d ** -0.5, M, m0, causal=True)   # auto -> peer for N <= 4
+    ref = ops.attention(q, k, v, H, d ** -0.5, causal=True)
+    err = (out.float() - ref.float()).abs().max().item()
+    bound = 1e-2 * ref.float().abs().max().item()
+    if rank == 0:
+        print(f"sharded decode step {(B, N, M, H, d)}: max err {err:.3e} (bound {bound:.3e})")
+    ok = ok and err <= bound
 # module-level entry point
 torch.manual_seed(0)
 layer = P.CrossAttention(8, 256, 256).to(dev).bfloat16().eval()
