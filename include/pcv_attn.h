@@ -300,6 +300,47 @@ typedef struct pcv_shard_fuse {
   int32_t reserved;
 } pcv_shard_fuse;
 
+/*
+ * Backward of the attention core (autograd through modules.py:141-167): from the forward's operands, its output and
+ * its saved row statistics (part_m / part_l of a write_partial forward over ALL keys, log2 domain) compute
+ *   grad_q = scale * dS K,  grad_k = scale * dS^T Q,  grad_v = P^T grad_out,   dS = P * (grad_out V^T - rowsum(grad_out*out))
+ * with the masks of the forward (finite fill: a filled score carries no gradient).  Tensors are laid out as in
+ * pcv_attn_params ((B, rows, H, d) by strides, in `dtype`); q_stride_b == 0 broadcasts one latent array over the batch and
+ * grad_q is then the SUM over the batch, shape (1, N, H*dqk).  Two tcgen05 kernels (dK/dV: key-tile outer; dQ: query-tile
+ * outer) — no (B, H, N, M) tensor is ever materialised.  Head dims: multiples of 8, at most 128.
+ */
+typedef struct pcv_attn_bwd_params {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* out;        /* forward output (B, N, H, dv)                               */
+  const void* grad_out;   /* gradient of the loss w.r.t. out, same shape                */
+  const float* stat_m;    /* (B, H, N) row maxima of the forward (log2 domain)          */
+  const float* stat_l;    /* (B, H, N) softmax denominators relative to stat_m          */
+  void* grad_q;           /* (B or 1, N, H, dqk)                                        */
+  void* grad_k;           /* (B, M, H, dqk)                                             */
+  void* grad_v;           /* (B, M, H, dv)                                              */
+  int64_t q_stride_b, q_stride_n, q_stride_h;
+  int64_t k_stride_b, k_stride_m, k_stride_h;
+  int64_t v_stride_b, v_stride_m, v_stride_h;
+  int64_t o_stride_b, o_stride_n, o_stride_h;
+  int64_t go_stride_b, go_stride_n, go_stride_h;
+  int64_t gq_stride_b, gq_stride_n, gq_stride_h;
+  int64_t gk_stride_b, gk_stride_m, gk_stride_h;
+  int64_t gv_stride_b, gv_stride_m, gv_stride_h;
+  int32_t B, H, N, M;
+  int32_t dqk, dv;
+  float scale;
+  int32_t dtype;           /* enum pcv_dtype (bf16 / fp16)                              */
+  int32_t causal;          /* right-aligned causal mask as in the forward               */
+  float dropout_p;         /* attention-probability dropout of the forward (0 = none)   */
+  uint64_t dropout_seed;
+  const uint8_t* pad_mask; /* (B, M) bytes, non-zero = padding key; NULL = none         */
+  int64_t pad_stride_b;
+  void* workspace;         /* >= pcv_attn_bwd_workspace_bytes(), 256-byte aligned       */
+  size_t workspace_bytes;
+} pcv_attn_bwd_params;
+
 /* library / device introspection */
 typedef struct pcv_device_info {
   int32_t device;
@@ -330,6 +371,10 @@ PCV_API int pcv_kv_append(const pcv_kv_append_params* p, void* stream);
 PCV_API int pcv_kv_project_supported(const pcv_kvproj_params* p);
 PCV_API int pcv_ln_stats(const pcv_ln_stats_params* p, void* stream);
 PCV_API int pcv_kv_project(const pcv_kvproj_params* p, void* stream);
+/* 1 if the tcgen05 backward kernels cover this problem, else 0 (reason via pcv_last_error) */
+PCV_API int pcv_attn_bwd_supported(const pcv_attn_bwd_params* p);
+PCV_API int pcv_attn_bwd_workspace_bytes(const pcv_attn_bwd_params* p, size_t* bytes);
+PCV_API int pcv_attn_bwd(const pcv_attn_bwd_params* p, void* stream);
 
 /*
  * Live timing of the dominant kernel (bench.py's roofline leg): between pcv_profile_begin() and

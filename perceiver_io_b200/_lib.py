@@ -38,6 +38,9 @@ EXPORTS = (
     "pcv_kv_project_supported",
     "pcv_ln_stats",
     "pcv_kv_project",
+    "pcv_attn_bwd_supported",
+    "pcv_attn_bwd_workspace_bytes",
+    "pcv_attn_bwd",
     "pcv_launch_count",
     "pcv_debug_plan",
     "pcv_profile_begin",
@@ -166,6 +169,28 @@ class LnStatsParams(C.Structure):
     ]
 
 
+class AttnBwdParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("grad_out", C.c_void_p),
+        ("stat_m", C.c_void_p), ("stat_l", C.c_void_p),
+        ("grad_q", C.c_void_p), ("grad_k", C.c_void_p), ("grad_v", C.c_void_p),
+        ("q_stride_b", C.c_int64), ("q_stride_n", C.c_int64), ("q_stride_h", C.c_int64),
+        ("k_stride_b", C.c_int64), ("k_stride_m", C.c_int64), ("k_stride_h", C.c_int64),
+        ("v_stride_b", C.c_int64), ("v_stride_m", C.c_int64), ("v_stride_h", C.c_int64),
+        ("o_stride_b", C.c_int64), ("o_stride_n", C.c_int64), ("o_stride_h", C.c_int64),
+        ("go_stride_b", C.c_int64), ("go_stride_n", C.c_int64), ("go_stride_h", C.c_int64),
+        ("gq_stride_b", C.c_int64), ("gq_stride_n", C.c_int64), ("gq_stride_h", C.c_int64),
+        ("gk_stride_b", C.c_int64), ("gk_stride_m", C.c_int64), ("gk_stride_h", C.c_int64),
+        ("gv_stride_b", C.c_int64), ("gv_stride_m", C.c_int64), ("gv_stride_h", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("M", C.c_int32),
+        ("dqk", C.c_int32), ("dv", C.c_int32),
+        ("scale", C.c_float), ("dtype", C.c_int32), ("causal", C.c_int32), ("dropout_p", C.c_float),
+        ("dropout_seed", C.c_uint64),
+        ("pad_mask", C.c_void_p), ("pad_stride_b", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("sm_major", C.c_int32), ("sm_minor", C.c_int32),
@@ -223,6 +248,12 @@ def lib() -> C.CDLL:
         l.pcv_ln_stats.restype = C.c_int
         l.pcv_kv_project.argtypes = [C.POINTER(KvProjParams), C.c_void_p]
         l.pcv_kv_project.restype = C.c_int
+        l.pcv_attn_bwd_supported.argtypes = [C.POINTER(AttnBwdParams)]
+        l.pcv_attn_bwd_supported.restype = C.c_int
+        l.pcv_attn_bwd_workspace_bytes.argtypes = [C.POINTER(AttnBwdParams), C.POINTER(C.c_size_t)]
+        l.pcv_attn_bwd_workspace_bytes.restype = C.c_int
+        l.pcv_attn_bwd.argtypes = [C.POINTER(AttnBwdParams), C.c_void_p]
+        l.pcv_attn_bwd.restype = C.c_int
         l.pcv_debug_plan.argtypes = [C.c_int32] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
         l.pcv_debug_plan.restype = C.c_int
         for name in ("pcv_get_device_info", "pcv_attn_supported_tcgen05", "pcv_attn_workspace_bytes",

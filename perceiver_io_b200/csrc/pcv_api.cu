@@ -256,4 +256,22 @@ int pcv_kv_project(const pcv_kvproj_params* p, void* stream) {
   return launch_kv_project(*p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int pcv_attn_bwd_supported(const pcv_attn_bwd_params* p) {
+  if (p == nullptr) return 0;
+  const char* why = "";
+  const bool ok = attn_bwd_supported(*p, &why);
+  if (!ok) set_error("attn_bwd not applicable: %s", why);
+  return ok ? 1 : 0;
+}
+
+int pcv_attn_bwd_workspace_bytes(const pcv_attn_bwd_params* p, size_t* bytes) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "attn_bwd_workspace_bytes: params is NULL");
+  return attn_bwd_workspace_bytes(*p, bytes);
+}
+
+int pcv_attn_bwd(const pcv_attn_bwd_params* p, void* stream) {
+  PCV_REQUIRE(p != nullptr, PCV_ERR_INVALID, "attn_bwd: params is NULL");
+  return launch_attn_bwd(*p, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

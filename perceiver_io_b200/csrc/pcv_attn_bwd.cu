@@ -1,0 +1,995 @@
+// pcv_attn_bwd.cu — backward of the fused attention core on the 5th-generation tensor cores.
+//
+// Reference: autograd through perceiver/model/core/modules.py:141-167 (einsum scores, masked_fill_ with the finite
+// fill, softmax, dropout, einsum with V).  With P = softmax(scale * Q K^T + fill), O = P V and the saved row statistics
+// (m, l) of the forward kernel (log2 domain: P = 2^(t - m) / l, t = scale*log2(e) * q.k):
+//     delta_q = sum_c dO[q,c] O[q,c]            dP = dO V^T            dS = P * (dP - delta)   (0 where filled)
+//     dV = P^T dO            dK = scale * dS^T Q            dQ = scale * dS K
+// The shape of the path is asymmetric (N = a few hundred latent queries, M >> N keys), so the work is split into two
+// kernels that never hold the (B, H, N, M) score tensor and need no atomics on the large axis:
+//
+//   bwd_dkdv_kernel  key-tile outer, persistent.  One CTA owns a 128-key tile (K, V resident in shared memory) and walks
+//                    the query tiles.  Scores are computed TRANSPOSED, S^T = K Q^T and dP^T = V dO^T (TMEM lanes =
+//                    keys), so P^T and dS^T, rounded to bf16/fp16, go back into TMEM and feed dV += P^T dO and
+//                    dK += dS^T Q as the A operand straight from TMEM (B = dO / Q tile read MN-major): P and dS never
+//                    touch shared memory.  dK, dV accumulate in TMEM over the query tiles and are written once.
+//   bwd_dq_kernel    query-tile outer.  One CTA owns (b, h, 128 queries) and a range of key tiles (K, V streamed through
+//                    a TMA ring); S = Q K^T, dP = dO V^T, dS -> TMEM, dQ += dS K (K tile read MN-major, as V is in
+//                    the forward).  dQ accumulates in TMEM over the CTA's key range and is added into an fp32 buffer
+//                    with one vector reduction per element per CTA (a few hundred KB in total).
+//
+// Recomputing S and dP in both kernels costs 7 tile GEMMs per (query tile, key tile) instead of 5; the one-kernel
+// alternative has to reduce a 128 x d fp32 dQ tile into global memory for EVERY (query tile, key tile) pair
+// (8.6 GB of reductions at the north-star shape, ~1.3 cycles per lane each), which is slower than the two extra
+// GEMMs.  Both kernels are warp specialised like the forward: warps 0-7 softmax/epilogue (thread = TMEM lane,
+// two warps per lane quarter splitting the 128 columns), warp 8 TMA producer, warp 9 MMA issuer.
+#include "pcv_common.cuh"
+#include "pcv_sm100.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <mutex>
+
+namespace pcv {
+namespace {
+
+using namespace sm100;
+
+constexpr int kT = 128;                 // tile rows (queries or keys) = TMEM lanes
+constexpr int kBoxBytes = kT * 128;     // one TMA box: 128 rows x 64 16-bit channels, SWIZZLE_128B
+constexpr int kThreads = 384;
+constexpr int kTmaWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kStatsBytes = kT * 16;    // float4 {m, 1/l, delta, 0} per query of a tile
+
+struct BwdParams {
+  int B, H, N, M, dqk, dv;
+  int Npad, nq, nk;          // query rows padded to tiles, query tiles, key tiles
+  int q_bcast;               // q has one batch row shared by all b (latents)
+  float scale, scale_log2;
+  int causal, cshift;        // key masked for query n iff key > n + cshift   (cshift = M - N: right aligned)
+  const uint32_t* pad_bits;  // (B, pad_wpr) bit set = padding key; nullptr if none
+  int pad_wpr;
+  const float4* stats;       // (B, H, Npad)
+  float* dq32;               // (Bq, N, H*dqk) fp32, zero-initialised; CTAs reduce into it
+  void* dk;
+  void* dv_out;
+  int64_t dk_sb, dk_sm, dk_sh, dv_sb, dv_sm, dv_sh;
+  int total_tiles;           // dkdv kernel: B*H*nk
+  int splits, tiles_per_split;  // dq kernel
+};
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, bool bf16) {
+  uint32_t r;
+  if (bf16)
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// one arrive per warp on a barrier initialised with count 8 (the eight softmax warps)
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prep: stats[b,h,n] = {m, 1/l, delta = sum_c dO*O, 0}; rows n >= N of the last tile are zero (their P is 0)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ out, const T* __restrict__ dout,
+                                                       const float* __restrict__ stat_m,
+                                                       const float* __restrict__ stat_l, float4* __restrict__ stats,
+                                                       int B, int H, int N, int Npad, int dv, int64_t o_sb,
+                                                       int64_t o_sn, int64_t o_sh, int64_t g_sb, int64_t g_sn,
+                                                       int64_t g_sh) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (int64_t)B * H * Npad) return;
+  const int n = (int)(row % Npad);
+  const int64_t bh = row / Npad;
+  const int h = (int)(bh % H), b = (int)(bh / H);
+  float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+    const T* o = out + b * o_sb + (int64_t)n * o_sn + h * o_sh;
+    const T* g = dout + b * g_sb + (int64_t)n * g_sn + h * g_sh;
+    float acc = 0.f;
+    for (int c = lane; c < dv; c += 32) acc += Elem<T>::to_f(o[c]) * Elem<T>::to_f(g[c]);
+    acc = warp_sum(acc);
+    const int64_t r = bh * N + n;
+    st.x = stat_m[r];
+    st.y = 1.f / stat_l[r];
+    st.z = acc;
+  }
+  if (lane == 0) stats[row] = st;
+}
+
+// pad_mask bytes (B, M) -> bit words (B, wpr), wpr = 4 * ceil(M/128); bit set = padding key
+__global__ void __launch_bounds__(256) bwd_pack_pad_kernel(const uint8_t* __restrict__ pad, int64_t stride_b, int B,
+                                                           int M, int wpr, uint32_t* __restrict__ bits) {
+  const int64_t total = (int64_t)B * wpr;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / wpr), w = (int)(idx % wpr);
+    uint32_t word = 0;
+    for (int i = 0; i < 32; ++i) {
+      const int j = w * 32 + i;
+      if (j < M && pad[(int64_t)b * stride_b + j] != 0) word |= (1u << i);
+    }
+    bits[idx] = word;
+  }
+}
+
+// dq32 (Bq, N, H*dqk) fp32 -> dq in the operand dtype with its own strides
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_cast_dq_kernel(const float* __restrict__ dq32, T* __restrict__ dq, int Bq,
+                                                          int N, int H, int dqk, int64_t sb, int64_t sn, int64_t sh) {
+  const int64_t total = (int64_t)Bq * N * H * dqk;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % dqk);
+    int64_t r = idx / dqk;
+    const int h = (int)(r % H);
+    r /= H;
+    const int n = (int)(r % N);
+    const int b = (int)(r / N);
+    dq[b * sb + (int64_t)n * sn + h * sh + c] = Elem<T>::from_f(dq32[idx]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel 1: dK, dV
+// ---------------------------------------------------------------------------------------------------------------
+template <int DQK, int DV>
+struct Cfg1 {
+  static constexpr int kQB = DQK / 64, kVB = DV / 64;
+  static constexpr int kKBytes = kQB * kBoxBytes, kVBytes = kVB * kBoxBytes;
+  static constexpr int kStage = kKBytes + kVBytes;  // Q_j then dO_j
+  static constexpr int kOffK = 0;
+  static constexpr int kOffV = kKBytes;
+  static constexpr int kOffStage = kKBytes + kVBytes;
+  static constexpr int kOffStats = kOffStage + 2 * kStage;
+  static constexpr int kOffBar = kOffStats + 2 * kStatsBytes;
+  static constexpr int kNeed = kOffBar + 256 + 1024;
+  static constexpr int kSmem = kNeed > 120 * 1024 ? kNeed : 120 * 1024;  // > half an SM: one CTA (512 TMEM columns) per SM
+  static constexpr uint32_t kColS = 0, kColP = 128, kColDK = 256, kColDV = 256 + DQK;
+};
+
+struct Bars1 {
+  uint64_t kv_full, kv_empty;
+  uint64_t qdo_full[2], qdo_empty[2];
+  uint64_t s_full, dp_full, p_ready, ds_ready;
+  uint64_t acc_full, acc_empty;
+  uint32_t tmem_base;
+};
+
+// thread = key row `r` of the tile (TMEM lane); this warp handles query columns [64*half, 64*half + 64)
+template <int DQK, int DV, bool BF16>
+__device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uint8_t* smem, int warp, int lane) {
+  using C = Cfg1<DQK, DV>;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int r = quarter * 32 + lane;
+  const uint32_t lanef = (uint32_t)(quarter * 32) << 16;
+  const uint32_t tS = bar.tmem_base + lanef + C::kColS + (uint32_t)(half * 64);
+  const uint32_t tP = bar.tmem_base + lanef + C::kColP + (uint32_t)(half * 64);
+  uint32_t n = 0, tile_iter = 0;
+  for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
+    const int kt = id % p.nk, bh = id / p.nk;
+    const int h = bh % p.H, b = bh / p.H;
+    const int key = kt * kT + r;
+    const bool oob = key >= p.M;
+    uint4 mw = make_uint4(0u, 0u, 0u, 0u);
+    if (p.pad_bits != nullptr) mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)b * p.pad_wpr + (size_t)kt * 4);
+    const uint32_t myw = quarter == 0 ? mw.x : (quarter == 1 ? mw.y : (quarter == 2 ? mw.z : mw.w));
+    const bool pad = (myw >> lane) & 1u;
+    const bool tile_masked = ((mw.x | mw.y | mw.z | mw.w) != 0u) || (kt * kT + kT > p.M);
+    for (int j = 0; j < p.nq; ++j) {
+      const uint32_t cur = n + (uint32_t)j, slot = cur & 1u;
+      const float4* st_s = reinterpret_cast<const float4*>(smem + C::kOffStats + slot * kStatsBytes) + half * 64;
+      // leading columns (queries) of this thread's 64 for which the key is causally hidden
+      const int q0 = j * kT + half * 64;
+      int nfill = 0;
+      if (p.causal) nfill = min(max(key - p.cshift - q0, 0), 64);
+      const bool masked = tile_masked || (p.causal && (kt * kT + kT - 1 > j * kT + p.cshift));
+      float pf[64];
+
+      mbar_wait(&bar.qdo_full[slot], (cur >> 1) & 1u, 20);  // the statistics of this query tile are visible
+      mbar_wait(&bar.s_full, cur & 1u, 21);
+      tc_fence_after_sync();
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t s[32];
+          tmem_ld32(tS + ch * 32, s);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 st = st_s[ch * 32 + i];
+            float x = fmaf(__uint_as_float(s[i]), p.scale_log2, -st.x);
+            if (masked) {
+              if (pad || (ch * 32 + i) < nfill) x = kMaskedScore - st.x;  // finite fill: 0, or 1/l on a fully filled row
+              if (oob) x = -INFINITY;
+            }
+            pf[ch * 32 + i] = ex2(x) * st.y;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) pk[ch * 16 + (i >> 1)] = pack2(pf[ch * 32 + i], pf[ch * 32 + i + 1], BF16);
+        }
+        tmem_st32(tS, pk);  // P^T (16-bit) over the first 32 columns of this warp's S^T columns
+        tmem_wait_st();
+      }
+      tc_fence_before_sync();
+      warp_arrive(&bar.p_ready);
+
+      mbar_wait(&bar.dp_full, cur & 1u, 22);
+      tc_fence_after_sync();
+      {
+        uint32_t dk[32];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t d[32];
+          tmem_ld32(tP + ch * 32, d);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float de0 = st_s[ch * 32 + i].z, de1 = st_s[ch * 32 + i + 1].z;
+            float g0 = pf[ch * 32 + i] * (__uint_as_float(d[i]) - de0);
+            float g1 = pf[ch * 32 + i + 1] * (__uint_as_float(d[i + 1]) - de1);
+            if (masked) {  // a filled score is a constant: no gradient through it
+              if (pad || oob || (ch * 32 + i) < nfill) g0 = 0.f;
+              if (pad || oob || (ch * 32 + i + 1) < nfill) g1 = 0.f;
+            }
+            dk[ch * 16 + (i >> 1)] = pack2(g0, g1, BF16);
+          }
+        }
+        tmem_st32(tP, dk);
+        tmem_wait_st();
+      }
+      tc_fence_before_sync();
+      warp_arrive(&bar.ds_ready);
+    }
+    n += (uint32_t)p.nq;
+
+    // ---- drain the accumulators of this key tile: half 0 -> dK (scaled), half 1 -> dV ----
+    mbar_wait(&bar.acc_full, tile_iter & 1u, 23);
+    tc_fence_after_sync();
+    {
+      const int cols = half == 0 ? DQK : DV;
+      const int nreal = half == 0 ? p.dqk : p.dv;
+      const float mult = half == 0 ? p.scale : 1.f;
+      const uint32_t tA = bar.tmem_base + lanef + (half == 0 ? C::kColDK : C::kColDV);
+      uint16_t* dst = half == 0
+                          ? reinterpret_cast<uint16_t*>(p.dk) + b * p.dk_sb + (int64_t)key * p.dk_sm + h * p.dk_sh
+                          : reinterpret_cast<uint16_t*>(p.dv_out) + b * p.dv_sb + (int64_t)key * p.dv_sm + h * p.dv_sh;
+      for (int ch = 0; ch < cols / 32; ++ch) {
+        uint32_t a[32];
+        tmem_ld32(tA + ch * 32, a);
+        tmem_wait_ld();
+        if (!oob) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = ch * 32 + g * 8;
+            if (c < nreal) {
+              uint4 w;
+              w.x = pack2(__uint_as_float(a[g * 8 + 0]) * mult, __uint_as_float(a[g * 8 + 1]) * mult, BF16);
+              w.y = pack2(__uint_as_float(a[g * 8 + 2]) * mult, __uint_as_float(a[g * 8 + 3]) * mult, BF16);
+              w.z = pack2(__uint_as_float(a[g * 8 + 4]) * mult, __uint_as_float(a[g * 8 + 5]) * mult, BF16);
+              w.w = pack2(__uint_as_float(a[g * 8 + 6]) * mult, __uint_as_float(a[g * 8 + 7]) * mult, BF16);
+              *reinterpret_cast<uint4*>(dst + c) = w;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+    warp_arrive(&bar.acc_empty);
+  }
+}
+
+template <int DQK, int DV, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                const BwdParams p) {
+  using C = Cfg1<DQK, DV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars1& bar = *reinterpret_cast<Bars1*>(smem + C::kOffBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar.kv_full, 1);
+    mbar_init(&bar.kv_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar.qdo_full[i], 1);
+      mbar_init(&bar.qdo_empty[i], 1);
+    }
+    mbar_init(&bar.s_full, 1);
+    mbar_init(&bar.dp_full, 1);
+    mbar_init(&bar.p_ready, 8);
+    mbar_init(&bar.ds_ready, 8);
+    mbar_init(&bar.acc_full, 1);
+    mbar_init(&bar.acc_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(&bar.tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  if (warp < 8) {
+    reg_alloc<208>();
+    softmax_dkdv<DQK, DV, BF16>(p, bar, smem, warp, lane);
+  } else {
+    reg_dealloc<88>();
+  }
+
+  if (warp == kTmaWarp) {
+    // ===== TMA producer: K, V of the key tile once; Q_j, dO_j and the row statistics per query tile =====
+    const bool leader = elect_one();
+    uint32_t it = 0, tile_iter = 0;
+    for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
+      const int kt = id % p.nk, bh = id / p.nk;
+      const int h = bh % p.H, b = bh / p.H;
+      mbar_wait(&bar.kv_empty, (tile_iter & 1u) ^ 1u, 1);
+      if (leader) {
+        mbar_arrive_expect_tx(&bar.kv_full, (uint32_t)(C::kKBytes + C::kVBytes));
+#pragma unroll
+        for (int bx = 0; bx < C::kQB; ++bx)
+          tma_load_4d(smem + C::kOffK + bx * kBoxBytes, &tmap_k, &bar.kv_full, bx * 64, kt * kT, h, b);
+#pragma unroll
+        for (int bx = 0; bx < C::kVB; ++bx)
+          tma_load_4d(smem + C::kOffV + bx * kBoxBytes, &tmap_v, &bar.kv_full, bx * 64, kt * kT, h, b);
+      }
+      for (int j = 0; j < p.nq; ++j, ++it) {
+        const uint32_t slot = it & 1u;
+        mbar_wait(&bar.qdo_empty[slot], ((it >> 1) & 1u) ^ 1u, 2);
+        if (leader) {
+          uint8_t* st = smem + C::kOffStage + slot * C::kStage;
+          mbar_arrive_expect_tx(&bar.qdo_full[slot], (uint32_t)(C::kStage + kStatsBytes));
+#pragma unroll
+          for (int bx = 0; bx < C::kQB; ++bx)
+            tma_load_4d(st + bx * kBoxBytes, &tmap_q, &bar.qdo_full[slot], bx * 64, j * kT, h, p.q_bcast ? 0 : b);
+#pragma unroll
+          for (int bx = 0; bx < C::kVB; ++bx)
+            tma_load_4d(st + C::kKBytes + bx * kBoxBytes, &tmap_do, &bar.qdo_full[slot], bx * 64, j * kT, h, b);
+          bulk_load_1d(smem + C::kOffStats + slot * kStatsBytes, p.stats + ((size_t)bh * p.Npad + (size_t)j * kT),
+                       kStatsBytes, &bar.qdo_full[slot]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===== MMA issuer (warp converged, one elected lane issues) =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(kT, kT, BF16, false);
+    constexpr uint32_t idesc_dv = make_idesc(kT, DV, BF16, true);
+    constexpr uint32_t idesc_dk = make_idesc(kT, DQK, BF16, true);
+    const uint32_t tmem = bar.tmem_base;
+    const uint64_t dK = make_smem_desc(smem_u32(smem + C::kOffK), 16, 1024);
+    const uint64_t dV = make_smem_desc(smem_u32(smem + C::kOffV), 16, 1024);
+    auto stage_q = [&](uint32_t slot) { return smem_u32(smem + C::kOffStage + slot * C::kStage); };
+    auto issue_s = [&](uint32_t slot) {  // S^T = K Q_j^T
+      if (leader) {
+        const uint64_t db = make_smem_desc(stage_q(slot), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < DQK / 16; ++kk) {
+          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          mma_ss(tmem + C::kColS, dK + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+        }
+      }
+    };
+    auto issue_dp = [&](uint32_t slot) {  // dP^T = V dO_j^T
+      if (leader) {
+        const uint64_t db = make_smem_desc(stage_q(slot) + C::kKBytes, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < DV / 16; ++kk) {
+          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          mma_ss(tmem + C::kColP, dV + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+        }
+      }
+    };
+    auto issue_dv = [&](uint32_t slot, bool acc) {  // dV += P^T(TMEM) dO_j   (dO_j read MN-major: 16 queries = 2048 bytes)
+      if (leader) {
+        const uint64_t db = make_smem_desc(stage_q(slot) + C::kKBytes, kBoxBytes, 1024);
+#pragma unroll
+        for (int kk = 0; kk < kT / 16; ++kk)
+          mma_ts(tmem + C::kColDV, tmem + C::kColS + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
+                 db + (uint64_t)((kk * 2048) >> 4), idesc_dv, (acc || kk > 0) ? 1u : 0u);
+      }
+    };
+    auto issue_dk = [&](uint32_t slot, bool acc) {  // dK += dS^T(TMEM) Q_j
+      if (leader) {
+        const uint64_t db = make_smem_desc(stage_q(slot), kBoxBytes, 1024);
+#pragma unroll
+        for (int kk = 0; kk < kT / 16; ++kk)
+          mma_ts(tmem + C::kColDK, tmem + C::kColP + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
+                 db + (uint64_t)((kk * 2048) >> 4), idesc_dk, (acc || kk > 0) ? 1u : 0u);
+      }
+    };
+    auto commit = [&](uint64_t* b) {
+      if (leader) tc_commit(b);
+    };
+
+    uint32_t n = 0, tile_iter = 0;
+    for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
+      mbar_wait(&bar.kv_full, tile_iter & 1u, 3);
+      {
+        const uint32_t slot = n & 1u;
+        mbar_wait(&bar.qdo_full[slot], (n >> 1) & 1u, 4);
+        tc_fence_after_sync();
+        issue_s(slot);
+        commit(&bar.s_full);
+        issue_dp(slot);
+        commit(&bar.dp_full);
+        if (p.nq == 1) commit(&bar.kv_empty);
+      }
+      for (int j = 0; j < p.nq; ++j) {
+        const uint32_t cur = n + (uint32_t)j, slot = cur & 1u, nslot = slot ^ 1u;
+        const bool more = j + 1 < p.nq;
+        mbar_wait(&bar.p_ready, cur & 1u, 5);
+        if (j == 0) mbar_wait(&bar.acc_empty, (tile_iter & 1u) ^ 1u, 6);
+        tc_fence_after_sync();
+        issue_dv(slot, j > 0);
+        if (more) {
+          mbar_wait(&bar.qdo_full[nslot], ((cur + 1) >> 1) & 1u, 7);
+          tc_fence_after_sync();
+          issue_s(nslot);
+          commit(&bar.s_full);
+        }
+        mbar_wait(&bar.ds_ready, cur & 1u, 8);
+        tc_fence_after_sync();
+        issue_dk(slot, j > 0);
+        commit(&bar.qdo_empty[slot]);
+        if (more) {
+          issue_dp(nslot);
+          commit(&bar.dp_full);
+          if (j + 2 == p.nq) commit(&bar.kv_empty);  // K and V are not read again for this key tile
+        }
+      }
+      commit(&bar.acc_full);
+      n += (uint32_t)p.nq;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(bar.tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel 2: dQ
+// ---------------------------------------------------------------------------------------------------------------
+template <int DQK, int DV>
+struct Cfg2 {
+  static constexpr int kQB = DQK / 64, kVB = DV / 64;
+  static constexpr int kKBytes = kQB * kBoxBytes, kVBytes = kVB * kBoxBytes;
+  static constexpr int kStage = kKBytes + kVBytes;  // K_t then V_t
+  static constexpr int kStages = 2;
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffDO = kKBytes;
+  static constexpr int kOffRing = kKBytes + kVBytes;
+  static constexpr int kOffBar = kOffRing + kStages * kStage;
+  static constexpr int kNeed = kOffBar + 256 + 1024;
+  static constexpr int kSmem = kNeed > 120 * 1024 ? kNeed : 120 * 1024;
+  static constexpr uint32_t kColS = 0, kColP = 128, kColDQ = 256;
+};
+
+struct Bars2 {
+  uint64_t q_full;
+  uint64_t kv_full[2], kv_empty[2];
+  uint64_t s_full, dp_full, s_free, ds_ready;
+  uint64_t dq_full;
+  uint32_t tmem_base;
+};
+
+// thread = query row `r` of the tile (TMEM lane); this warp handles key columns [64*half, 64*half + 64)
+template <int DQK, int DV, bool BF16>
+__device__ __forceinline__ void softmax_dq(const BwdParams& p, Bars2& bar, int warp, int lane, int b, int h, int j,
+                                           int t0, int t1) {
+  using C = Cfg2<DQK, DV>;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int r = quarter * 32 + lane;
+  const int nrow = j * kT + r;
+  const uint32_t lanef = (uint32_t)(quarter * 32) << 16;
+  const uint32_t tS = bar.tmem_base + lanef + C::kColS + (uint32_t)(half * 64);
+  const uint32_t tP = bar.tmem_base + lanef + C::kColP + (uint32_t)(half * 64);
+  const float4 st = p.stats[((size_t)b * p.H + h) * p.Npad + nrow];
+  const float neg_m = -st.x, inv_l = st.y, delta = st.z;
+
+  for (int t = t0; t < t1; ++t) {
+    const uint32_t i_t = (uint32_t)(t - t0);
+    const int k0 = t * kT + half * 64;  // first key of this thread's 64 columns
+    uint32_t w0 = 0u, w1 = 0u;
+    bool tile_masked = (t * kT + kT > p.M);
+    if (p.pad_bits != nullptr) {
+      const uint4 mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)b * p.pad_wpr + (size_t)t * 4);
+      w0 = half == 0 ? mw.x : mw.z;
+      w1 = half == 0 ? mw.y : mw.w;
+      tile_masked = tile_masked || ((mw.x | mw.y | mw.z | mw.w) != 0u);
+    }
+    const bool masked = tile_masked || (p.causal && (t * kT + kT - 1 > j * kT + p.cshift));
+    const int cmax = p.causal ? (nrow + p.cshift - k0) : 0x7fffffff;  // column i filled iff i > cmax
+    const int oob_from = p.M - k0;                                   // column i beyond the tensor iff i >= oob_from
+    float pf[64];
+
+    mbar_wait(&bar.s_full, i_t & 1u, 30);
+    tc_fence_after_sync();
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t s[32];
+      tmem_ld32(tS + ch * 32, s);
+      tmem_wait_ld();
+      const uint32_t word = ch == 0 ? w0 : w1;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m);
+        if (masked) {
+          if (((word >> i) & 1u) || (ch * 32 + i) > cmax) x = kMaskedScore + neg_m;
+          if ((ch * 32 + i) >= oob_from) x = -INFINITY;
+        }
+        pf[ch * 32 + i] = ex2(x) * inv_l;
+      }
+    }
+    tc_fence_before_sync();
+    warp_arrive(&bar.s_free);  // S has been read: the issuer may overwrite it with the next tile's scores
+
+    mbar_wait(&bar.dp_full, i_t & 1u, 31);
+    tc_fence_after_sync();
+    {
+      uint32_t dk[32];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t d[32];
+        tmem_ld32(tP + ch * 32, d);
+        tmem_wait_ld();
+        const uint32_t word = ch == 0 ? w0 : w1;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float g0 = pf[ch * 32 + i] * (__uint_as_float(d[i]) - delta);
+          float g1 = pf[ch * 32 + i + 1] * (__uint_as_float(d[i + 1]) - delta);
+          if (masked) {
+            const int c0 = ch * 32 + i, c1 = c0 + 1;
+            if (((word >> i) & 1u) || c0 > cmax || c0 >= oob_from) g0 = 0.f;
+            if (((word >> (i + 1)) & 1u) || c1 > cmax || c1 >= oob_from) g1 = 0.f;
+          }
+          dk[ch * 16 + (i >> 1)] = pack2(g0, g1, BF16);
+        }
+      }
+      tmem_st32(tP, dk);  // dS (16-bit) over the first 32 columns of this warp's dP columns
+      tmem_wait_st();
+    }
+    tc_fence_before_sync();
+    warp_arrive(&bar.ds_ready);
+  }
+
+  // ---- add this CTA's dQ (scaled) into the fp32 buffer ----
+  mbar_wait(&bar.dq_full, 0u, 32);
+  tc_fence_after_sync();
+  {
+    constexpr int kCols = DQK / 2;  // columns per warp half
+    const uint32_t tQ = bar.tmem_base + lanef + C::kColDQ + (uint32_t)(half * kCols);
+    float* dst = p.dq32 + ((size_t)(p.q_bcast ? 0 : b) * p.N + (size_t)nrow) * ((size_t)p.H * p.dqk) + (size_t)h * p.dqk +
+                 (size_t)half * kCols;
+#pragma unroll
+    for (int ch = 0; ch < kCols / 32; ++ch) {
+      uint32_t a[32];
+      tmem_ld32(tQ + ch * 32, a);
+      tmem_wait_ld();
+      if (nrow < p.N) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int c = half * kCols + ch * 32 + g * 4;
+          if (c < p.dqk)
+            red_add_v4(dst + ch * 32 + g * 4, __uint_as_float(a[g * 4 + 0]) * p.scale,
+                       __uint_as_float(a[g * 4 + 1]) * p.scale, __uint_as_float(a[g * 4 + 2]) * p.scale,
+                       __uint_as_float(a[g * 4 + 3]) * p.scale);
+        }
+      }
+    }
+  }
+}
+
+template <int DQK, int DV, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+              const BwdParams p) {
+  using C = Cfg2<DQK, DV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars2& bar = *reinterpret_cast<Bars2*>(smem + C::kOffBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // blockIdx -> (b, h, query tile j, key-tile range); the query tiles of one (b, h) and split are neighbours, so the
+  // CTAs that stream the same K/V range run together and meet in L2
+  const int j = blockIdx.x % p.nq;
+  const int sp = (blockIdx.x / p.nq) % p.splits;
+  const int bh = blockIdx.x / (p.nq * p.splits);
+  const int h = bh % p.H, b = bh / p.H;
+  const int t0 = sp * p.tiles_per_split;
+  const int t1 = min(p.nk, t0 + p.tiles_per_split);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar.q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar.kv_full[i], 1);
+      mbar_init(&bar.kv_empty[i], 1);
+    }
+    mbar_init(&bar.s_full, 1);
+    mbar_init(&bar.dp_full, 1);
+    mbar_init(&bar.s_free, 8);
+    mbar_init(&bar.ds_ready, 8);
+    mbar_init(&bar.dq_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(&bar.tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  if (warp < 8) {
+    reg_alloc<208>();
+    softmax_dq<DQK, DV, BF16>(p, bar, warp, lane, b, h, j, t0, t1);
+  } else {
+    reg_dealloc<88>();
+  }
+
+  if (warp == kTmaWarp) {
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_arrive_expect_tx(&bar.q_full, (uint32_t)(C::kKBytes + C::kVBytes));
+#pragma unroll
+      for (int bx = 0; bx < C::kQB; ++bx)
+        tma_load_4d(smem + C::kOffQ + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64, j * kT, h, p.q_bcast ? 0 : b);
+#pragma unroll
+      for (int bx = 0; bx < C::kVB; ++bx)
+        tma_load_4d(smem + C::kOffDO + bx * kBoxBytes, &tmap_do, &bar.q_full, bx * 64, j * kT, h, b);
+    }
+    for (int t = t0; t < t1; ++t) {
+      const uint32_t it = (uint32_t)(t - t0), slot = it & 1u;
+      mbar_wait(&bar.kv_empty[slot], ((it >> 1) & 1u) ^ 1u, 10);
+      if (leader) {
+        uint8_t* st = smem + C::kOffRing + slot * C::kStage;
+        mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)C::kStage);
+#pragma unroll
+        for (int bx = 0; bx < C::kQB; ++bx)
+          tma_load_4d(st + bx * kBoxBytes, &tmap_k, &bar.kv_full[slot], bx * 64, t * kT, h, b);
+#pragma unroll
+        for (int bx = 0; bx < C::kVB; ++bx)
+          tma_load_4d(st + C::kKBytes + bx * kBoxBytes, &tmap_v, &bar.kv_full[slot], bx * 64, t * kT, h, b);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(kT, kT, BF16, false);
+    constexpr uint32_t idesc_dq = make_idesc(kT, DQK, BF16, true);
+    const uint32_t tmem = bar.tmem_base;
+    const uint64_t dQ = make_smem_desc(smem_u32(smem + C::kOffQ), 16, 1024);
+    const uint64_t dDO = make_smem_desc(smem_u32(smem + C::kOffDO), 16, 1024);
+    auto ring = [&](uint32_t slot) { return smem_u32(smem + C::kOffRing + slot * C::kStage); };
+    auto issue_s = [&](uint32_t slot) {  // S = Q_j K_t^T
+      if (leader) {
+        const uint64_t db = make_smem_desc(ring(slot), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < DQK / 16; ++kk) {
+          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          mma_ss(tmem + C::kColS, dQ + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+        }
+      }
+    };
+    auto issue_dp = [&](uint32_t slot) {  // dP = dO_j V_t^T
+      if (leader) {
+        const uint64_t db = make_smem_desc(ring(slot) + C::kKBytes, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < DV / 16; ++kk) {
+          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          mma_ss(tmem + C::kColP, dDO + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+        }
+      }
+    };
+    auto issue_dq = [&](uint32_t slot, bool acc) {  // dQ += dS(TMEM) K_t   (K_t read MN-major)
+      if (leader) {
+        const uint64_t db = make_smem_desc(ring(slot), kBoxBytes, 1024);
+#pragma unroll
+        for (int kk = 0; kk < kT / 16; ++kk)
+          mma_ts(tmem + C::kColDQ, tmem + C::kColP + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
+                 db + (uint64_t)((kk * 2048) >> 4), idesc_dq, (acc || kk > 0) ? 1u : 0u);
+      }
+    };
+    auto commit = [&](uint64_t* bp) {
+      if (leader) tc_commit(bp);
+    };
+
+    const int nt = t1 - t0;
+    mbar_wait(&bar.q_full, 0u, 11);
+    mbar_wait(&bar.kv_full[0], 0u, 12);
+    tc_fence_after_sync();
+    issue_s(0);
+    commit(&bar.s_full);
+    issue_dp(0);
+    commit(&bar.dp_full);
+    for (int i = 0; i < nt; ++i) {
+      const uint32_t slot = (uint32_t)i & 1u, nslot = slot ^ 1u;
+      const bool more = i + 1 < nt;
+      mbar_wait(&bar.s_free, (uint32_t)i & 1u, 13);
+      if (more) {
+        mbar_wait(&bar.kv_full[nslot], ((uint32_t)(i + 1) >> 1) & 1u, 14);
+        tc_fence_after_sync();
+        issue_s(nslot);
+        commit(&bar.s_full);
+      }
+      mbar_wait(&bar.ds_ready, (uint32_t)i & 1u, 15);
+      tc_fence_after_sync();
+      issue_dq(slot, i > 0);
+      commit(&bar.kv_empty[slot]);
+      if (more) {
+        issue_dp(nslot);
+        commit(&bar.dp_full);
+      }
+    }
+    commit(&bar.dq_full);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(bar.tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 bwd_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// (channels, rows, heads, batch) view of a (batch, rows, heads*channels)-style tensor; box = 64 x 128 x 1 x 1
+int bwd_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int rows, int heads, int batch,
+             int64_t stride_row, int64_t stride_head, int64_t stride_batch) {
+  auto fn = bwd_encode_fn();
+  PCV_REQUIRE(fn != nullptr, PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)batch};
+  if (stride_batch == 0) stride_batch = (int64_t)rows * stride_row;
+  cuuint64_t strides[3] = {(cuuint64_t)stride_row * 2, (cuuint64_t)stride_head * 2, (cuuint64_t)stride_batch * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kT, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = dtype == PCV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(tm, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PCV_REQUIRE(r == CUDA_SUCCESS, PCV_ERR_CUDA, "cuTensorMapEncodeTiled (backward) failed with CUresult %d", (int)r);
+  return PCV_OK;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct BwdLayout {
+  int Npad, nq, nk, wpr, Bq;
+  size_t off_stats, off_dq32, off_pad, total;
+};
+
+BwdLayout bwd_layout(const pcv_attn_bwd_params& a) {
+  BwdLayout L;
+  L.nq = (a.N + kT - 1) / kT;
+  L.nk = (a.M + kT - 1) / kT;
+  L.Npad = L.nq * kT;
+  L.wpr = L.nk * 4;
+  L.Bq = a.q_stride_b == 0 ? 1 : a.B;
+  L.off_stats = 0;
+  L.off_dq32 = align256(sizeof(float4) * (size_t)a.B * a.H * L.Npad);
+  L.off_pad = L.off_dq32 + align256(sizeof(float) * (size_t)L.Bq * a.N * a.H * a.dqk);
+  L.total = L.off_pad + (a.pad_mask != nullptr ? align256(sizeof(uint32_t) * (size_t)a.B * L.wpr) : 0);
+  return L;
+}
+
+template <int DQK, int DV, bool BF16>
+int launch_bwd_kernels(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                       const BwdParams& p, int sms, cudaStream_t stream) {
+  using C1 = Cfg1<DQK, DV>;
+  using C2 = Cfg2<DQK, DV>;
+  auto k1 = bwd_dkdv_kernel<DQK, DV, BF16>;
+  auto k2 = bwd_dq_kernel<DQK, DV, BF16>;
+  // per device and cheap: set on every launch rather than caching per process
+  PCV_CHECK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, C1::kSmem));
+  PCV_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem));
+  const int grid1 = std::min(p.total_tiles, sms);
+  k1<<<grid1, kThreads, C1::kSmem, stream>>>(tq, tk, tv, tdo, p);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  const int grid2 = p.B * p.H * p.nq * p.splits;
+  k2<<<grid2, kThreads, C2::kSmem, stream>>>(tq, tk, tv, tdo, p);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PCV_OK;
+}
+
+}  // namespace
+
+bool attn_bwd_supported(const pcv_attn_bwd_params& a, const char** why) {
+  auto no = [&](const char* w) {
+    if (why) *why = w;
+    return false;
+  };
+  if (a.dtype != PCV_BF16 && a.dtype != PCV_F16) return no("dtype must be bf16 or fp16");
+  if (a.B < 1 || a.H < 1 || a.N < 1 || a.M < 1) return no("empty problem");
+  if (a.dqk < 8 || a.dv < 8 || a.dqk > 128 || a.dv > 128) return no("head dims must be in [8, 128]");
+  if (a.dqk % 8 || a.dv % 8) return no("head dims must be multiples of 8");
+  if (a.dropout_p != 0.f) return no("attention dropout is not fused into the backward kernels");
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out) || !al16(a.grad_out) || !al16(a.grad_q) ||
+      !al16(a.grad_k) || !al16(a.grad_v))
+    return no("tensors must be 16-byte aligned");
+  const int64_t strides[] = {a.q_stride_b, a.q_stride_n, a.q_stride_h, a.k_stride_b, a.k_stride_m, a.k_stride_h,
+                             a.v_stride_b, a.v_stride_m, a.v_stride_h, a.go_stride_b, a.go_stride_n, a.go_stride_h,
+                             a.gk_stride_b, a.gk_stride_m, a.gk_stride_h, a.gv_stride_b, a.gv_stride_m, a.gv_stride_h};
+  for (int64_t s : strides)
+    if (s % 8) return no("strides must be multiples of 8 elements");
+  if ((int64_t)a.M >= (int64_t)1 << 30 || (int64_t)a.N >= (int64_t)1 << 24) return no("N or M too large");
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return no("no CUDA device");
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return no("needs an sm_100 device");
+  return true;
+}
+
+int attn_bwd_workspace_bytes(const pcv_attn_bwd_params& a, size_t* bytes) {
+  PCV_REQUIRE(bytes != nullptr, PCV_ERR_INVALID, "attn_bwd_workspace_bytes: bytes is NULL");
+  *bytes = bwd_layout(a).total;
+  return PCV_OK;
+}
+
+int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
+  const char* why = "";
+  PCV_REQUIRE(attn_bwd_supported(a, &why), PCV_ERR_UNSUPPORTED, "attn_bwd: %s", why);
+  PCV_REQUIRE(a.stat_m != nullptr && a.stat_l != nullptr, PCV_ERR_INVALID, "attn_bwd: forward statistics are NULL");
+  const BwdLayout L = bwd_layout(a);
+  PCV_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= L.total, PCV_ERR_INVALID,
+              "attn_bwd: workspace too small (%zu < %zu)", a.workspace_bytes, L.total);
+  PCV_REQUIRE((reinterpret_cast<uintptr_t>(a.workspace) & 255u) == 0, PCV_ERR_INVALID,
+              "attn_bwd: workspace must be 256-byte aligned");
+  int dev = 0, sms = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  PCV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a.workspace);
+  BwdParams p{};
+  p.B = a.B; p.H = a.H; p.N = a.N; p.M = a.M; p.dqk = a.dqk; p.dv = a.dv;
+  p.Npad = L.Npad; p.nq = L.nq; p.nk = L.nk;
+  p.q_bcast = (a.q_stride_b == 0 && a.B > 1) ? 1 : 0;
+  p.scale = a.scale;
+  p.scale_log2 = a.scale * kLog2e;
+  p.causal = a.causal;
+  p.cshift = a.M - a.N;
+  p.stats = reinterpret_cast<const float4*>(ws + L.off_stats);
+  p.dq32 = reinterpret_cast<float*>(ws + L.off_dq32);
+  p.dk = a.grad_k; p.dv_out = a.grad_v;
+  p.dk_sb = a.gk_stride_b; p.dk_sm = a.gk_stride_m; p.dk_sh = a.gk_stride_h;
+  p.dv_sb = a.gv_stride_b; p.dv_sm = a.gv_stride_m; p.dv_sh = a.gv_stride_h;
+  p.total_tiles = a.B * a.H * L.nk;
+  // dq kernel: aim at ~64 key tiles per CTA (launch + Q/dO load amortised) but at least ~4 CTAs per SM in total
+  {
+    const int units = a.B * a.H * L.nq;
+    int splits = std::max(1, (L.nk + 63) / 64);
+    while (units * splits < 4 * sms && splits < L.nk && (L.nk + splits - 1) / splits > 4) ++splits;
+    p.tiles_per_split = (L.nk + splits - 1) / splits;
+    p.splits = (L.nk + p.tiles_per_split - 1) / p.tiles_per_split;
+  }
+
+  const size_t dq32_bytes = sizeof(float) * (size_t)L.Bq * a.N * a.H * a.dqk;
+  PCV_CHECK_CUDA(cudaMemsetAsync(p.dq32, 0, dq32_bytes, stream));
+  {
+    const int64_t rows = (int64_t)a.B * a.H * L.Npad;
+    const int blocks = (int)((rows + 7) / 8);
+    float4* stats = reinterpret_cast<float4*>(ws + L.off_stats);
+    if (a.dtype == PCV_BF16)
+      bwd_prep_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
+          reinterpret_cast<const __nv_bfloat16*>(a.out), reinterpret_cast<const __nv_bfloat16*>(a.grad_out), a.stat_m,
+          a.stat_l, stats, a.B, a.H, a.N, L.Npad, a.dv, a.o_stride_b, a.o_stride_n, a.o_stride_h, a.go_stride_b,
+          a.go_stride_n, a.go_stride_h);
+    else
+      bwd_prep_kernel<__half><<<blocks, 256, 0, stream>>>(
+          reinterpret_cast<const __half*>(a.out), reinterpret_cast<const __half*>(a.grad_out), a.stat_m, a.stat_l, stats,
+          a.B, a.H, a.N, L.Npad, a.dv, a.o_stride_b, a.o_stride_n, a.o_stride_h, a.go_stride_b, a.go_stride_n,
+          a.go_stride_h);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  if (a.pad_mask != nullptr) {
+    uint32_t* bits = reinterpret_cast<uint32_t*>(ws + L.off_pad);
+    const int64_t total = (int64_t)a.B * L.wpr;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 1024);
+    bwd_pack_pad_kernel<<<blocks, 256, 0, stream>>>(a.pad_mask, a.pad_stride_b, a.B, a.M, L.wpr, bits);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    p.pad_bits = bits;
+    p.pad_wpr = L.wpr;
+  }
+
+  CUtensorMap tq, tk, tv, tdo;
+  int rc = bwd_tmap(&tq, a.q, a.dtype, a.dqk, a.N, a.H, L.Bq, a.q_stride_n, a.q_stride_h, a.q_stride_b);
+  if (rc != PCV_OK) return rc;
+  rc = bwd_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b);
+  if (rc != PCV_OK) return rc;
+  rc = bwd_tmap(&tv, a.v, a.dtype, a.dv, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
+  if (rc != PCV_OK) return rc;
+  rc = bwd_tmap(&tdo, a.grad_out, a.dtype, a.dv, a.N, a.H, a.B, a.go_stride_n, a.go_stride_h, a.go_stride_b);
+  if (rc != PCV_OK) return rc;
+
+  const bool bf16 = a.dtype == PCV_BF16;
+  const int DQK = a.dqk <= 64 ? 64 : 128, DV = a.dv <= 64 ? 64 : 128;
+#define PCV_BWD_CASE(dq_, dv_)                                                                              \
+  if (DQK == dq_ && DV == dv_)                                                                              \
+    rc = bf16 ? launch_bwd_kernels<dq_, dv_, true>(tq, tk, tv, tdo, p, sms, stream)                         \
+              : launch_bwd_kernels<dq_, dv_, false>(tq, tk, tv, tdo, p, sms, stream);
+  PCV_BWD_CASE(64, 64)
+  PCV_BWD_CASE(64, 128)
+  PCV_BWD_CASE(128, 64)
+  PCV_BWD_CASE(128, 128)
+#undef PCV_BWD_CASE
+  if (rc != PCV_OK) return rc;
+
+  {
+    const int64_t total = (int64_t)L.Bq * a.N * a.H * a.dqk;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    if (bf16)
+      bwd_cast_dq_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(p.dq32, reinterpret_cast<__nv_bfloat16*>(a.grad_q),
+                                                                    L.Bq, a.N, a.H, a.dqk, a.gq_stride_b, a.gq_stride_n,
+                                                                    a.gq_stride_h);
+    else
+      bwd_cast_dq_kernel<__half><<<blocks, 256, 0, stream>>>(p.dq32, reinterpret_cast<__half*>(a.grad_q), L.Bq, a.N, a.H,
+                                                             a.dqk, a.gq_stride_b, a.gq_stride_n, a.gq_stride_h);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return PCV_OK;
+}
+
+}  // namespace pcv

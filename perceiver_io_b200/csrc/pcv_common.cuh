@@ -100,5 +100,8 @@ int launch_kv_append(const pcv_kv_append_params& p, cudaStream_t stream);
 int launch_ln_stats(const pcv_ln_stats_params& p, cudaStream_t stream);
 bool kv_project_supported(const pcv_kvproj_params& p, const char** why);
 int launch_kv_project(const pcv_kvproj_params& p, cudaStream_t stream);
+bool attn_bwd_supported(const pcv_attn_bwd_params& p, const char** why);
+int attn_bwd_workspace_bytes(const pcv_attn_bwd_params& p, size_t* bytes);
+int launch_attn_bwd(const pcv_attn_bwd_params& p, cudaStream_t stream);
 
 }  // namespace pcv

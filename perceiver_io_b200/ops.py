@@ -174,16 +174,74 @@ def _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl):
 
 
 #: Budget of the backward shim: the largest fp32 score block (B, H, N, chunk) it materialises at a time.
-backward_config = {"max_score_bytes": 1 << 30}
+# "impl": "auto" = the tcgen05 backward kernels (pcv_attn_bwd) whenever they cover the call, else the torch shim;
+# "kernel" = kernels or raise; "shim" = always the shim.  "max_score_bytes" bounds the shim's score chunk.
+backward_config = {"max_score_bytes": 1 << 30, "impl": "auto"}
+
+
+def _fill_bwd_params(q, k, v, out, grad_out, stat_m, stat_l, num_heads, scale, pad_mask, causal):
+    ap, keep = _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, None, 0, "auto")
+    B, H, N, M, dqk, dv = ap.B, ap.H, ap.N, ap.M, ap.dqk, ap.dv
+    for name, t in (("out", out), ("grad_out", grad_out)):
+        if tuple(t.shape) != (B, N, H * dv) or t.stride(2) != 1:
+            raise ValueError(f"{name} must be a (B, N, H*dv) tensor with unit channel stride, got {tuple(t.shape)}")
+    for name, t in (("stat_m", stat_m), ("stat_l", stat_l)):
+        if tuple(t.shape) != (B, H, N) or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous float32 (B, H, N) tensor")
+    Bq = q.shape[0]
+    gq = torch.empty(Bq, N, H * dqk, dtype=q.dtype, device=q.device)
+    gk = torch.empty(B, M, H * dqk, dtype=q.dtype, device=q.device)
+    gv = torch.empty(B, M, H * dv, dtype=q.dtype, device=q.device)
+    p = _lib.AttnBwdParams()
+    p.q, p.k, p.v, p.out, p.grad_out = ap.q, ap.k, ap.v, out.data_ptr(), grad_out.data_ptr()
+    p.stat_m, p.stat_l = stat_m.data_ptr(), stat_l.data_ptr()
+    p.grad_q, p.grad_k, p.grad_v = gq.data_ptr(), gk.data_ptr(), gv.data_ptr()
+    for f in ("q_stride_b", "q_stride_n", "q_stride_h", "k_stride_b", "k_stride_m", "k_stride_h",
+              "v_stride_b", "v_stride_m", "v_stride_h"):
+        setattr(p, f, getattr(ap, f))
+    p.o_stride_b, p.o_stride_n, p.o_stride_h = out.stride(0), out.stride(1), dv
+    p.go_stride_b, p.go_stride_n, p.go_stride_h = grad_out.stride(0), grad_out.stride(1), dv
+    p.gq_stride_b, p.gq_stride_n, p.gq_stride_h = gq.stride(0), gq.stride(1), dqk
+    p.gk_stride_b, p.gk_stride_m, p.gk_stride_h = gk.stride(0), gk.stride(1), dqk
+    p.gv_stride_b, p.gv_stride_m, p.gv_stride_h = gv.stride(0), gv.stride(1), dv
+    p.B, p.H, p.N, p.M, p.dqk, p.dv = B, H, N, M, dqk, dv
+    p.scale, p.dtype, p.causal = float(scale), ap.dtype, ap.causal
+    p.pad_mask, p.pad_stride_b = ap.pad_mask, ap.pad_stride_b
+    return p, (gq, gk, gv), keep + (out, grad_out, stat_m, stat_l)
+
+
+def attention_backward(q, k, v, out, grad_out, stat_m, stat_l, num_heads: int, scale: float, pad_mask=None,
+                       causal: bool = False, check_only: bool = False):
+    """Gradients (grad_q, grad_k, grad_v) of ``attention`` on the tcgen05 backward kernels (pcv_attn_bwd).
+
+    ``out`` is the forward output, ``stat_m`` / ``stat_l`` the (B, H, N) row statistics of ``attention_partial`` over all
+    keys.  grad_q has q's batch size (a batch-1 ``q`` shared by the batch receives the sum).  ``check_only`` launches
+    nothing and returns whether the kernels cover these operands."""
+    q, k, v, _ = _prep(q, k, v)
+    cdt = q.dtype
+    out = _rows_contiguous(out if out.dtype == cdt else out.to(cdt))
+    grad_out = _rows_contiguous(grad_out if grad_out.dtype == cdt else grad_out.to(cdt))
+    _require_cuda(out, grad_out, stat_m, stat_l, pad_mask)
+    with torch.cuda.device(k.device):
+        p, grads, keep = _fill_bwd_params(q, k, v, out, grad_out, stat_m, stat_l, num_heads, scale, pad_mask, causal)
+        if check_only:
+            return bool(_lib.lib().pcv_attn_bwd_supported(C.byref(p)))
+        need = C.c_size_t(0)
+        check(_lib.lib().pcv_attn_bwd_workspace_bytes(C.byref(p), C.byref(need)), "pcv_attn_bwd_workspace_bytes")
+        ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=k.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), need.value
+        check(_lib.lib().pcv_attn_bwd(C.byref(p), _stream()), "pcv_attn_bwd")
+    del keep
+    return grads
 
 
 class _FusedAttention(torch.autograd.Function):
     """Forward = the fused CUDA kernel (partial-state mode, so the row max and denominator are kept).
-    Backward = TRAINING-SUPPORT SHIM, not a kernel: the flash-attention backward recurrence in plain torch ops,
-    chunked over the key axis from the saved softmax statistics, so that the reference's Lightning wrappers can call
-    ``loss.backward()`` (SURVEY.md §7.3 "Training") at any M without ever holding the (B, H, N, M) score tensor
-    (8.6 GB at the north-star shape): memory is bounded by ``backward_config["max_score_bytes"]``.  A fused backward
-    kernel is SURVEY.md §8(f) rank 2.  The inference forward never routes through this class."""
+    Backward = the tcgen05 backward kernels (``attention_backward`` -> pcv_attn_bwd: dK/dV and dQ kernels, SURVEY.md
+    §8(f) rank 2) for head dims that are multiples of 8 up to 128.  Other shapes take the labelled SHIM below: the
+    flash-attention backward recurrence in plain torch ops, chunked over the key axis from the saved statistics,
+    memory bounded by ``backward_config["max_score_bytes"]``; neither path ever holds the (B, H, N, M) score tensor
+    (8.6 GB at the north-star shape).  The inference forward never routes through this class."""
 
     @staticmethod
     def forward(ctx, q, k, v, num_heads, scale, pad_mask, causal, impl):
@@ -204,6 +262,18 @@ class _FusedAttention(torch.autograd.Function):
     def backward(ctx, grad_out):
         q, k, v, pad_mask, out, pm, pl = ctx.saved_tensors
         H, scale, causal = ctx.meta
+        mode = backward_config["impl"]
+        if mode not in ("auto", "kernel", "shim"):
+            raise ValueError(f"backward_config['impl'] = {mode!r}")
+        if mode != "shim":
+            ok = (pm is not None and q.is_cuda and q.dim() == 3 and k.dim() == 3 and v.dim() == 3
+                  and attention_backward(q, k, v, out, grad_out, pm, pl, H, scale, pad_mask, causal, check_only=True))
+            if ok:
+                gq, gk, gv = attention_backward(q, k, v, out, grad_out, pm, pl, H, scale, pad_mask, causal)
+                return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), None, None, None, None, None
+            if mode == "kernel":
+                raise RuntimeError("backward_config['impl'] = 'kernel' but pcv_attn_bwd does not cover this call: "
+                                   + _lib.lib().pcv_last_error().decode())
         B, M = k.shape[0], k.shape[1]
         N = q.shape[1]
         cdt = _compute_dtype(q.dtype)

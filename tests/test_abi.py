@@ -57,6 +57,7 @@ def test_ctypes_layout_matches_header(tmp_path):
         "pcv_ln_stats_params": _lib.LnStatsParams,
         "pcv_merge_params": _lib.MergeParams,
         "pcv_shard_fuse": _lib.ShardFuse,
+        "pcv_attn_bwd_params": _lib.AttnBwdParams,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, cls in structs.items():
