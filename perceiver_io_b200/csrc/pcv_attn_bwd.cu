@@ -42,7 +42,7 @@ constexpr int kBoxBytes = kT * 128;     // one TMA box: 128 rows x 64 16-bit cha
 constexpr int kThreads = 384;
 constexpr int kTmaWarp = 8;
 constexpr int kMmaWarp = 9;
-constexpr int kStatsBytes = kT * 16;    // float4 {m, 1/l, delta, 0} per query of a tile
+constexpr int kStatsBytes = kT * 12;    // row statistics of one 128-query tile (see bwd_prep_kernel)
 
 struct BwdParams {
   int B, H, N, M, dqk, dv;
@@ -52,7 +52,7 @@ struct BwdParams {
   int causal, cshift;        // key masked for query n iff key > n + cshift   (cshift = M - N: right aligned)
   const uint32_t* pad_bits;  // (B, pad_wpr) bit set = padding key; nullptr if none
   int pad_wpr;
-  const float4* stats;       // (B, H, Npad)
+  const float* stats;        // (B, H, nq) blocks of kStatsBytes (layout: see bwd_prep_kernel)
   float* dq32;               // (Bq, N, H*dqk) fp32, zero-initialised; CTAs reduce into it
   void* dk;
   void* dv_out;
@@ -83,6 +83,25 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 // one arrive per warp on a barrier initialised with count 8 (the eight softmax warps)
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   __syncwarp();
@@ -90,12 +109,19 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// prep: stats[b,h,n] = {m, 1/l, delta = sum_c dO*O, 0}; rows n >= N of the last tile are zero (their P is 0)
+// Row statistics, one 1536-byte block per (b, h, query tile): 64 x float4 {nlse[2c], nlse[2c+1], delta[2c], delta[2c+1]}
+// then 128 x float fillp.   nlse = -(m + log2 l) so that P = 2^(t + nlse); delta = sum_c dO*O; fillp = the probability
+// of a FILLED score: 1/l on a row whose scores are all filled (uniform attention), else 0.  Rows beyond N (tile
+// padding) and fully filled rows get nlse = -inf (their live P is exactly 0).
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int stat_nlse_idx(int r) { return (r >> 1) * 4 + (r & 1); }
+__device__ __forceinline__ int stat_delta_idx(int r) { return (r >> 1) * 4 + 2 + (r & 1); }
+__device__ __forceinline__ int stat_fillp_idx(int r) { return 256 + r; }
+
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ out, const T* __restrict__ dout,
                                                        const float* __restrict__ stat_m,
-                                                       const float* __restrict__ stat_l, float4* __restrict__ stats,
+                                                       const float* __restrict__ stat_l, float* __restrict__ stats,
                                                        int B, int H, int N, int Npad, int dv, int64_t o_sb,
                                                        int64_t o_sn, int64_t o_sh, int64_t g_sb, int64_t g_sn,
                                                        int64_t g_sh) {
@@ -105,19 +131,27 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ out
   const int n = (int)(row % Npad);
   const int64_t bh = row / Npad;
   const int h = (int)(bh % H), b = (int)(bh / H);
-  float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+  float nlse = -INFINITY, delta = 0.f, fillp = 0.f;
   if (n < N) {
     const T* o = out + b * o_sb + (int64_t)n * o_sn + h * o_sh;
     const T* g = dout + b * g_sb + (int64_t)n * g_sn + h * g_sh;
     float acc = 0.f;
     for (int c = lane; c < dv; c += 32) acc += Elem<T>::to_f(o[c]) * Elem<T>::to_f(g[c]);
-    acc = warp_sum(acc);
+    delta = warp_sum(acc);
     const int64_t r = bh * N + n;
-    st.x = stat_m[r];
-    st.y = 1.f / stat_l[r];
-    st.z = acc;
+    const float m = stat_m[r], l = stat_l[r];
+    if (m <= -1e37f)
+      fillp = 1.f / l;  // every score of the row is the finite fill: uniform over the l filled keys
+    else
+      nlse = -(m + log2f(l));
   }
-  if (lane == 0) stats[row] = st;
+  if (lane == 0) {
+    float* blk = stats + (bh * (Npad / kT) + n / kT) * (kStatsBytes / 4);
+    const int r = n % kT;
+    blk[stat_nlse_idx(r)] = nlse;
+    blk[stat_delta_idx(r)] = delta;
+    blk[stat_fillp_idx(r)] = fillp;
+  }
 }
 
 // pad_mask bytes (B, M) -> bit words (B, wpr), wpr = 4 * ceil(M/128); bit set = padding key
@@ -154,13 +188,15 @@ __global__ void __launch_bounds__(256) bwd_cast_dq_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// kernel 1: dK, dV
+// kernel 1: dK, dV.   A "sub-step" is (key tile, 64 queries): S^T and dP^T are 64 columns each, so two sets fit next to
+// the dK / dV accumulators (2 x 128 + 256 = 512 TMEM columns) and the tensor pipe computes the scores of sub-step u+1
+// while the softmax warps turn those of sub-step u into P^T / dS^T.
 // ---------------------------------------------------------------------------------------------------------------
 template <int DQK, int DV>
 struct Cfg1 {
   static constexpr int kQB = DQK / 64, kVB = DV / 64;
   static constexpr int kKBytes = kQB * kBoxBytes, kVBytes = kVB * kBoxBytes;
-  static constexpr int kStage = kKBytes + kVBytes;  // Q_j then dO_j
+  static constexpr int kStage = kKBytes + kVBytes;  // Q_j then dO_j (128 queries)
   static constexpr int kOffK = 0;
   static constexpr int kOffV = kKBytes;
   static constexpr int kOffStage = kKBytes + kVBytes;
@@ -168,27 +204,89 @@ struct Cfg1 {
   static constexpr int kOffBar = kOffStats + 2 * kStatsBytes;
   static constexpr int kNeed = kOffBar + 256 + 1024;
   static constexpr int kSmem = kNeed > 120 * 1024 ? kNeed : 120 * 1024;  // > half an SM: one CTA (512 TMEM columns) per SM
-  static constexpr uint32_t kColS = 0, kColP = 128, kColDK = 256, kColDV = 256 + DQK;
+  static constexpr uint32_t kColDK = 256, kColDV = 256 + DQK;
+  // set s (0/1): S^T at 128*s, dP^T at 128*s + 64
 };
 
 struct Bars1 {
   uint64_t kv_full, kv_empty;
   uint64_t qdo_full[2], qdo_empty[2];
-  uint64_t s_full, dp_full, p_ready, ds_ready;
+  uint64_t s_full[2], dp_full[2], p_ready[2], ds_ready[2];
   uint64_t acc_full, acc_empty;
   uint32_t tmem_base;
 };
 
-// thread = key row `r` of the tile (TMEM lane); this warp handles query columns [64*half, 64*half + 64)
+// One sub-step of one thread: key row (TMEM lane) x 32 query columns.  MASKED: some score of the CTA's tile is
+// filled / out of range (padding keys, causal diagonal, ragged last key tile).
+template <bool BF16, bool MASKED>
+__device__ __forceinline__ void dkdv_substep(Bars1& bar, uint32_t set, uint32_t par, uint32_t tS, uint32_t tP,
+                                             const float* st, const float* fp, float scale_log2, bool row_filled,
+                                             bool oob, int nfill) {
+  const float4* st4 = reinterpret_cast<const float4*>(st);
+  const float2 sc2 = make_float2(scale_log2, scale_log2);
+  uint32_t s[32];
+  float2 de[16];
+  mbar_wait(&bar.s_full[set], par, 21);
+  tc_fence_after_sync();
+  tmem_ld32(tS, s);
+  tmem_wait_ld();
+  {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float4 q = st4[i >> 1];  // {nlse_i, nlse_i+1, delta_i, delta_i+1}: same address for the whole warp
+      de[i >> 1] = make_float2(q.z, q.w);
+      const float2 x = fma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, make_float2(q.x, q.y));
+      float p0 = ex2(x.x), p1 = ex2(x.y);
+      if (MASKED) {
+        if (row_filled || i < nfill) p0 = fp[i];
+        if (row_filled || i + 1 < nfill) p1 = fp[i + 1];
+        if (oob) p0 = p1 = 0.f;
+      }
+      s[i] = __float_as_uint(p0);
+      s[i + 1] = __float_as_uint(p1);
+      pk[i >> 1] = pack2(p0, p1, BF16);
+    }
+    tmem_st16(tS, pk);  // P^T (16-bit) over the first 16 of this warp's 32 S^T columns
+    tmem_wait_st();
+  }
+  tc_fence_before_sync();
+  warp_arrive(&bar.p_ready[set]);
+
+  mbar_wait(&bar.dp_full[set], par, 22);
+  tc_fence_after_sync();
+  {
+    uint32_t d[32];
+    uint32_t gk[16];
+    tmem_ld32(tP, d);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float2 t = sub2(make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1])), de[i >> 1]);
+      float2 g = mul2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), t);
+      if (MASKED) {  // a filled score is a constant: no gradient through it
+        if (row_filled || oob || i < nfill) g.x = 0.f;
+        if (row_filled || oob || i + 1 < nfill) g.y = 0.f;
+      }
+      gk[i >> 1] = pack2(g.x, g.y, BF16);
+    }
+    tmem_st16(tP, gk);
+    tmem_wait_st();
+  }
+  tc_fence_before_sync();
+  warp_arrive(&bar.ds_ready[set]);
+}
+
+// thread = key row `r` of the tile (TMEM lane); this warp handles 32 of the 64 query columns of every sub-step
 template <int DQK, int DV, bool BF16>
 __device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uint8_t* smem, int warp, int lane) {
   using C = Cfg1<DQK, DV>;
   const int quarter = warp & 3, half = warp >> 2;
   const int r = quarter * 32 + lane;
   const uint32_t lanef = (uint32_t)(quarter * 32) << 16;
-  const uint32_t tS = bar.tmem_base + lanef + C::kColS + (uint32_t)(half * 64);
-  const uint32_t tP = bar.tmem_base + lanef + C::kColP + (uint32_t)(half * 64);
-  uint32_t n = 0, tile_iter = 0;
+  const uint32_t tbase = bar.tmem_base + lanef + (uint32_t)(half * 32);
+  const int U = 2 * p.nq;
+  uint32_t g = 0, tile_iter = 0;
   for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
     const int kt = id % p.nk, bh = id / p.nk;
     const int h = bh % p.H, b = bh / p.H;
@@ -199,73 +297,26 @@ __device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uin
     const uint32_t myw = quarter == 0 ? mw.x : (quarter == 1 ? mw.y : (quarter == 2 ? mw.z : mw.w));
     const bool pad = (myw >> lane) & 1u;
     const bool tile_masked = ((mw.x | mw.y | mw.z | mw.w) != 0u) || (kt * kT + kT > p.M);
-    for (int j = 0; j < p.nq; ++j) {
-      const uint32_t cur = n + (uint32_t)j, slot = cur & 1u;
-      const float4* st_s = reinterpret_cast<const float4*>(smem + C::kOffStats + slot * kStatsBytes) + half * 64;
-      // leading columns (queries) of this thread's 64 for which the key is causally hidden
-      const int q0 = j * kT + half * 64;
-      int nfill = 0;
-      if (p.causal) nfill = min(max(key - p.cshift - q0, 0), 64);
-      const bool masked = tile_masked || (p.causal && (kt * kT + kT - 1 > j * kT + p.cshift));
-      float pf[64];
-
-      mbar_wait(&bar.qdo_full[slot], (cur >> 1) & 1u, 20);  // the statistics of this query tile are visible
-      mbar_wait(&bar.s_full, cur & 1u, 21);
-      tc_fence_after_sync();
-      {
-        uint32_t pk[32];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t s[32];
-          tmem_ld32(tS + ch * 32, s);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 st = st_s[ch * 32 + i];
-            float x = fmaf(__uint_as_float(s[i]), p.scale_log2, -st.x);
-            if (masked) {
-              if (pad || (ch * 32 + i) < nfill) x = kMaskedScore - st.x;  // finite fill: 0, or 1/l on a fully filled row
-              if (oob) x = -INFINITY;
-            }
-            pf[ch * 32 + i] = ex2(x) * st.y;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) pk[ch * 16 + (i >> 1)] = pack2(pf[ch * 32 + i], pf[ch * 32 + i + 1], BF16);
-        }
-        tmem_st32(tS, pk);  // P^T (16-bit) over the first 32 columns of this warp's S^T columns
-        tmem_wait_st();
+    for (int u = 0; u < U; ++u) {
+      const uint32_t gu = g + (uint32_t)u, set = gu & 1u, it = gu >> 1, slot = it & 1u, par = it & 1u;
+      const int j = u >> 1, sub = u & 1;
+      const int c0 = sub * 64 + half * 32;       // first of this thread's 32 columns within the 128-query stage
+      const int q0 = j * kT + c0;                // ... as a query index
+      if (sub == 0) mbar_wait(&bar.qdo_full[slot], (it >> 1) & 1u, 20);  // the statistics of this stage are visible
+      const float* blk = reinterpret_cast<const float*>(smem + C::kOffStats + slot * kStatsBytes);
+      const float* st = blk + (c0 >> 1) * 4;   // {nlse, nlse, delta, delta} of this thread's column pairs
+      const float* fp = blk + 256 + c0;        // fill probabilities of its columns
+      const uint32_t tS = tbase + set * 128u, tP = tS + 64u;
+      const bool masked = tile_masked || (p.causal && (kt * kT + kT - 1 > j * kT + sub * 64 + p.cshift));
+      if (!masked) {
+        dkdv_substep<BF16, false>(bar, set, par, tS, tP, st, fp, p.scale_log2, false, false, 0);
+      } else {
+        int nfill = 0;  // leading columns (queries) for which this key is causally hidden
+        if (p.causal) nfill = min(max(key - p.cshift - q0, 0), 32);
+        dkdv_substep<BF16, true>(bar, set, par, tS, tP, st, fp, p.scale_log2, pad, oob, nfill);
       }
-      tc_fence_before_sync();
-      warp_arrive(&bar.p_ready);
-
-      mbar_wait(&bar.dp_full, cur & 1u, 22);
-      tc_fence_after_sync();
-      {
-        uint32_t dk[32];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t d[32];
-          tmem_ld32(tP + ch * 32, d);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float de0 = st_s[ch * 32 + i].z, de1 = st_s[ch * 32 + i + 1].z;
-            float g0 = pf[ch * 32 + i] * (__uint_as_float(d[i]) - de0);
-            float g1 = pf[ch * 32 + i + 1] * (__uint_as_float(d[i + 1]) - de1);
-            if (masked) {  // a filled score is a constant: no gradient through it
-              if (pad || oob || (ch * 32 + i) < nfill) g0 = 0.f;
-              if (pad || oob || (ch * 32 + i + 1) < nfill) g1 = 0.f;
-            }
-            dk[ch * 16 + (i >> 1)] = pack2(g0, g1, BF16);
-          }
-        }
-        tmem_st32(tP, dk);
-        tmem_wait_st();
-      }
-      tc_fence_before_sync();
-      warp_arrive(&bar.ds_ready);
     }
-    n += (uint32_t)p.nq;
+    g += (uint32_t)U;
 
     // ---- drain the accumulators of this key tile: half 0 -> dK (scaled), half 1 -> dV ----
     mbar_wait(&bar.acc_full, tile_iter & 1u, 23);
@@ -284,14 +335,14 @@ __device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uin
         tmem_wait_ld();
         if (!oob) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = ch * 32 + g * 8;
+          for (int gq = 0; gq < 4; ++gq) {
+            const int c = ch * 32 + gq * 8;
             if (c < nreal) {
               uint4 w;
-              w.x = pack2(__uint_as_float(a[g * 8 + 0]) * mult, __uint_as_float(a[g * 8 + 1]) * mult, BF16);
-              w.y = pack2(__uint_as_float(a[g * 8 + 2]) * mult, __uint_as_float(a[g * 8 + 3]) * mult, BF16);
-              w.z = pack2(__uint_as_float(a[g * 8 + 4]) * mult, __uint_as_float(a[g * 8 + 5]) * mult, BF16);
-              w.w = pack2(__uint_as_float(a[g * 8 + 6]) * mult, __uint_as_float(a[g * 8 + 7]) * mult, BF16);
+              w.x = pack2(__uint_as_float(a[gq * 8 + 0]) * mult, __uint_as_float(a[gq * 8 + 1]) * mult, BF16);
+              w.y = pack2(__uint_as_float(a[gq * 8 + 2]) * mult, __uint_as_float(a[gq * 8 + 3]) * mult, BF16);
+              w.z = pack2(__uint_as_float(a[gq * 8 + 4]) * mult, __uint_as_float(a[gq * 8 + 5]) * mult, BF16);
+              w.w = pack2(__uint_as_float(a[gq * 8 + 6]) * mult, __uint_as_float(a[gq * 8 + 7]) * mult, BF16);
               *reinterpret_cast<uint4*>(dst + c) = w;
             }
           }
@@ -320,11 +371,11 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar.qdo_full[i], 1);
       mbar_init(&bar.qdo_empty[i], 1);
+      mbar_init(&bar.s_full[i], 1);
+      mbar_init(&bar.dp_full[i], 1);
+      mbar_init(&bar.p_ready[i], 8);
+      mbar_init(&bar.ds_ready[i], 8);
     }
-    mbar_init(&bar.s_full, 1);
-    mbar_init(&bar.dp_full, 1);
-    mbar_init(&bar.p_ready, 8);
-    mbar_init(&bar.ds_ready, 8);
     mbar_init(&bar.acc_full, 1);
     mbar_init(&bar.acc_empty, 8);
     fence_mbar_init();
@@ -351,7 +402,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 
   if (warp == kTmaWarp) {
-    // ===== TMA producer: K, V of the key tile once; Q_j, dO_j and the row statistics per query tile =====
+    // ===== TMA producer: K, V of the key tile once; Q_j, dO_j and the row statistics per 128-query stage =====
     const bool leader = elect_one();
     uint32_t it = 0, tile_iter = 0;
     for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
@@ -379,7 +430,8 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int bx = 0; bx < C::kVB; ++bx)
             tma_load_4d(st + C::kKBytes + bx * kBoxBytes, &tmap_do, &bar.qdo_full[slot], bx * 64, j * kT, h, b);
-          bulk_load_1d(smem + C::kOffStats + slot * kStatsBytes, p.stats + ((size_t)bh * p.Npad + (size_t)j * kT),
+          bulk_load_1d(smem + C::kOffStats + slot * kStatsBytes,
+                       reinterpret_cast<const uint8_t*>(p.stats) + ((size_t)bh * p.nq + (size_t)j) * kStatsBytes,
                        kStatsBytes, &bar.qdo_full[slot]);
         }
       }
@@ -387,93 +439,91 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   } else if (warp == kMmaWarp) {
     // ===== MMA issuer (warp converged, one elected lane issues) =====
     const bool leader = elect_one();
-    constexpr uint32_t idesc_s = make_idesc(kT, kT, BF16, false);
+    constexpr uint32_t idesc_s = make_idesc(kT, 64, BF16, false);
     constexpr uint32_t idesc_dv = make_idesc(kT, DV, BF16, true);
     constexpr uint32_t idesc_dk = make_idesc(kT, DQK, BF16, true);
     const uint32_t tmem = bar.tmem_base;
     const uint64_t dK = make_smem_desc(smem_u32(smem + C::kOffK), 16, 1024);
     const uint64_t dV = make_smem_desc(smem_u32(smem + C::kOffV), 16, 1024);
     auto stage_q = [&](uint32_t slot) { return smem_u32(smem + C::kOffStage + slot * C::kStage); };
-    auto issue_s = [&](uint32_t slot) {  // S^T = K Q_j^T
+    // sub-step gu: stage slot (gu>>1)&1, query rows [64*(gu&1), +64) of the stage, TMEM set gu&1
+    auto issue_s = [&](uint32_t gu) {  // S^T = K Q^T
       if (leader) {
-        const uint64_t db = make_smem_desc(stage_q(slot), 16, 1024);
+        const uint64_t db = make_smem_desc(stage_q((gu >> 1) & 1u) + (gu & 1u) * 8192u, 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < DQK / 16; ++kk) {
           const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          mma_ss(tmem + C::kColS, dK + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+          mma_ss(tmem + (gu & 1u) * 128u, dK + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
         }
       }
     };
-    auto issue_dp = [&](uint32_t slot) {  // dP^T = V dO_j^T
+    auto issue_dp = [&](uint32_t gu) {  // dP^T = V dO^T
       if (leader) {
-        const uint64_t db = make_smem_desc(stage_q(slot) + C::kKBytes, 16, 1024);
+        const uint64_t db = make_smem_desc(stage_q((gu >> 1) & 1u) + C::kKBytes + (gu & 1u) * 8192u, 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < DV / 16; ++kk) {
           const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          mma_ss(tmem + C::kColP, dV + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+          mma_ss(tmem + (gu & 1u) * 128u + 64u, dV + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
         }
       }
     };
-    auto issue_dv = [&](uint32_t slot, bool acc) {  // dV += P^T(TMEM) dO_j   (dO_j read MN-major: 16 queries = 2048 bytes)
+    auto issue_dv = [&](uint32_t gu, bool acc) {  // dV += P^T(TMEM) dO   (dO read MN-major: 16 queries = 2048 bytes)
       if (leader) {
-        const uint64_t db = make_smem_desc(stage_q(slot) + C::kKBytes, kBoxBytes, 1024);
+        const uint64_t db = make_smem_desc(stage_q((gu >> 1) & 1u) + C::kKBytes, kBoxBytes, 1024);
 #pragma unroll
-        for (int kk = 0; kk < kT / 16; ++kk)
-          mma_ts(tmem + C::kColDV, tmem + C::kColS + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
-                 db + (uint64_t)((kk * 2048) >> 4), idesc_dv, (acc || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk)
+          mma_ts(tmem + C::kColDV, tmem + (gu & 1u) * 128u + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8),
+                 db + (uint64_t)((((gu & 1u) * 4 + kk) * 2048) >> 4), idesc_dv, (acc || kk > 0) ? 1u : 0u);
       }
     };
-    auto issue_dk = [&](uint32_t slot, bool acc) {  // dK += dS^T(TMEM) Q_j
+    auto issue_dk = [&](uint32_t gu, bool acc) {  // dK += dS^T(TMEM) Q
       if (leader) {
-        const uint64_t db = make_smem_desc(stage_q(slot), kBoxBytes, 1024);
+        const uint64_t db = make_smem_desc(stage_q((gu >> 1) & 1u), kBoxBytes, 1024);
 #pragma unroll
-        for (int kk = 0; kk < kT / 16; ++kk)
-          mma_ts(tmem + C::kColDK, tmem + C::kColP + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
-                 db + (uint64_t)((kk * 2048) >> 4), idesc_dk, (acc || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk)
+          mma_ts(tmem + C::kColDK, tmem + (gu & 1u) * 128u + 64u + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8),
+                 db + (uint64_t)((((gu & 1u) * 4 + kk) * 2048) >> 4), idesc_dk, (acc || kk > 0) ? 1u : 0u);
       }
     };
-    auto commit = [&](uint64_t* b) {
-      if (leader) tc_commit(b);
+    auto commit = [&](uint64_t* bp) {
+      if (leader) tc_commit(bp);
     };
 
-    uint32_t n = 0, tile_iter = 0;
+    const int U = 2 * p.nq;
+    uint32_t g = 0, tile_iter = 0;
     for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
       mbar_wait(&bar.kv_full, tile_iter & 1u, 3);
-      {
-        const uint32_t slot = n & 1u;
-        mbar_wait(&bar.qdo_full[slot], (n >> 1) & 1u, 4);
-        tc_fence_after_sync();
-        issue_s(slot);
-        commit(&bar.s_full);
-        issue_dp(slot);
-        commit(&bar.dp_full);
-        if (p.nq == 1) commit(&bar.kv_empty);
-      }
-      for (int j = 0; j < p.nq; ++j) {
-        const uint32_t cur = n + (uint32_t)j, slot = cur & 1u, nslot = slot ^ 1u;
-        const bool more = j + 1 < p.nq;
-        mbar_wait(&bar.p_ready, cur & 1u, 5);
-        if (j == 0) mbar_wait(&bar.acc_empty, (tile_iter & 1u) ^ 1u, 6);
-        tc_fence_after_sync();
-        issue_dv(slot, j > 0);
-        if (more) {
-          mbar_wait(&bar.qdo_full[nslot], ((cur + 1) >> 1) & 1u, 7);
-          tc_fence_after_sync();
-          issue_s(nslot);
-          commit(&bar.s_full);
+      mbar_wait(&bar.qdo_full[(g >> 1) & 1u], (g >> 2) & 1u, 4);
+      tc_fence_after_sync();
+      issue_s(g);
+      commit(&bar.s_full[g & 1u]);
+      issue_dp(g);
+      commit(&bar.dp_full[g & 1u]);
+      for (int u = 0; u < U; ++u) {
+        const uint32_t gu = g + (uint32_t)u, set = gu & 1u, par = (gu >> 1) & 1u;
+        if (u + 1 < U) {
+          const uint32_t gn = gu + 1;
+          if ((gn & 1u) == 0u) {
+            mbar_wait(&bar.qdo_full[(gn >> 1) & 1u], (gn >> 2) & 1u, 7);
+            tc_fence_after_sync();
+          }
+          issue_s(gn);
+          commit(&bar.s_full[gn & 1u]);
+          issue_dp(gn);
+          commit(&bar.dp_full[gn & 1u]);
+          if (u + 2 == U) commit(&bar.kv_empty);  // K and V are not read again for this key tile
         }
-        mbar_wait(&bar.ds_ready, cur & 1u, 8);
+        mbar_wait(&bar.p_ready[set], par, 5);
+        if (u == 0) mbar_wait(&bar.acc_empty, (tile_iter & 1u) ^ 1u, 6);
         tc_fence_after_sync();
-        issue_dk(slot, j > 0);
-        commit(&bar.qdo_empty[slot]);
-        if (more) {
-          issue_dp(nslot);
-          commit(&bar.dp_full);
-          if (j + 2 == p.nq) commit(&bar.kv_empty);  // K and V are not read again for this key tile
-        }
+        issue_dv(gu, u > 0);
+        mbar_wait(&bar.ds_ready[set], par, 8);
+        tc_fence_after_sync();
+        issue_dk(gu, u > 0);
+        if (gu & 1u) commit(&bar.qdo_empty[(gu >> 1) & 1u]);
       }
       commit(&bar.acc_full);
-      n += (uint32_t)p.nq;
+      g += (uint32_t)U;
     }
   }
 
@@ -486,7 +536,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// kernel 2: dQ
+// kernel 2: dQ.   TMEM: S 0..127, dP double buffered at 128 / 256 (dS overwrites its dP), dQ at 384.
 // ---------------------------------------------------------------------------------------------------------------
 template <int DQK, int DV>
 struct Cfg2 {
@@ -500,16 +550,71 @@ struct Cfg2 {
   static constexpr int kOffBar = kOffRing + kStages * kStage;
   static constexpr int kNeed = kOffBar + 256 + 1024;
   static constexpr int kSmem = kNeed > 120 * 1024 ? kNeed : 120 * 1024;
-  static constexpr uint32_t kColS = 0, kColP = 128, kColDQ = 256;
+  static constexpr uint32_t kColS = 0, kColP = 128, kColDQ = 384;
 };
 
 struct Bars2 {
   uint64_t q_full;
   uint64_t kv_full[2], kv_empty[2];
-  uint64_t s_full, dp_full, s_free, ds_ready;
+  uint64_t s_full, dp_full[2], s_free, ds_ready;
   uint64_t dq_full;
   uint32_t tmem_base;
 };
+
+// one key tile of one thread: query row (TMEM lane) x 64 key columns
+template <bool BF16, bool MASKED>
+__device__ __forceinline__ void dq_tile(Bars2& bar, uint32_t i_t, uint32_t tS, uint32_t tP, float scale_log2,
+                                        float nlse, float delta, float fillp, uint32_t w0, uint32_t w1, int cmax,
+                                        int oob_from) {
+  const float2 sc2 = make_float2(scale_log2, scale_log2), nl2 = make_float2(nlse, nlse), de2 = make_float2(delta, delta);
+  uint32_t s[64];
+  mbar_wait(&bar.s_full, i_t & 1u, 30);
+  tc_fence_after_sync();
+  tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+  tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+  tmem_wait_ld();
+  tc_fence_before_sync();
+  warp_arrive(&bar.s_free);  // S is in registers: the issuer may overwrite it with the next tile's scores
+#pragma unroll
+  for (int i = 0; i < 64; i += 2) {
+    const float2 x = fma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nl2);
+    float p0 = ex2(x.x), p1 = ex2(x.y);
+    if (MASKED) {
+      const uint32_t word = i < 32 ? w0 : w1;
+      if (((word >> (i & 31)) & 1u) || i > cmax) p0 = fillp;
+      if (((word >> ((i + 1) & 31)) & 1u) || i + 1 > cmax) p1 = fillp;
+      if (i >= oob_from) p0 = 0.f;
+      if (i + 1 >= oob_from) p1 = 0.f;
+    }
+    s[i] = __float_as_uint(p0);
+    s[i + 1] = __float_as_uint(p1);
+  }
+
+  mbar_wait(&bar.dp_full[i_t & 1u], (i_t >> 1) & 1u, 31);
+  tc_fence_after_sync();
+  {
+    uint32_t d[64];
+    uint32_t gk[32];
+    tmem_ld32(tP, *reinterpret_cast<uint32_t(*)[32]>(&d[0]));
+    tmem_ld32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&d[32]));
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 64; i += 2) {
+      const float2 t = sub2(make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1])), de2);
+      float2 g = mul2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), t);
+      if (MASKED) {
+        const uint32_t word = i < 32 ? w0 : w1;
+        if (((word >> (i & 31)) & 1u) || i > cmax || i >= oob_from) g.x = 0.f;
+        if (((word >> ((i + 1) & 31)) & 1u) || i + 1 > cmax || i + 1 >= oob_from) g.y = 0.f;
+      }
+      gk[i >> 1] = pack2(g.x, g.y, BF16);
+    }
+    tmem_st32(tP, gk);  // dS (16-bit) over the first 32 of this warp's 64 dP columns
+    tmem_wait_st();
+  }
+  tc_fence_before_sync();
+  warp_arrive(&bar.ds_ready);
+}
 
 // thread = query row `r` of the tile (TMEM lane); this warp handles key columns [64*half, 64*half + 64)
 template <int DQK, int DV, bool BF16>
@@ -521,12 +626,13 @@ __device__ __forceinline__ void softmax_dq(const BwdParams& p, Bars2& bar, int w
   const int nrow = j * kT + r;
   const uint32_t lanef = (uint32_t)(quarter * 32) << 16;
   const uint32_t tS = bar.tmem_base + lanef + C::kColS + (uint32_t)(half * 64);
-  const uint32_t tP = bar.tmem_base + lanef + C::kColP + (uint32_t)(half * 64);
-  const float4 st = p.stats[((size_t)b * p.H + h) * p.Npad + nrow];
-  const float neg_m = -st.x, inv_l = st.y, delta = st.z;
+  const uint32_t tP0 = bar.tmem_base + lanef + C::kColP + (uint32_t)(half * 64);
+  const float* blk = p.stats + (((size_t)b * p.H + h) * p.nq + (size_t)j) * (kStatsBytes / 4);
+  const float nlse = blk[stat_nlse_idx(r)], delta = blk[stat_delta_idx(r)], fillp = blk[stat_fillp_idx(r)];
 
   for (int t = t0; t < t1; ++t) {
     const uint32_t i_t = (uint32_t)(t - t0);
+    const uint32_t tP = tP0 + (i_t & 1u) * 128u;
     const int k0 = t * kT + half * 64;  // first key of this thread's 64 columns
     uint32_t w0 = 0u, w1 = 0u;
     bool tile_masked = (t * kT + kT > p.M);
@@ -537,58 +643,13 @@ __device__ __forceinline__ void softmax_dq(const BwdParams& p, Bars2& bar, int w
       tile_masked = tile_masked || ((mw.x | mw.y | mw.z | mw.w) != 0u);
     }
     const bool masked = tile_masked || (p.causal && (t * kT + kT - 1 > j * kT + p.cshift));
-    const int cmax = p.causal ? (nrow + p.cshift - k0) : 0x7fffffff;  // column i filled iff i > cmax
-    const int oob_from = p.M - k0;                                   // column i beyond the tensor iff i >= oob_from
-    float pf[64];
-
-    mbar_wait(&bar.s_full, i_t & 1u, 30);
-    tc_fence_after_sync();
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t s[32];
-      tmem_ld32(tS + ch * 32, s);
-      tmem_wait_ld();
-      const uint32_t word = ch == 0 ? w0 : w1;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m);
-        if (masked) {
-          if (((word >> i) & 1u) || (ch * 32 + i) > cmax) x = kMaskedScore + neg_m;
-          if ((ch * 32 + i) >= oob_from) x = -INFINITY;
-        }
-        pf[ch * 32 + i] = ex2(x) * inv_l;
-      }
+    if (!masked) {
+      dq_tile<BF16, false>(bar, i_t, tS, tP, p.scale_log2, nlse, delta, fillp, 0u, 0u, 0, 0);
+    } else {
+      const int cmax = p.causal ? (nrow + p.cshift - k0) : 0x7fffffff;  // column i filled iff i > cmax
+      const int oob_from = p.M - k0;                                   // column i beyond the tensor iff i >= oob_from
+      dq_tile<BF16, true>(bar, i_t, tS, tP, p.scale_log2, nlse, delta, fillp, w0, w1, cmax, oob_from);
     }
-    tc_fence_before_sync();
-    warp_arrive(&bar.s_free);  // S has been read: the issuer may overwrite it with the next tile's scores
-
-    mbar_wait(&bar.dp_full, i_t & 1u, 31);
-    tc_fence_after_sync();
-    {
-      uint32_t dk[32];
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t d[32];
-        tmem_ld32(tP + ch * 32, d);
-        tmem_wait_ld();
-        const uint32_t word = ch == 0 ? w0 : w1;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float g0 = pf[ch * 32 + i] * (__uint_as_float(d[i]) - delta);
-          float g1 = pf[ch * 32 + i + 1] * (__uint_as_float(d[i + 1]) - delta);
-          if (masked) {
-            const int c0 = ch * 32 + i, c1 = c0 + 1;
-            if (((word >> i) & 1u) || c0 > cmax || c0 >= oob_from) g0 = 0.f;
-            if (((word >> (i + 1)) & 1u) || c1 > cmax || c1 >= oob_from) g1 = 0.f;
-          }
-          dk[ch * 16 + (i >> 1)] = pack2(g0, g1, BF16);
-        }
-      }
-      tmem_st32(tP, dk);  // dS (16-bit) over the first 32 columns of this warp's dP columns
-      tmem_wait_st();
-    }
-    tc_fence_before_sync();
-    warp_arrive(&bar.ds_ready);
   }
 
   // ---- add this CTA's dQ (scaled) into the fp32 buffer ----
@@ -606,12 +667,12 @@ __device__ __forceinline__ void softmax_dq(const BwdParams& p, Bars2& bar, int w
       tmem_wait_ld();
       if (nrow < p.N) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int c = half * kCols + ch * 32 + g * 4;
+        for (int gq = 0; gq < 8; ++gq) {
+          const int c = half * kCols + ch * 32 + gq * 4;
           if (c < p.dqk)
-            red_add_v4(dst + ch * 32 + g * 4, __uint_as_float(a[g * 4 + 0]) * p.scale,
-                       __uint_as_float(a[g * 4 + 1]) * p.scale, __uint_as_float(a[g * 4 + 2]) * p.scale,
-                       __uint_as_float(a[g * 4 + 3]) * p.scale);
+            red_add_v4(dst + ch * 32 + gq * 4, __uint_as_float(a[gq * 4 + 0]) * p.scale,
+                       __uint_as_float(a[gq * 4 + 1]) * p.scale, __uint_as_float(a[gq * 4 + 2]) * p.scale,
+                       __uint_as_float(a[gq * 4 + 3]) * p.scale);
         }
       }
     }
@@ -643,9 +704,9 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar.kv_full[i], 1);
       mbar_init(&bar.kv_empty[i], 1);
+      mbar_init(&bar.dp_full[i], 1);
     }
     mbar_init(&bar.s_full, 1);
-    mbar_init(&bar.dp_full, 1);
     mbar_init(&bar.s_free, 8);
     mbar_init(&bar.ds_ready, 8);
     mbar_init(&bar.dq_full, 1);
@@ -715,22 +776,22 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
       }
     };
-    auto issue_dp = [&](uint32_t slot) {  // dP = dO_j V_t^T
+    auto issue_dp = [&](uint32_t i) {  // dP = dO_j V_t^T into dP buffer i & 1 (K/V ring slot i & 1)
       if (leader) {
-        const uint64_t db = make_smem_desc(ring(slot) + C::kKBytes, 16, 1024);
+        const uint64_t db = make_smem_desc(ring(i & 1u) + C::kKBytes, 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < DV / 16; ++kk) {
           const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          mma_ss(tmem + C::kColP, dDO + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+          mma_ss(tmem + C::kColP + (i & 1u) * 128u, dDO + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
         }
       }
     };
-    auto issue_dq = [&](uint32_t slot, bool acc) {  // dQ += dS(TMEM) K_t   (K_t read MN-major)
+    auto issue_dq = [&](uint32_t i, bool acc) {  // dQ += dS(TMEM) K_t   (K_t read MN-major)
       if (leader) {
-        const uint64_t db = make_smem_desc(ring(slot), kBoxBytes, 1024);
+        const uint64_t db = make_smem_desc(ring(i & 1u), kBoxBytes, 1024);
 #pragma unroll
         for (int kk = 0; kk < kT / 16; ++kk)
-          mma_ts(tmem + C::kColDQ, tmem + C::kColP + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
+          mma_ts(tmem + C::kColDQ, tmem + C::kColP + (i & 1u) * 128u + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
                  db + (uint64_t)((kk * 2048) >> 4), idesc_dq, (acc || kk > 0) ? 1u : 0u);
       }
     };
@@ -745,25 +806,22 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     issue_s(0);
     commit(&bar.s_full);
     issue_dp(0);
-    commit(&bar.dp_full);
+    commit(&bar.dp_full[0]);
     for (int i = 0; i < nt; ++i) {
-      const uint32_t slot = (uint32_t)i & 1u, nslot = slot ^ 1u;
-      const bool more = i + 1 < nt;
-      mbar_wait(&bar.s_free, (uint32_t)i & 1u, 13);
-      if (more) {
-        mbar_wait(&bar.kv_full[nslot], ((uint32_t)(i + 1) >> 1) & 1u, 14);
+      const uint32_t ui = (uint32_t)i;
+      if (i + 1 < nt) {
+        mbar_wait(&bar.s_free, ui & 1u, 13);  // S_i is in the softmax warps' registers
+        mbar_wait(&bar.kv_full[(ui + 1) & 1u], ((ui + 1) >> 1) & 1u, 14);
         tc_fence_after_sync();
-        issue_s(nslot);
+        issue_s((ui + 1) & 1u);
         commit(&bar.s_full);
+        issue_dp(ui + 1);  // the other dP buffer: its dS was consumed by dQ(i-1), issued before
+        commit(&bar.dp_full[(ui + 1) & 1u]);
       }
-      mbar_wait(&bar.ds_ready, (uint32_t)i & 1u, 15);
+      mbar_wait(&bar.ds_ready, ui & 1u, 15);
       tc_fence_after_sync();
-      issue_dq(slot, i > 0);
-      commit(&bar.kv_empty[slot]);
-      if (more) {
-        issue_dp(nslot);
-        commit(&bar.dp_full);
-      }
+      issue_dq(ui, i > 0);
+      commit(&bar.kv_empty[ui & 1u]);
     }
     commit(&bar.dq_full);
   }
@@ -824,7 +882,7 @@ BwdLayout bwd_layout(const pcv_attn_bwd_params& a) {
   L.wpr = L.nk * 4;
   L.Bq = a.q_stride_b == 0 ? 1 : a.B;
   L.off_stats = 0;
-  L.off_dq32 = align256(sizeof(float4) * (size_t)a.B * a.H * L.Npad);
+  L.off_dq32 = align256((size_t)kStatsBytes * a.B * a.H * L.nq);
   L.off_pad = L.off_dq32 + align256(sizeof(float) * (size_t)L.Bq * a.N * a.H * a.dqk);
   L.total = L.off_pad + (a.pad_mask != nullptr ? align256(sizeof(uint32_t) * (size_t)a.B * L.wpr) : 0);
   return L;
@@ -908,7 +966,7 @@ int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * kLog2e;
   p.causal = a.causal;
   p.cshift = a.M - a.N;
-  p.stats = reinterpret_cast<const float4*>(ws + L.off_stats);
+  p.stats = reinterpret_cast<const float*>(ws + L.off_stats);
   p.dq32 = reinterpret_cast<float*>(ws + L.off_dq32);
   p.dk = a.grad_k; p.dv_out = a.grad_v;
   p.dk_sb = a.gk_stride_b; p.dk_sm = a.gk_stride_m; p.dk_sh = a.gk_stride_h;
@@ -928,7 +986,7 @@ int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
   {
     const int64_t rows = (int64_t)a.B * a.H * L.Npad;
     const int blocks = (int)((rows + 7) / 8);
-    float4* stats = reinterpret_cast<float4*>(ws + L.off_stats);
+    float* stats = reinterpret_cast<float*>(ws + L.off_stats);
     if (a.dtype == PCV_BF16)
       bwd_prep_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
           reinterpret_cast<const __nv_bfloat16*>(a.out), reinterpret_cast<const __nv_bfloat16*>(a.grad_out), a.stat_m,
