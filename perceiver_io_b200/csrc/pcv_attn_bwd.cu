@@ -30,6 +30,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace pcv {
@@ -42,7 +43,15 @@ constexpr int kBoxBytes = kT * 128;     // one TMA box: 128 rows x 64 16-bit cha
 constexpr int kThreads = 384;
 constexpr int kTmaWarp = 8;
 constexpr int kMmaWarp = 9;
-constexpr int kStatsBytes = kT * 12;    // row statistics of one 128-query tile (see bwd_prep_kernel)
+constexpr int kStatsBytes = 64 * 12;    // row statistics of one block of 64 queries (see bwd_prep_kernel)
+#ifndef PCV_BWD_POLY_EVERY
+#define PCV_BWD_POLY_EVERY 0
+#endif
+// Experiment (compile time, off): one column pair in kPolyEvery takes its 2^x from a cubic on the FMA/ALU pipes instead
+// of MUFU.  Measured with every 2nd pair: dQ kernel 1.22 -> 1.36 ms, dK/dV kernel +1 % — neither kernel is MUFU bound
+// (XU pipe 21 % busy), the extra issue slots only lengthen the softmax warps' critical path.
+constexpr int kPolyEvery = PCV_BWD_POLY_EVERY;
+constexpr int kBox64 = 64 * 128;        // a 64-row TMA box (the dK/dV kernel stages Q / dO in 64-query pieces)
 
 struct BwdParams {
   int B, H, N, M, dqk, dv;
@@ -52,11 +61,12 @@ struct BwdParams {
   int causal, cshift;        // key masked for query n iff key > n + cshift   (cshift = M - N: right aligned)
   const uint32_t* pad_bits;  // (B, pad_wpr) bit set = padding key; nullptr if none
   int pad_wpr;
-  const float* stats;        // (B, H, nq) blocks of kStatsBytes (layout: see bwd_prep_kernel)
+  const float* stats;        // (B, H, 2*nq) blocks of kStatsBytes (layout: see bwd_prep_kernel)
   float* dq32;               // (Bq, N, H*dqk) fp32, zero-initialised; CTAs reduce into it
   void* dk;
   void* dv_out;
   int64_t dk_sb, dk_sm, dk_sh, dv_sb, dv_sm, dv_sh;
+  int wide_store;            // dk / dv rows are 32-byte aligned: 256-bit stores
   int total_tiles;           // dkdv kernel: B*H*nk
   int splits, tiles_per_split;  // dq kernel
 };
@@ -102,6 +112,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// 256-bit store (sm_100): `addr` 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* addr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
 // one arrive per warp on a barrier initialised with count 8 (the eight softmax warps)
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   __syncwarp();
@@ -109,14 +126,14 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Row statistics, one 1536-byte block per (b, h, query tile): 64 x float4 {nlse[2c], nlse[2c+1], delta[2c], delta[2c+1]}
-// then 128 x float fillp.   nlse = -(m + log2 l) so that P = 2^(t + nlse); delta = sum_c dO*O; fillp = the probability
+// Row statistics, one 768-byte block per (b, h, 64 queries): 32 x float4 {nlse[2c], nlse[2c+1], delta[2c], delta[2c+1]}
+// then 64 x float fillp.   nlse = -(m + log2 l) so that P = 2^(t + nlse); delta = sum_c dO*O; fillp = the probability
 // of a FILLED score: 1/l on a row whose scores are all filled (uniform attention), else 0.  Rows beyond N (tile
 // padding) and fully filled rows get nlse = -inf (their live P is exactly 0).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int stat_nlse_idx(int r) { return (r >> 1) * 4 + (r & 1); }
 __device__ __forceinline__ int stat_delta_idx(int r) { return (r >> 1) * 4 + 2 + (r & 1); }
-__device__ __forceinline__ int stat_fillp_idx(int r) { return 256 + r; }
+__device__ __forceinline__ int stat_fillp_idx(int r) { return 128 + r; }
 
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ out, const T* __restrict__ dout,
@@ -146,8 +163,8 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ out
       nlse = -(m + log2f(l));
   }
   if (lane == 0) {
-    float* blk = stats + (bh * (Npad / kT) + n / kT) * (kStatsBytes / 4);
-    const int r = n % kT;
+    float* blk = stats + (bh * (Npad / 64) + n / 64) * (kStatsBytes / 4);
+    const int r = n % 64;
     blk[stat_nlse_idx(r)] = nlse;
     blk[stat_delta_idx(r)] = delta;
     blk[stat_fillp_idx(r)] = fillp;
@@ -196,13 +213,15 @@ template <int DQK, int DV>
 struct Cfg1 {
   static constexpr int kQB = DQK / 64, kVB = DV / 64;
   static constexpr int kKBytes = kQB * kBoxBytes, kVBytes = kVB * kBoxBytes;
-  static constexpr int kStage = kKBytes + kVBytes;  // Q_j then dO_j (128 queries)
+  static constexpr int kQStage = kQB * kBox64;       // 64 queries of Q
+  static constexpr int kStage = (kQB + kVB) * kBox64;  // ... then the same 64 rows of dO
   static constexpr int kOffK = 0;
   static constexpr int kOffV = kKBytes;
   static constexpr int kOffStage = kKBytes + kVBytes;
-  static constexpr int kOffStats = kOffStage + 2 * kStage;
-  static constexpr int kOffBar = kOffStats + 2 * kStatsBytes;
-  static constexpr int kNeed = kOffBar + 256 + 1024;
+  static constexpr int kAvail = 232448 - 1024 - 512 - kOffStage;
+  static constexpr int kStages = kAvail / kStage > 6 ? 6 : kAvail / kStage;  // 5 at 128/128: the L2 latency of a stage
+  static constexpr int kOffBar = kOffStage + kStages * kStage;               // is ~4 sub-steps of tensor work
+  static constexpr int kNeed = kOffBar + 512 + 1024;
   static constexpr int kSmem = kNeed > 120 * 1024 ? kNeed : 120 * 1024;  // > half an SM: one CTA (512 TMEM columns) per SM
   static constexpr uint32_t kColDK = 256, kColDV = 256 + DQK;
   // set s (0/1): S^T at 128*s, dP^T at 128*s + 64
@@ -210,81 +229,104 @@ struct Cfg1 {
 
 struct Bars1 {
   uint64_t kv_full, kv_empty;
-  uint64_t qdo_full[2], qdo_empty[2];
+  uint64_t qdo_full[6], qdo_empty[6];
   uint64_t s_full[2], dp_full[2], p_ready[2], ds_ready[2];
   uint64_t acc_full, acc_empty;
   uint32_t tmem_base;
 };
 
-// One sub-step of one thread: key row (TMEM lane) x 32 query columns.  MASKED: some score of the CTA's tile is
-// filled / out of range (padding keys, causal diagonal, ragged last key tile).
+// One sub-step of one thread: key row (TMEM lane) x all 64 query columns, in two passes of 32.  MASKED: some score of
+// the CTA's tile is filled / out of range (padding keys, causal diagonal, ragged last key tile).
+//   st: the 32 float4 {nlse, nlse, delta, delta} of the sub-step's 64 queries; fp: their 64 fill probabilities.
 template <bool BF16, bool MASKED>
 __device__ __forceinline__ void dkdv_substep(Bars1& bar, uint32_t set, uint32_t par, uint32_t tS, uint32_t tP,
                                              const float* st, const float* fp, float scale_log2, bool row_filled,
                                              bool oob, int nfill) {
   const float4* st4 = reinterpret_cast<const float4*>(st);
   const float2 sc2 = make_float2(scale_log2, scale_log2);
-  uint32_t s[32];
-  float2 de[16];
+  float pf[64];
   mbar_wait(&bar.s_full[set], par, 21);
   tc_fence_after_sync();
-  tmem_ld32(tS, s);
-  tmem_wait_ld();
-  {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t s[32];
     uint32_t pk[16];
+    tmem_ld32(tS + hh * 32, s);
+    float2 nl[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {  // same address for the whole warp; a few KB per (b, h): L1 resident
+      const float4 q = __ldg(st4 + hh * 16 + i);
+      nl[i] = make_float2(q.x, q.y);
+    }
+    tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const float4 q = st4[i >> 1];  // {nlse_i, nlse_i+1, delta_i, delta_i+1}: same address for the whole warp
-      de[i >> 1] = make_float2(q.z, q.w);
-      const float2 x = fma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, make_float2(q.x, q.y));
-      float p0 = ex2(x.x), p1 = ex2(x.y);
+      const float2 x = fma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nl[i >> 1]);
+      float p0, p1;
+      if (kPolyEvery > 0 && ((i >> 1) % kPolyEvery) == kPolyEvery - 1) {  // FMA/ALU pipes instead of the MUFU queue
+        const float2 e = exp2_poly2_fast(x);
+        p0 = e.x;
+        p1 = e.y;
+      } else {
+        p0 = ex2(x.x);
+        p1 = ex2(x.y);
+      }
       if (MASKED) {
-        if (row_filled || i < nfill) p0 = fp[i];
-        if (row_filled || i + 1 < nfill) p1 = fp[i + 1];
+        if (row_filled || hh * 32 + i < nfill) p0 = __ldg(fp + hh * 32 + i);
+        if (row_filled || hh * 32 + i + 1 < nfill) p1 = __ldg(fp + hh * 32 + i + 1);
         if (oob) p0 = p1 = 0.f;
       }
-      s[i] = __float_as_uint(p0);
-      s[i + 1] = __float_as_uint(p1);
+      pf[hh * 32 + i] = p0;
+      pf[hh * 32 + i + 1] = p1;
       pk[i >> 1] = pack2(p0, p1, BF16);
     }
-    tmem_st16(tS, pk);  // P^T (16-bit) over the first 16 of this warp's 32 S^T columns
-    tmem_wait_st();
+    tmem_st16(tS + hh * 32, pk);  // P^T (16-bit) over the first 16 of each 32 S^T columns
   }
+  tmem_wait_st();
   tc_fence_before_sync();
   warp_arrive(&bar.p_ready[set]);
 
   mbar_wait(&bar.dp_full[set], par, 22);
   tc_fence_after_sync();
-  {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
     uint32_t d[32];
     uint32_t gk[16];
-    tmem_ld32(tP, d);
+    tmem_ld32(tP + hh * 32, d);
+    float2 de[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 q = __ldg(st4 + hh * 16 + i);
+      de[i] = make_float2(q.z, q.w);
+    }
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       const float2 t = sub2(make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1])), de[i >> 1]);
-      float2 g = mul2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), t);
+      float2 g = mul2(make_float2(pf[hh * 32 + i], pf[hh * 32 + i + 1]), t);
       if (MASKED) {  // a filled score is a constant: no gradient through it
-        if (row_filled || oob || i < nfill) g.x = 0.f;
-        if (row_filled || oob || i + 1 < nfill) g.y = 0.f;
+        if (row_filled || oob || hh * 32 + i < nfill) g.x = 0.f;
+        if (row_filled || oob || hh * 32 + i + 1 < nfill) g.y = 0.f;
       }
       gk[i >> 1] = pack2(g.x, g.y, BF16);
     }
-    tmem_st16(tP, gk);
-    tmem_wait_st();
+    tmem_st16(tP + hh * 32, gk);
   }
+  tmem_wait_st();
   tc_fence_before_sync();
   warp_arrive(&bar.ds_ready[set]);
 }
 
-// thread = key row `r` of the tile (TMEM lane); this warp handles 32 of the 64 query columns of every sub-step
+// thread = key row `r` of the tile (TMEM lane).  The two warps of a lane quarter take ALTERNATE sub-steps (warps 0-3 the
+// even ones = TMEM set 0, warps 4-7 the odd ones = set 1), each all 64 query columns: two sub-steps are in flight, so the
+// TMEM round trips and barrier hand-offs of one overlap the arithmetic of the other.
 template <int DQK, int DV, bool BF16>
 __device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uint8_t* smem, int warp, int lane) {
   using C = Cfg1<DQK, DV>;
   const int quarter = warp & 3, half = warp >> 2;
   const int r = quarter * 32 + lane;
   const uint32_t lanef = (uint32_t)(quarter * 32) << 16;
-  const uint32_t tbase = bar.tmem_base + lanef + (uint32_t)(half * 32);
+  const uint32_t tbase = bar.tmem_base + lanef;
   const int U = 2 * p.nq;
   uint32_t g = 0, tile_iter = 0;
   for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
@@ -297,22 +339,19 @@ __device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uin
     const uint32_t myw = quarter == 0 ? mw.x : (quarter == 1 ? mw.y : (quarter == 2 ? mw.z : mw.w));
     const bool pad = (myw >> lane) & 1u;
     const bool tile_masked = ((mw.x | mw.y | mw.z | mw.w) != 0u) || (kt * kT + kT > p.M);
-    for (int u = 0; u < U; ++u) {
-      const uint32_t gu = g + (uint32_t)u, set = gu & 1u, it = gu >> 1, slot = it & 1u, par = it & 1u;
-      const int j = u >> 1, sub = u & 1;
-      const int c0 = sub * 64 + half * 32;       // first of this thread's 32 columns within the 128-query stage
-      const int q0 = j * kT + c0;                // ... as a query index
-      if (sub == 0) mbar_wait(&bar.qdo_full[slot], (it >> 1) & 1u, 20);  // the statistics of this stage are visible
-      const float* blk = reinterpret_cast<const float*>(smem + C::kOffStats + slot * kStatsBytes);
-      const float* st = blk + (c0 >> 1) * 4;   // {nlse, nlse, delta, delta} of this thread's column pairs
-      const float* fp = blk + 256 + c0;        // fill probabilities of its columns
+    for (int u = half; u < U; u += 2) {       // U is even and g a multiple of it: set == half
+      const uint32_t gu = g + (uint32_t)u, set = gu & 1u, par = (gu >> 1) & 1u;
+      const int q0 = u * 64;                     // first query column of the sub-step
+      const float* blk = p.stats + ((size_t)bh * U + (size_t)u) * (kStatsBytes / 4);
+      const float* st = blk;                     // {nlse, nlse, delta, delta} of the 32 column pairs
+      const float* fp = blk + 128;               // fill probabilities of the 64 columns
       const uint32_t tS = tbase + set * 128u, tP = tS + 64u;
-      const bool masked = tile_masked || (p.causal && (kt * kT + kT - 1 > j * kT + sub * 64 + p.cshift));
+      const bool masked = tile_masked || (p.causal && (kt * kT + kT - 1 > u * 64 + p.cshift));
       if (!masked) {
         dkdv_substep<BF16, false>(bar, set, par, tS, tP, st, fp, p.scale_log2, false, false, 0);
       } else {
         int nfill = 0;  // leading columns (queries) for which this key is causally hidden
-        if (p.causal) nfill = min(max(key - p.cshift - q0, 0), 32);
+        if (p.causal) nfill = min(max(key - p.cshift - q0, 0), 64);
         dkdv_substep<BF16, true>(bar, set, par, tS, tP, st, fp, p.scale_log2, pad, oob, nfill);
       }
     }
@@ -329,21 +368,24 @@ __device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uin
       uint16_t* dst = half == 0
                           ? reinterpret_cast<uint16_t*>(p.dk) + b * p.dk_sb + (int64_t)key * p.dk_sm + h * p.dk_sh
                           : reinterpret_cast<uint16_t*>(p.dv_out) + b * p.dv_sb + (int64_t)key * p.dv_sm + h * p.dv_sh;
-      for (int ch = 0; ch < cols / 32; ++ch) {
-        uint32_t a[32];
-        tmem_ld32(tA + ch * 32, a);
+      for (int ch = 0; ch < cols / 64; ++ch) {  // 64 accumulator columns per round trip to TMEM
+        uint32_t a[64];
+        tmem_ld32(tA + ch * 64, *reinterpret_cast<uint32_t(*)[32]>(&a[0]));
+        tmem_ld32(tA + ch * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&a[32]));
         tmem_wait_ld();
         if (!oob) {
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            const int c = ch * 32 + gq * 8;
-            if (c < nreal) {
-              uint4 w;
-              w.x = pack2(__uint_as_float(a[gq * 8 + 0]) * mult, __uint_as_float(a[gq * 8 + 1]) * mult, BF16);
-              w.y = pack2(__uint_as_float(a[gq * 8 + 2]) * mult, __uint_as_float(a[gq * 8 + 3]) * mult, BF16);
-              w.z = pack2(__uint_as_float(a[gq * 8 + 4]) * mult, __uint_as_float(a[gq * 8 + 5]) * mult, BF16);
-              w.w = pack2(__uint_as_float(a[gq * 8 + 6]) * mult, __uint_as_float(a[gq * 8 + 7]) * mult, BF16);
-              *reinterpret_cast<uint4*>(dst + c) = w;
+          for (int gq = 0; gq < 4; ++gq) {  // 16 channels = 32 bytes per store
+            const int c = ch * 64 + gq * 16;
+            uint32_t w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              w[e] = pack2(__uint_as_float(a[gq * 16 + 2 * e]) * mult, __uint_as_float(a[gq * 16 + 2 * e + 1]) * mult, BF16);
+            if (p.wide_store && c + 16 <= nreal) {
+              st_global_v8(dst + c, w);  // one full 32-byte sector per lane (16-byte stores leave half sectors to L2)
+            } else {
+              if (c < nreal) *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+              if (c + 8 < nreal) *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
             }
           }
         }
@@ -368,13 +410,15 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(&bar.kv_full, 1);
     mbar_init(&bar.kv_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&bar.qdo_full[i], 1);
       mbar_init(&bar.qdo_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&bar.s_full[i], 1);
       mbar_init(&bar.dp_full[i], 1);
-      mbar_init(&bar.p_ready[i], 8);
-      mbar_init(&bar.ds_ready[i], 8);
+      mbar_init(&bar.p_ready[i], 4);   // the four warps that own this set
+      mbar_init(&bar.ds_ready[i], 4);
     }
     mbar_init(&bar.acc_full, 1);
     mbar_init(&bar.acc_empty, 8);
@@ -402,7 +446,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 
   if (warp == kTmaWarp) {
-    // ===== TMA producer: K, V of the key tile once; Q_j, dO_j and the row statistics per 128-query stage =====
+    // ===== TMA producer: K, V of the key tile once; 64 queries of Q and dO per sub-step through the ring =====
     const bool leader = elect_one();
     uint32_t it = 0, tile_iter = 0;
     for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
@@ -418,21 +462,18 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int bx = 0; bx < C::kVB; ++bx)
           tma_load_4d(smem + C::kOffV + bx * kBoxBytes, &tmap_v, &bar.kv_full, bx * 64, kt * kT, h, b);
       }
-      for (int j = 0; j < p.nq; ++j, ++it) {
-        const uint32_t slot = it & 1u;
-        mbar_wait(&bar.qdo_empty[slot], ((it >> 1) & 1u) ^ 1u, 2);
+      for (int u = 0; u < 2 * p.nq; ++u, ++it) {
+        const uint32_t slot = it % C::kStages;
+        mbar_wait(&bar.qdo_empty[slot], ((it / C::kStages) & 1u) ^ 1u, 2);
         if (leader) {
           uint8_t* st = smem + C::kOffStage + slot * C::kStage;
-          mbar_arrive_expect_tx(&bar.qdo_full[slot], (uint32_t)(C::kStage + kStatsBytes));
+          mbar_arrive_expect_tx(&bar.qdo_full[slot], (uint32_t)C::kStage);
 #pragma unroll
           for (int bx = 0; bx < C::kQB; ++bx)
-            tma_load_4d(st + bx * kBoxBytes, &tmap_q, &bar.qdo_full[slot], bx * 64, j * kT, h, p.q_bcast ? 0 : b);
+            tma_load_4d(st + bx * kBox64, &tmap_q, &bar.qdo_full[slot], bx * 64, u * 64, h, p.q_bcast ? 0 : b);
 #pragma unroll
           for (int bx = 0; bx < C::kVB; ++bx)
-            tma_load_4d(st + C::kKBytes + bx * kBoxBytes, &tmap_do, &bar.qdo_full[slot], bx * 64, j * kT, h, b);
-          bulk_load_1d(smem + C::kOffStats + slot * kStatsBytes,
-                       reinterpret_cast<const uint8_t*>(p.stats) + ((size_t)bh * p.nq + (size_t)j) * kStatsBytes,
-                       kStatsBytes, &bar.qdo_full[slot]);
+            tma_load_4d(st + C::kQStage + bx * kBox64, &tmap_do, &bar.qdo_full[slot], bx * 64, u * 64, h, b);
         }
       }
     }
@@ -445,44 +486,46 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t tmem = bar.tmem_base;
     const uint64_t dK = make_smem_desc(smem_u32(smem + C::kOffK), 16, 1024);
     const uint64_t dV = make_smem_desc(smem_u32(smem + C::kOffV), 16, 1024);
-    auto stage_q = [&](uint32_t slot) { return smem_u32(smem + C::kOffStage + slot * C::kStage); };
-    // sub-step gu: stage slot (gu>>1)&1, query rows [64*(gu&1), +64) of the stage, TMEM set gu&1
+    auto stage_q = [&](uint32_t gu) { return smem_u32(smem + C::kOffStage + (gu % C::kStages) * C::kStage); };
+    // sub-step gu: ring slot gu % kStages (64 queries of Q, then of dO), TMEM set gu & 1
     auto issue_s = [&](uint32_t gu) {  // S^T = K Q^T
       if (leader) {
-        const uint64_t db = make_smem_desc(stage_q((gu >> 1) & 1u) + (gu & 1u) * 8192u, 16, 1024);
+        const uint64_t db = make_smem_desc(stage_q(gu), 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < DQK / 16; ++kk) {
-          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          mma_ss(tmem + (gu & 1u) * 128u, dK + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+          const uint64_t offa = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          const uint64_t offb = (uint64_t)(((kk >> 2) * kBox64 + (kk & 3) * 32) >> 4);
+          mma_ss(tmem + (gu & 1u) * 128u, dK + offa, db + offb, idesc_s, kk > 0 ? 1u : 0u);
         }
       }
     };
     auto issue_dp = [&](uint32_t gu) {  // dP^T = V dO^T
       if (leader) {
-        const uint64_t db = make_smem_desc(stage_q((gu >> 1) & 1u) + C::kKBytes + (gu & 1u) * 8192u, 16, 1024);
+        const uint64_t db = make_smem_desc(stage_q(gu) + C::kQStage, 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < DV / 16; ++kk) {
-          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          mma_ss(tmem + (gu & 1u) * 128u + 64u, dV + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+          const uint64_t offa = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          const uint64_t offb = (uint64_t)(((kk >> 2) * kBox64 + (kk & 3) * 32) >> 4);
+          mma_ss(tmem + (gu & 1u) * 128u + 64u, dV + offa, db + offb, idesc_s, kk > 0 ? 1u : 0u);
         }
       }
     };
     auto issue_dv = [&](uint32_t gu, bool acc) {  // dV += P^T(TMEM) dO   (dO read MN-major: 16 queries = 2048 bytes)
       if (leader) {
-        const uint64_t db = make_smem_desc(stage_q((gu >> 1) & 1u) + C::kKBytes, kBoxBytes, 1024);
+        const uint64_t db = make_smem_desc(stage_q(gu) + C::kQStage, kBox64, 1024);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           mma_ts(tmem + C::kColDV, tmem + (gu & 1u) * 128u + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8),
-                 db + (uint64_t)((((gu & 1u) * 4 + kk) * 2048) >> 4), idesc_dv, (acc || kk > 0) ? 1u : 0u);
+                 db + (uint64_t)((kk * 2048) >> 4), idesc_dv, (acc || kk > 0) ? 1u : 0u);
       }
     };
     auto issue_dk = [&](uint32_t gu, bool acc) {  // dK += dS^T(TMEM) Q
       if (leader) {
-        const uint64_t db = make_smem_desc(stage_q((gu >> 1) & 1u), kBoxBytes, 1024);
+        const uint64_t db = make_smem_desc(stage_q(gu), kBox64, 1024);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           mma_ts(tmem + C::kColDK, tmem + (gu & 1u) * 128u + 64u + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8),
-                 db + (uint64_t)((((gu & 1u) * 4 + kk) * 2048) >> 4), idesc_dk, (acc || kk > 0) ? 1u : 0u);
+                 db + (uint64_t)((kk * 2048) >> 4), idesc_dk, (acc || kk > 0) ? 1u : 0u);
       }
     };
     auto commit = [&](uint64_t* bp) {
@@ -493,34 +536,43 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint32_t g = 0, tile_iter = 0;
     for (int id = blockIdx.x; id < p.total_tiles; id += gridDim.x, ++tile_iter) {
       mbar_wait(&bar.kv_full, tile_iter & 1u, 3);
-      mbar_wait(&bar.qdo_full[(g >> 1) & 1u], (g >> 2) & 1u, 4);
-      tc_fence_after_sync();
-      issue_s(g);
-      commit(&bar.s_full[g & 1u]);
-      issue_dp(g);
-      commit(&bar.dp_full[g & 1u]);
+      // the scores of the first two sub-steps (one per TMEM set); U >= 2
+      for (uint32_t u0 = 0; u0 < 2; ++u0) {
+        const uint32_t gn = g + u0;
+        mbar_wait(&bar.qdo_full[gn % C::kStages], (gn / C::kStages) & 1u, 4);
+        tc_fence_after_sync();
+        issue_s(gn);
+        commit(&bar.s_full[gn & 1u]);
+        issue_dp(gn);
+        commit(&bar.dp_full[gn & 1u]);
+      }
+      if (U == 2) commit(&bar.kv_empty);
       for (int u = 0; u < U; ++u) {
         const uint32_t gu = g + (uint32_t)u, set = gu & 1u, par = (gu >> 1) & 1u;
-        if (u + 1 < U) {
-          const uint32_t gn = gu + 1;
-          if ((gn & 1u) == 0u) {
-            mbar_wait(&bar.qdo_full[(gn >> 1) & 1u], (gn >> 2) & 1u, 7);
-            tc_fence_after_sync();
-          }
-          issue_s(gn);
-          commit(&bar.s_full[gn & 1u]);
-          issue_dp(gn);
-          commit(&bar.dp_full[gn & 1u]);
-          if (u + 2 == U) commit(&bar.kv_empty);  // K and V are not read again for this key tile
-        }
+        const bool more = u + 2 < U;
         mbar_wait(&bar.p_ready[set], par, 5);
         if (u == 0) mbar_wait(&bar.acc_empty, (tile_iter & 1u) ^ 1u, 6);
         tc_fence_after_sync();
         issue_dv(gu, u > 0);
+        if (more) {
+          // S(u+2) goes into this set's S columns: the softmax warps have read S(u), and dV(u) — the reader of the P
+          // they stored there — is ahead of it in the in-order pipe.  Issuing it here rather than after dK(u) gives
+          // the owners of this set their next scores half a sub-step earlier (measured: -2 %).
+          const uint32_t gn = gu + 2;
+          mbar_wait(&bar.qdo_full[gn % C::kStages], (gn / C::kStages) & 1u, 7);
+          tc_fence_after_sync();
+          issue_s(gn);
+          commit(&bar.s_full[set]);
+        }
         mbar_wait(&bar.ds_ready[set], par, 8);
         tc_fence_after_sync();
         issue_dk(gu, u > 0);
-        if (gu & 1u) commit(&bar.qdo_empty[(gu >> 1) & 1u]);
+        commit(&bar.qdo_empty[gu % C::kStages]);
+        if (more) {
+          issue_dp(gu + 2);  // over dS(u), which dK(u) has just been queued to read
+          commit(&bar.dp_full[set]);
+          if (u + 3 == U) commit(&bar.kv_empty);  // K and V are not read again for this key tile
+        }
       }
       commit(&bar.acc_full);
       g += (uint32_t)U;
@@ -542,20 +594,25 @@ template <int DQK, int DV>
 struct Cfg2 {
   static constexpr int kQB = DQK / 64, kVB = DV / 64;
   static constexpr int kKBytes = kQB * kBoxBytes, kVBytes = kVB * kBoxBytes;
-  static constexpr int kStage = kKBytes + kVBytes;  // K_t then V_t
-  static constexpr int kStages = 2;
+  // K_t is read by S(t) and again by dQ(t); V_t only by dP(t): separate rings, so that a V slot is refilled as soon as
+  // dP has consumed it.  The load of a slot is issued when its previous tile retires, i.e. (stages - 1) tiles ahead:
+  // 3 K stages + 2 V stages hide the ~2 us L2 round trip of a tile (2 + 2 measured 3.6k cycles per tile, MMA 1.5k).
+  static constexpr int kKS = 3;
+  static constexpr int kAvail = 232448 - 1024 - 512 - (kKBytes + kVBytes) - kKS * kKBytes;
+  static constexpr int kVS = kAvail / kVBytes >= 3 ? 3 : 2;
   static constexpr int kOffQ = 0;
   static constexpr int kOffDO = kKBytes;
-  static constexpr int kOffRing = kKBytes + kVBytes;
-  static constexpr int kOffBar = kOffRing + kStages * kStage;
-  static constexpr int kNeed = kOffBar + 256 + 1024;
+  static constexpr int kOffKRing = kKBytes + kVBytes;
+  static constexpr int kOffVRing = kOffKRing + kKS * kKBytes;
+  static constexpr int kOffBar = kOffVRing + kVS * kVBytes;
+  static constexpr int kNeed = kOffBar + 512 + 1024;
   static constexpr int kSmem = kNeed > 120 * 1024 ? kNeed : 120 * 1024;
   static constexpr uint32_t kColS = 0, kColP = 128, kColDQ = 384;
 };
 
 struct Bars2 {
   uint64_t q_full;
-  uint64_t kv_full[2], kv_empty[2];
+  uint64_t k_full[3], k_empty[3], v_full[3], v_empty[3];
   uint64_t s_full, dp_full[2], s_free, ds_ready;
   uint64_t dq_full;
   uint32_t tmem_base;
@@ -578,7 +635,15 @@ __device__ __forceinline__ void dq_tile(Bars2& bar, uint32_t i_t, uint32_t tS, u
 #pragma unroll
   for (int i = 0; i < 64; i += 2) {
     const float2 x = fma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nl2);
-    float p0 = ex2(x.x), p1 = ex2(x.y);
+    float p0, p1;
+    if (kPolyEvery > 0 && ((i >> 1) % kPolyEvery) == kPolyEvery - 1) {
+      const float2 e = exp2_poly2_fast(x);
+      p0 = e.x;
+      p1 = e.y;
+    } else {
+      p0 = ex2(x.x);
+      p1 = ex2(x.y);
+    }
     if (MASKED) {
       const uint32_t word = i < 32 ? w0 : w1;
       if (((word >> (i & 31)) & 1u) || i > cmax) p0 = fillp;
@@ -627,8 +692,8 @@ __device__ __forceinline__ void softmax_dq(const BwdParams& p, Bars2& bar, int w
   const uint32_t lanef = (uint32_t)(quarter * 32) << 16;
   const uint32_t tS = bar.tmem_base + lanef + C::kColS + (uint32_t)(half * 64);
   const uint32_t tP0 = bar.tmem_base + lanef + C::kColP + (uint32_t)(half * 64);
-  const float* blk = p.stats + (((size_t)b * p.H + h) * p.nq + (size_t)j) * (kStatsBytes / 4);
-  const float nlse = blk[stat_nlse_idx(r)], delta = blk[stat_delta_idx(r)], fillp = blk[stat_fillp_idx(r)];
+  const float* blk = p.stats + (((size_t)b * p.H + h) * (2 * p.nq) + (size_t)(nrow >> 6)) * (kStatsBytes / 4);
+  const float nlse = blk[stat_nlse_idx(r & 63)], delta = blk[stat_delta_idx(r & 63)], fillp = blk[stat_fillp_idx(r & 63)];
 
   for (int t = t0; t < t1; ++t) {
     const uint32_t i_t = (uint32_t)(t - t0);
@@ -701,11 +766,14 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   if (threadIdx.x == 0) {
     mbar_init(&bar.q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar.kv_full[i], 1);
-      mbar_init(&bar.kv_empty[i], 1);
-      mbar_init(&bar.dp_full[i], 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bar.k_full[i], 1);
+      mbar_init(&bar.k_empty[i], 1);
+      mbar_init(&bar.v_full[i], 1);
+      mbar_init(&bar.v_empty[i], 1);
     }
+    mbar_init(&bar.dp_full[0], 1);
+    mbar_init(&bar.dp_full[1], 1);
     mbar_init(&bar.s_full, 1);
     mbar_init(&bar.s_free, 8);
     mbar_init(&bar.ds_ready, 8);
@@ -744,18 +812,28 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       for (int bx = 0; bx < C::kVB; ++bx)
         tma_load_4d(smem + C::kOffDO + bx * kBoxBytes, &tmap_do, &bar.q_full, bx * 64, j * kT, h, b);
     }
-    for (int t = t0; t < t1; ++t) {
-      const uint32_t it = (uint32_t)(t - t0), slot = it & 1u;
-      mbar_wait(&bar.kv_empty[slot], ((it >> 1) & 1u) ^ 1u, 10);
+    for (int t = t0; t < t1; ++t) {  // K ring
+      const uint32_t it = (uint32_t)(t - t0), slot = it % C::kKS;
+      mbar_wait(&bar.k_empty[slot], ((it / C::kKS) & 1u) ^ 1u, 10);
       if (leader) {
-        uint8_t* st = smem + C::kOffRing + slot * C::kStage;
-        mbar_arrive_expect_tx(&bar.kv_full[slot], (uint32_t)C::kStage);
+        uint8_t* st = smem + C::kOffKRing + slot * C::kKBytes;
+        mbar_arrive_expect_tx(&bar.k_full[slot], (uint32_t)C::kKBytes);
 #pragma unroll
         for (int bx = 0; bx < C::kQB; ++bx)
-          tma_load_4d(st + bx * kBoxBytes, &tmap_k, &bar.kv_full[slot], bx * 64, t * kT, h, b);
+          tma_load_4d(st + bx * kBoxBytes, &tmap_k, &bar.k_full[slot], bx * 64, t * kT, h, b);
+      }
+    }
+  } else if (warp == kTmaWarp + 2) {  // V ring: its own warp, so that a full K ring never delays a V load
+    const bool leader = elect_one();
+    for (int t = t0; t < t1; ++t) {
+      const uint32_t it = (uint32_t)(t - t0), slot = it % C::kVS;
+      mbar_wait(&bar.v_empty[slot], ((it / C::kVS) & 1u) ^ 1u, 16);
+      if (leader) {
+        uint8_t* st = smem + C::kOffVRing + slot * C::kVBytes;
+        mbar_arrive_expect_tx(&bar.v_full[slot], (uint32_t)C::kVBytes);
 #pragma unroll
         for (int bx = 0; bx < C::kVB; ++bx)
-          tma_load_4d(st + C::kKBytes + bx * kBoxBytes, &tmap_v, &bar.kv_full[slot], bx * 64, t * kT, h, b);
+          tma_load_4d(st + bx * kBoxBytes, &tmap_v, &bar.v_full[slot], bx * 64, t * kT, h, b);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -765,10 +843,11 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const uint32_t tmem = bar.tmem_base;
     const uint64_t dQ = make_smem_desc(smem_u32(smem + C::kOffQ), 16, 1024);
     const uint64_t dDO = make_smem_desc(smem_u32(smem + C::kOffDO), 16, 1024);
-    auto ring = [&](uint32_t slot) { return smem_u32(smem + C::kOffRing + slot * C::kStage); };
-    auto issue_s = [&](uint32_t slot) {  // S = Q_j K_t^T
+    auto kring = [&](uint32_t i) { return smem_u32(smem + C::kOffKRing + (i % C::kKS) * C::kKBytes); };
+    auto vring = [&](uint32_t i) { return smem_u32(smem + C::kOffVRing + (i % C::kVS) * C::kVBytes); };
+    auto issue_s = [&](uint32_t i) {  // S = Q_j K_t^T
       if (leader) {
-        const uint64_t db = make_smem_desc(ring(slot), 16, 1024);
+        const uint64_t db = make_smem_desc(kring(i), 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < DQK / 16; ++kk) {
           const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
@@ -776,9 +855,9 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
       }
     };
-    auto issue_dp = [&](uint32_t i) {  // dP = dO_j V_t^T into dP buffer i & 1 (K/V ring slot i & 1)
+    auto issue_dp = [&](uint32_t i) {  // dP = dO_j V_t^T into dP buffer i & 1
       if (leader) {
-        const uint64_t db = make_smem_desc(ring(i & 1u) + C::kKBytes, 16, 1024);
+        const uint64_t db = make_smem_desc(vring(i), 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < DV / 16; ++kk) {
           const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
@@ -788,7 +867,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     };
     auto issue_dq = [&](uint32_t i, bool acc) {  // dQ += dS(TMEM) K_t   (K_t read MN-major)
       if (leader) {
-        const uint64_t db = make_smem_desc(ring(i & 1u), kBoxBytes, 1024);
+        const uint64_t db = make_smem_desc(kring(i), kBoxBytes, 1024);
 #pragma unroll
         for (int kk = 0; kk < kT / 16; ++kk)
           mma_ts(tmem + C::kColDQ, tmem + C::kColP + (i & 1u) * 128u + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
@@ -801,27 +880,34 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
     const int nt = t1 - t0;
     mbar_wait(&bar.q_full, 0u, 11);
-    mbar_wait(&bar.kv_full[0], 0u, 12);
+    mbar_wait(&bar.k_full[0], 0u, 12);
     tc_fence_after_sync();
     issue_s(0);
     commit(&bar.s_full);
+    mbar_wait(&bar.v_full[0], 0u, 17);
+    tc_fence_after_sync();
     issue_dp(0);
     commit(&bar.dp_full[0]);
+    commit(&bar.v_empty[0]);
     for (int i = 0; i < nt; ++i) {
       const uint32_t ui = (uint32_t)i;
       if (i + 1 < nt) {
+        const uint32_t un = ui + 1;
         mbar_wait(&bar.s_free, ui & 1u, 13);  // S_i is in the softmax warps' registers
-        mbar_wait(&bar.kv_full[(ui + 1) & 1u], ((ui + 1) >> 1) & 1u, 14);
+        mbar_wait(&bar.k_full[un % C::kKS], (un / C::kKS) & 1u, 14);
         tc_fence_after_sync();
-        issue_s((ui + 1) & 1u);
+        issue_s(un);
         commit(&bar.s_full);
-        issue_dp(ui + 1);  // the other dP buffer: its dS was consumed by dQ(i-1), issued before
-        commit(&bar.dp_full[(ui + 1) & 1u]);
+        mbar_wait(&bar.v_full[un % C::kVS], (un / C::kVS) & 1u, 18);
+        tc_fence_after_sync();
+        issue_dp(un);  // the other dP buffer: its dS was consumed by dQ(i-1), issued before
+        commit(&bar.dp_full[un & 1u]);
+        commit(&bar.v_empty[un % C::kVS]);
       }
       mbar_wait(&bar.ds_ready, ui & 1u, 15);
       tc_fence_after_sync();
       issue_dq(ui, i > 0);
-      commit(&bar.kv_empty[ui & 1u]);
+      commit(&bar.k_empty[ui % C::kKS]);
     }
     commit(&bar.dq_full);
   }
@@ -852,13 +938,13 @@ PFN_cuTensorMapEncodeTiled_v12000 bwd_encode_fn() {
 
 // (channels, rows, heads, batch) view of a (batch, rows, heads*channels)-style tensor; box = 64 x 128 x 1 x 1
 int bwd_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int rows, int heads, int batch,
-             int64_t stride_row, int64_t stride_head, int64_t stride_batch) {
+             int64_t stride_row, int64_t stride_head, int64_t stride_batch, int box_rows = kT) {
   auto fn = bwd_encode_fn();
   PCV_REQUIRE(fn != nullptr, PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)batch};
   if (stride_batch == 0) stride_batch = (int64_t)rows * stride_row;
   cuuint64_t strides[3] = {(cuuint64_t)stride_row * 2, (cuuint64_t)stride_head * 2, (cuuint64_t)stride_batch * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)kT, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapDataType dt = dtype == PCV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = fn(tm, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -882,7 +968,7 @@ BwdLayout bwd_layout(const pcv_attn_bwd_params& a) {
   L.wpr = L.nk * 4;
   L.Bq = a.q_stride_b == 0 ? 1 : a.B;
   L.off_stats = 0;
-  L.off_dq32 = align256((size_t)kStatsBytes * a.B * a.H * L.nq);
+  L.off_dq32 = align256((size_t)kStatsBytes * a.B * a.H * 2 * L.nq);
   L.off_pad = L.off_dq32 + align256(sizeof(float) * (size_t)L.Bq * a.N * a.H * a.dqk);
   L.total = L.off_pad + (a.pad_mask != nullptr ? align256(sizeof(uint32_t) * (size_t)a.B * L.wpr) : 0);
   return L;
@@ -890,7 +976,8 @@ BwdLayout bwd_layout(const pcv_attn_bwd_params& a) {
 
 template <int DQK, int DV, bool BF16>
 int launch_bwd_kernels(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                       const BwdParams& p, int sms, cudaStream_t stream) {
+                       const CUtensorMap& tq64, const CUtensorMap& tdo64, const BwdParams& p, int sms,
+                       cudaStream_t stream) {
   using C1 = Cfg1<DQK, DV>;
   using C2 = Cfg2<DQK, DV>;
   auto k1 = bwd_dkdv_kernel<DQK, DV, BF16>;
@@ -899,7 +986,7 @@ int launch_bwd_kernels(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   PCV_CHECK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, C1::kSmem));
   PCV_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmem));
   const int grid1 = std::min(p.total_tiles, sms);
-  k1<<<grid1, kThreads, C1::kSmem, stream>>>(tq, tk, tv, tdo, p);
+  k1<<<grid1, kThreads, C1::kSmem, stream>>>(tq64, tk, tv, tdo64, p);
   PCV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   const int grid2 = p.B * p.H * p.nq * p.splits;
@@ -972,6 +1059,12 @@ int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
   p.dk_sb = a.gk_stride_b; p.dk_sm = a.gk_stride_m; p.dk_sh = a.gk_stride_h;
   p.dv_sb = a.gv_stride_b; p.dv_sm = a.gv_stride_m; p.dv_sh = a.gv_stride_h;
   p.total_tiles = a.B * a.H * L.nk;
+  {
+    const int64_t st[] = {a.gk_stride_b, a.gk_stride_m, a.gk_stride_h, a.gv_stride_b, a.gv_stride_m, a.gv_stride_h};
+    bool wide = ((reinterpret_cast<uintptr_t>(a.grad_k) | reinterpret_cast<uintptr_t>(a.grad_v)) & 31u) == 0;
+    for (int64_t x : st) wide = wide && (x % 16 == 0);
+    p.wide_store = wide ? 1 : 0;
+  }
   // dq kernel: aim at ~64 key tiles per CTA (launch + Q/dO load amortised) but at least ~4 CTAs per SM in total
   {
     const int units = a.B * a.H * L.nq;
@@ -1011,7 +1104,7 @@ int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
     p.pad_wpr = L.wpr;
   }
 
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tq64, tdo64;
   int rc = bwd_tmap(&tq, a.q, a.dtype, a.dqk, a.N, a.H, L.Bq, a.q_stride_n, a.q_stride_h, a.q_stride_b);
   if (rc != PCV_OK) return rc;
   rc = bwd_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b);
@@ -1020,13 +1113,17 @@ int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
   if (rc != PCV_OK) return rc;
   rc = bwd_tmap(&tdo, a.grad_out, a.dtype, a.dv, a.N, a.H, a.B, a.go_stride_n, a.go_stride_h, a.go_stride_b);
   if (rc != PCV_OK) return rc;
+  rc = bwd_tmap(&tq64, a.q, a.dtype, a.dqk, a.N, a.H, L.Bq, a.q_stride_n, a.q_stride_h, a.q_stride_b, 64);
+  if (rc != PCV_OK) return rc;
+  rc = bwd_tmap(&tdo64, a.grad_out, a.dtype, a.dv, a.N, a.H, a.B, a.go_stride_n, a.go_stride_h, a.go_stride_b, 64);
+  if (rc != PCV_OK) return rc;
 
   const bool bf16 = a.dtype == PCV_BF16;
   const int DQK = a.dqk <= 64 ? 64 : 128, DV = a.dv <= 64 ? 64 : 128;
 #define PCV_BWD_CASE(dq_, dv_)                                                                              \
   if (DQK == dq_ && DV == dv_)                                                                              \
-    rc = bf16 ? launch_bwd_kernels<dq_, dv_, true>(tq, tk, tv, tdo, p, sms, stream)                         \
-              : launch_bwd_kernels<dq_, dv_, false>(tq, tk, tv, tdo, p, sms, stream);
+    rc = bf16 ? launch_bwd_kernels<dq_, dv_, true>(tq, tk, tv, tdo, tq64, tdo64, p, sms, stream)            \
+              : launch_bwd_kernels<dq_, dv_, false>(tq, tk, tv, tdo, tq64, tdo64, p, sms, stream);
   PCV_BWD_CASE(64, 64)
   PCV_BWD_CASE(64, 128)
   PCV_BWD_CASE(128, 64)
