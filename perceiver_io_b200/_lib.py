@@ -41,6 +41,10 @@ EXPORTS = (
     "pcv_attn_bwd_supported",
     "pcv_attn_bwd_workspace_bytes",
     "pcv_attn_bwd",
+    "pcv_attn_fwd_dropout_supported",
+    "pcv_attn_fwd_dropout_workspace_bytes",
+    "pcv_attn_fwd_dropout",
+    "pcv_attn_dropout_mask",
     "pcv_launch_count",
     "pcv_debug_plan",
     "pcv_profile_begin",
@@ -254,6 +258,16 @@ def lib() -> C.CDLL:
         l.pcv_attn_bwd_workspace_bytes.restype = C.c_int
         l.pcv_attn_bwd.argtypes = [C.POINTER(AttnBwdParams), C.c_void_p]
         l.pcv_attn_bwd.restype = C.c_int
+        l.pcv_attn_fwd_dropout_supported.argtypes = [C.POINTER(AttnParams), C.c_float]
+        l.pcv_attn_fwd_dropout_supported.restype = C.c_int
+        l.pcv_attn_fwd_dropout_workspace_bytes.argtypes = [C.POINTER(AttnParams), C.POINTER(C.c_size_t)]
+        l.pcv_attn_fwd_dropout_workspace_bytes.restype = C.c_int
+        l.pcv_attn_fwd_dropout.argtypes = [C.POINTER(AttnParams), C.c_void_p, C.c_void_p, C.c_float, C.c_uint64,
+                                           C.c_void_p]
+        l.pcv_attn_fwd_dropout.restype = C.c_int
+        l.pcv_attn_dropout_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                            C.c_uint64, C.c_void_p]
+        l.pcv_attn_dropout_mask.restype = C.c_int
         l.pcv_debug_plan.argtypes = [C.c_int32] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
         l.pcv_debug_plan.restype = C.c_int
         for name in ("pcv_get_device_info", "pcv_attn_supported_tcgen05", "pcv_attn_workspace_bytes",

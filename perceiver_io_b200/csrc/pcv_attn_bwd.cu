@@ -30,6 +30,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -67,9 +68,64 @@ struct BwdParams {
   void* dv_out;
   int64_t dk_sb, dk_sm, dk_sh, dv_sb, dv_sm, dv_sh;
   int wide_store;            // dk / dv rows are 32-byte aligned: 256-bit stores
+  uint32_t drop_thresh;      // attention dropout: element kept iff its random byte >= drop_thresh (0 = no dropout)
+  uint32_t seed_lo, seed_hi;
+  float drop_rp;             // 1 / (1 - drop_thresh / 256)
+  float* o32;                // forward-with-dropout kernel: (B, N, H*dv) fp32 accumulation buffer
   int total_tiles;           // dkdv kernel: B*H*nk
   int splits, tiles_per_split;  // dq kernel
 };
+
+// ---- attention-probability dropout (modules.py:161: nn.Dropout on the softmax output) -----------------------------
+// Counter-based: the keep decision of element (b, h, query q, key k) is a pure function of (seed, b*H+h, q, k), so the
+// forward kernel and both backward kernels regenerate the same mask without storing it.  One 32-bit murmur3 hash per
+// 2 x 2 block (query pair q>>1, key pair k>>1) yields four random bytes, byte (q&1)*2 + (k&1) belongs to (q, k); an
+// element is dropped iff its byte < drop_thresh, i.e. with probability drop_thresh/256 (the requested p rounded to
+// 1/256; the survivors are scaled by exactly 1/(1 - drop_thresh/256)).  A thread that walks keys (query fixed) or
+// queries (key fixed) needs one hash per two columns either way.
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+__device__ __forceinline__ uint32_t drop_qword(uint32_t bh, uint32_t q) { return bh * 0x9E3779B1u + (q >> 1); }
+// murmur3 block mix of one 32-bit word
+__device__ __forceinline__ uint32_t drop_mixk(uint32_t k) {
+  k *= 0xCC9E2D51u;
+  k = rotl32(k, 15);
+  return k * 0x1B873593u;
+}
+__device__ __forceinline__ uint32_t drop_mixh(uint32_t h, uint32_t mixed_k) {
+  h ^= mixed_k;
+  h = rotl32(h, 13);
+  return h * 5u + 0xE6546B64u;
+}
+// hash of (seed_lo; block 1 = qword; block 2 = (k >> 1) ^ seed_hi), given h1 = drop_mixh(seed_lo, drop_mixk(qword)) and
+// mk = drop_mixk((k >> 1) ^ seed_hi): the per-thread constant half is hoisted by the callers
+__device__ __forceinline__ uint32_t drop_finish(uint32_t h1, uint32_t mk) {
+  uint32_t h = drop_mixh(h1, mk);
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint32_t drop_bits(uint32_t seed_lo, uint32_t seed_hi, uint32_t bh, uint32_t q, uint32_t k) {
+  return drop_finish(drop_mixh(seed_lo, drop_mixk(drop_qword(bh, q))), drop_mixk((k >> 1) ^ seed_hi));
+}
+__device__ __forceinline__ bool drop_keep(uint32_t bits, uint32_t q, uint32_t k, uint32_t thresh) {
+  return ((bits >> (((q & 1u) * 2u + (k & 1u)) * 8u)) & 0xffu) >= thresh;
+}
+
+// keep mask of a whole problem (tests / debugging): keep[b][h][q][k] = 1 if the element survives
+__global__ void __launch_bounds__(256) drop_mask_kernel(uint8_t* __restrict__ keep, int B, int H, int N, int M,
+                                                        uint32_t thresh, uint32_t seed_lo, uint32_t seed_hi) {
+  const int64_t total = (int64_t)B * H * N * M;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = (uint32_t)(idx % M);
+    const int64_t r = idx / M;
+    const uint32_t q = (uint32_t)(r % N), bh = (uint32_t)(r / N);
+    keep[idx] = drop_keep(drop_bits(seed_lo, seed_hi, bh, q, k), q, k, thresh) ? 1 : 0;
+  }
+}
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi, bool bf16) {
   uint32_t r;
@@ -153,7 +209,8 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const T* __restrict__ out
     const T* o = out + b * o_sb + (int64_t)n * o_sn + h * o_sh;
     const T* g = dout + b * g_sb + (int64_t)n * g_sn + h * g_sh;
     float acc = 0.f;
-    for (int c = lane; c < dv; c += 32) acc += Elem<T>::to_f(o[c]) * Elem<T>::to_f(g[c]);
+    if (dout != nullptr)
+      for (int c = lane; c < dv; c += 32) acc += Elem<T>::to_f(o[c]) * Elem<T>::to_f(g[c]);
     delta = warp_sum(acc);
     const int64_t r = bh * N + n;
     const float m = stat_m[r], l = stat_l[r];
@@ -238,13 +295,17 @@ struct Bars1 {
 // One sub-step of one thread: key row (TMEM lane) x all 64 query columns, in two passes of 32.  MASKED: some score of
 // the CTA's tile is filled / out of range (padding keys, causal diagonal, ragged last key tile).
 //   st: the 32 float4 {nlse, nlse, delta, delta} of the sub-step's 64 queries; fp: their 64 fill probabilities.
-template <bool BF16, bool MASKED>
+// DROP: attention dropout; `dq0` = drop_qword of the sub-step's first query, `dmk` = drop_mixk of this thread's key pair,
+// `ksh` = bit offset of the key's byte within a query's half of the hash (8 * (key & 1)).
+template <bool BF16, bool MASKED, bool DROP>
 __device__ __forceinline__ void dkdv_substep(Bars1& bar, uint32_t set, uint32_t par, uint32_t tS, uint32_t tP,
                                              const float* st, const float* fp, float scale_log2, bool row_filled,
-                                             bool oob, int nfill) {
+                                             bool oob, int nfill, const BwdParams& p, uint32_t dq0, uint32_t dmk,
+                                             uint32_t ksh) {
   const float4* st4 = reinterpret_cast<const float4*>(st);
   const float2 sc2 = make_float2(scale_log2, scale_log2);
   float pf[64];
+  uint32_t keepm[2] = {0u, 0u};  // DROP: bit i of keepm[hh] = column hh*32 + i survives
   mbar_wait(&bar.s_full[set], par, 21);
   tc_fence_after_sync();
 #pragma unroll
@@ -278,6 +339,16 @@ __device__ __forceinline__ void dkdv_substep(Bars1& bar, uint32_t set, uint32_t 
       }
       pf[hh * 32 + i] = p0;
       pf[hh * 32 + i + 1] = p1;
+      if (DROP) {  // dV sees the dropped-out, rescaled probabilities; dS below the plain ones
+        const uint32_t bits =
+            drop_finish(drop_mixh(p.seed_lo, drop_mixk(dq0 + (uint32_t)(hh * 16 + (i >> 1)))), dmk);
+        const bool k0 = ((bits >> ksh) & 0xffu) >= p.drop_thresh;
+        const bool k1 = ((bits >> (ksh + 16u)) & 0xffu) >= p.drop_thresh;
+        keepm[hh] |= (k0 ? 1u : 0u) << i;
+        keepm[hh] |= (k1 ? 1u : 0u) << (i + 1);
+        p0 = k0 ? p0 * p.drop_rp : 0.f;
+        p1 = k1 ? p1 * p.drop_rp : 0.f;
+      }
       pk[i >> 1] = pack2(p0, p1, BF16);
     }
     tmem_st16(tS + hh * 32, pk);  // P^T (16-bit) over the first 16 of each 32 S^T columns
@@ -302,7 +373,12 @@ __device__ __forceinline__ void dkdv_substep(Bars1& bar, uint32_t set, uint32_t 
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const float2 t = sub2(make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1])), de[i >> 1]);
+      float2 dp = make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1]));
+      if (DROP) {  // gradient through the dropout: kept elements carry dP / (1 - p), dropped ones nothing
+        dp.x = ((keepm[hh] >> i) & 1u) ? dp.x * p.drop_rp : 0.f;
+        dp.y = ((keepm[hh] >> (i + 1)) & 1u) ? dp.y * p.drop_rp : 0.f;
+      }
+      const float2 t = sub2(dp, de[i >> 1]);
       float2 g = mul2(make_float2(pf[hh * 32 + i], pf[hh * 32 + i + 1]), t);
       if (MASKED) {  // a filled score is a constant: no gradient through it
         if (row_filled || oob || hh * 32 + i < nfill) g.x = 0.f;
@@ -347,12 +423,20 @@ __device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uin
       const float* fp = blk + 128;               // fill probabilities of the 64 columns
       const uint32_t tS = tbase + set * 128u, tP = tS + 64u;
       const bool masked = tile_masked || (p.causal && (kt * kT + kT - 1 > u * 64 + p.cshift));
-      if (!masked) {
-        dkdv_substep<BF16, false>(bar, set, par, tS, tP, st, fp, p.scale_log2, false, false, 0);
+      int nfill = 0;  // leading columns (queries) for which this key is causally hidden
+      if (masked && p.causal) nfill = min(max(key - p.cshift - q0, 0), 64);
+      if (p.drop_thresh == 0u) {
+        if (!masked)
+          dkdv_substep<BF16, false, false>(bar, set, par, tS, tP, st, fp, p.scale_log2, false, false, 0, p, 0u, 0u, 0u);
+        else
+          dkdv_substep<BF16, true, false>(bar, set, par, tS, tP, st, fp, p.scale_log2, pad, oob, nfill, p, 0u, 0u, 0u);
       } else {
-        int nfill = 0;  // leading columns (queries) for which this key is causally hidden
-        if (p.causal) nfill = min(max(key - p.cshift - q0, 0), 64);
-        dkdv_substep<BF16, true>(bar, set, par, tS, tP, st, fp, p.scale_log2, pad, oob, nfill);
+        const uint32_t dq0 = drop_qword((uint32_t)bh, (uint32_t)q0);
+        const uint32_t dmk = drop_mixk(((uint32_t)key >> 1) ^ p.seed_hi), ksh = ((uint32_t)key & 1u) * 8u;
+        if (!masked)
+          dkdv_substep<BF16, false, true>(bar, set, par, tS, tP, st, fp, p.scale_log2, false, false, 0, p, dq0, dmk, ksh);
+        else
+          dkdv_substep<BF16, true, true>(bar, set, par, tS, tP, st, fp, p.scale_log2, pad, oob, nfill, p, dq0, dmk, ksh);
       }
     }
     g += (uint32_t)U;
@@ -619,10 +703,11 @@ struct Bars2 {
 };
 
 // one key tile of one thread: query row (TMEM lane) x 64 key columns
-template <bool BF16, bool MASKED>
+// DROP: `dh1` = this query's half of the dropout hash, `qsh` = 16 * (query & 1), `k0` = first key of the 64 columns
+template <bool BF16, bool MASKED, bool DROP>
 __device__ __forceinline__ void dq_tile(Bars2& bar, uint32_t i_t, uint32_t tS, uint32_t tP, float scale_log2,
                                         float nlse, float delta, float fillp, uint32_t w0, uint32_t w1, int cmax,
-                                        int oob_from) {
+                                        int oob_from, const BwdParams& p, uint32_t dh1, uint32_t qsh, uint32_t k0) {
   const float2 sc2 = make_float2(scale_log2, scale_log2), nl2 = make_float2(nlse, nlse), de2 = make_float2(delta, delta);
   uint32_t s[64];
   mbar_wait(&bar.s_full, i_t & 1u, 30);
@@ -665,7 +750,13 @@ __device__ __forceinline__ void dq_tile(Bars2& bar, uint32_t i_t, uint32_t tS, u
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 64; i += 2) {
-      const float2 t = sub2(make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1])), de2);
+      float2 dp = make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1]));
+      if (DROP) {
+        const uint32_t bits = drop_finish(dh1, drop_mixk(((k0 + (uint32_t)i) >> 1) ^ p.seed_hi));
+        dp.x = (((bits >> qsh) & 0xffu) >= p.drop_thresh) ? dp.x * p.drop_rp : 0.f;
+        dp.y = (((bits >> (qsh + 8u)) & 0xffu) >= p.drop_thresh) ? dp.y * p.drop_rp : 0.f;
+      }
+      const float2 t = sub2(dp, de2);
       float2 g = mul2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), t);
       if (MASKED) {
         const uint32_t word = i < 32 ? w0 : w1;
@@ -694,6 +785,9 @@ __device__ __forceinline__ void softmax_dq(const BwdParams& p, Bars2& bar, int w
   const uint32_t tP0 = bar.tmem_base + lanef + C::kColP + (uint32_t)(half * 64);
   const float* blk = p.stats + (((size_t)b * p.H + h) * (2 * p.nq) + (size_t)(nrow >> 6)) * (kStatsBytes / 4);
   const float nlse = blk[stat_nlse_idx(r & 63)], delta = blk[stat_delta_idx(r & 63)], fillp = blk[stat_fillp_idx(r & 63)];
+  // dropout: this query's half of the hash and the bit offset of its two bytes within a key pair's hash
+  const uint32_t dh1 = drop_mixh(p.seed_lo, drop_mixk(drop_qword((uint32_t)(b * p.H + h), (uint32_t)nrow)));
+  const uint32_t qsh = ((uint32_t)nrow & 1u) * 16u;
 
   for (int t = t0; t < t1; ++t) {
     const uint32_t i_t = (uint32_t)(t - t0);
@@ -708,12 +802,21 @@ __device__ __forceinline__ void softmax_dq(const BwdParams& p, Bars2& bar, int w
       tile_masked = tile_masked || ((mw.x | mw.y | mw.z | mw.w) != 0u);
     }
     const bool masked = tile_masked || (p.causal && (t * kT + kT - 1 > j * kT + p.cshift));
-    if (!masked) {
-      dq_tile<BF16, false>(bar, i_t, tS, tP, p.scale_log2, nlse, delta, fillp, 0u, 0u, 0, 0);
+    const int cmax = p.causal ? (nrow + p.cshift - k0) : 0x7fffffff;  // column i filled iff i > cmax
+    const int oob_from = p.M - k0;                                   // column i beyond the tensor iff i >= oob_from
+    if (p.drop_thresh == 0u) {
+      if (!masked)
+        dq_tile<BF16, false, false>(bar, i_t, tS, tP, p.scale_log2, nlse, delta, fillp, 0u, 0u, 0, 0, p, 0u, 0u, 0u);
+      else
+        dq_tile<BF16, true, false>(bar, i_t, tS, tP, p.scale_log2, nlse, delta, fillp, w0, w1, cmax, oob_from, p, 0u,
+                                   0u, 0u);
     } else {
-      const int cmax = p.causal ? (nrow + p.cshift - k0) : 0x7fffffff;  // column i filled iff i > cmax
-      const int oob_from = p.M - k0;                                   // column i beyond the tensor iff i >= oob_from
-      dq_tile<BF16, true>(bar, i_t, tS, tP, p.scale_log2, nlse, delta, fillp, w0, w1, cmax, oob_from);
+      if (!masked)
+        dq_tile<BF16, false, true>(bar, i_t, tS, tP, p.scale_log2, nlse, delta, fillp, 0u, 0u, 0, 0, p, dh1, qsh,
+                                   (uint32_t)k0);
+      else
+        dq_tile<BF16, true, true>(bar, i_t, tS, tP, p.scale_log2, nlse, delta, fillp, w0, w1, cmax, oob_from, p, dh1,
+                                  qsh, (uint32_t)k0);
     }
   }
 
@@ -921,6 +1024,269 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// kernel 3: forward WITH attention dropout (training).  The fused inference/forward kernel has already produced the row
+// statistics; this pass recomputes S = Q K^T per tile, forms the NORMALISED probabilities 2^(t + nlse) directly (no
+// running maximum: partial sums over key ranges simply add), applies the counter-based dropout mask and accumulates
+// O += dropout(P) V.  Same skeleton as the dQ kernel: query-tile outer, K and V through their own TMA rings, S double
+// buffered in TMEM (P overwrites its S), one fp32 vector reduction per output element per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+template <int DQK, int DV>
+struct Cfg3 {
+  static constexpr int kQB = DQK / 64, kVB = DV / 64;
+  static constexpr int kKBytes = kQB * kBoxBytes, kVBytes = kVB * kBoxBytes;
+  static constexpr int kKS = 3;
+  static constexpr int kAvail = 232448 - 1024 - 512 - kKBytes - kKS * kKBytes;
+  static constexpr int kVS = kAvail / kVBytes >= 3 ? 3 : 2;
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffKRing = kKBytes;
+  static constexpr int kOffVRing = kOffKRing + kKS * kKBytes;
+  static constexpr int kOffBar = kOffVRing + kVS * kVBytes;
+  static constexpr int kNeed = kOffBar + 512 + 1024;
+  static constexpr int kSmem = kNeed > 120 * 1024 ? kNeed : 120 * 1024;
+  static constexpr uint32_t kColO = 256;  // S buffers at 0 and 128
+};
+
+struct Bars3 {
+  uint64_t q_full;
+  uint64_t k_full[3], k_empty[3], v_full[3], v_empty[3];
+  uint64_t s_full[2], p_ready[2];
+  uint64_t o_full;
+  uint32_t tmem_base;
+};
+
+template <bool BF16, bool MASKED>
+__device__ __forceinline__ void fwd_drop_tile(Bars3& bar, uint32_t i_t, uint32_t tS, const BwdParams& p, float nlse,
+                                              float fillp, uint32_t w0, uint32_t w1, int cmax, int oob_from,
+                                              uint32_t dh1, uint32_t qsh, uint32_t k0) {
+  const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nl2 = make_float2(nlse, nlse);
+  const uint32_t buf = i_t & 1u;
+  uint32_t s[64];
+  uint32_t pk[32];
+  mbar_wait(&bar.s_full[buf], (i_t >> 1) & 1u, 40);
+  tc_fence_after_sync();
+  tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+  tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 64; i += 2) {
+    const float2 x = fma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nl2);
+    float p0 = ex2(x.x), p1 = ex2(x.y);
+    if (MASKED) {
+      const uint32_t word = i < 32 ? w0 : w1;
+      if (((word >> (i & 31)) & 1u) || i > cmax) p0 = fillp;
+      if (((word >> ((i + 1) & 31)) & 1u) || i + 1 > cmax) p1 = fillp;
+      if (i >= oob_from) p0 = 0.f;
+      if (i + 1 >= oob_from) p1 = 0.f;
+    }
+    const uint32_t bits = drop_finish(dh1, drop_mixk(((k0 + (uint32_t)i) >> 1) ^ p.seed_hi));
+    p0 = (((bits >> qsh) & 0xffu) >= p.drop_thresh) ? p0 * p.drop_rp : 0.f;
+    p1 = (((bits >> (qsh + 8u)) & 0xffu) >= p.drop_thresh) ? p1 * p.drop_rp : 0.f;
+    pk[i >> 1] = pack2(p0, p1, BF16);
+  }
+  tmem_st32(tS, pk);  // dropout(P) (16-bit) over the first 32 of this warp's 64 S columns
+  tmem_wait_st();
+  tc_fence_before_sync();
+  warp_arrive(&bar.p_ready[buf]);
+}
+
+template <int DQK, int DV, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+fwd_drop_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const BwdParams p) {
+  using C = Cfg3<DQK, DV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars3& bar = *reinterpret_cast<Bars3*>(smem + C::kOffBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x % p.nq;
+  const int sp = (blockIdx.x / p.nq) % p.splits;
+  const int bh = blockIdx.x / (p.nq * p.splits);
+  const int h = bh % p.H, b = bh / p.H;
+  const int t0 = sp * p.tiles_per_split;
+  const int t1 = min(p.nk, t0 + p.tiles_per_split);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar.q_full, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bar.k_full[i], 1);
+      mbar_init(&bar.k_empty[i], 1);
+      mbar_init(&bar.v_full[i], 1);
+      mbar_init(&bar.v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar.s_full[i], 1);
+      mbar_init(&bar.p_ready[i], 8);
+    }
+    mbar_init(&bar.o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(&bar.tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  if (warp < 8) {
+    reg_alloc<208>();
+    // ===== softmax / dropout: thread = query row, this warp's half of the 128 key columns =====
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const int nrow = j * kT + r;
+    const uint32_t lanef = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS0 = bar.tmem_base + lanef + (uint32_t)(half * 64);
+    const float* blk = p.stats + (((size_t)b * p.H + h) * (2 * p.nq) + (size_t)(nrow >> 6)) * (kStatsBytes / 4);
+    const float nlse = blk[stat_nlse_idx(r & 63)], fillp = blk[stat_fillp_idx(r & 63)];
+    const uint32_t dh1 = drop_mixh(p.seed_lo, drop_mixk(drop_qword((uint32_t)bh, (uint32_t)nrow)));
+    const uint32_t qsh = ((uint32_t)nrow & 1u) * 16u;
+    for (int t = t0; t < t1; ++t) {
+      const uint32_t i_t = (uint32_t)(t - t0);
+      const uint32_t tS = tS0 + (i_t & 1u) * 128u;
+      const int k0 = t * kT + half * 64;
+      uint32_t w0 = 0u, w1 = 0u;
+      bool tile_masked = (t * kT + kT > p.M);
+      if (p.pad_bits != nullptr) {
+        const uint4 mw = *reinterpret_cast<const uint4*>(p.pad_bits + (size_t)b * p.pad_wpr + (size_t)t * 4);
+        w0 = half == 0 ? mw.x : mw.z;
+        w1 = half == 0 ? mw.y : mw.w;
+        tile_masked = tile_masked || ((mw.x | mw.y | mw.z | mw.w) != 0u);
+      }
+      const bool masked = tile_masked || (p.causal && (t * kT + kT - 1 > j * kT + p.cshift));
+      const int cmax = p.causal ? (nrow + p.cshift - k0) : 0x7fffffff;
+      const int oob_from = p.M - k0;
+      if (!masked)
+        fwd_drop_tile<BF16, false>(bar, i_t, tS, p, nlse, fillp, 0u, 0u, 0, 0, dh1, qsh, (uint32_t)k0);
+      else
+        fwd_drop_tile<BF16, true>(bar, i_t, tS, p, nlse, fillp, w0, w1, cmax, oob_from, dh1, qsh, (uint32_t)k0);
+    }
+    // ---- add this CTA's part of the output into the fp32 buffer ----
+    mbar_wait(&bar.o_full, 0u, 41);
+    tc_fence_after_sync();
+    {
+      constexpr int kCols = DV / 2;
+      const uint32_t tO = bar.tmem_base + lanef + C::kColO + (uint32_t)(half * kCols);
+      float* dst = p.o32 + ((size_t)b * p.N + (size_t)nrow) * ((size_t)p.H * p.dv) + (size_t)h * p.dv + (size_t)half * kCols;
+#pragma unroll
+      for (int ch = 0; ch < kCols / 32; ++ch) {
+        uint32_t a[32];
+        tmem_ld32(tO + ch * 32, a);
+        tmem_wait_ld();
+        if (nrow < p.N) {
+#pragma unroll
+          for (int gq = 0; gq < 8; ++gq) {
+            const int c = half * kCols + ch * 32 + gq * 4;
+            if (c < p.dv)
+              red_add_v4(dst + ch * 32 + gq * 4, __uint_as_float(a[gq * 4 + 0]), __uint_as_float(a[gq * 4 + 1]),
+                         __uint_as_float(a[gq * 4 + 2]), __uint_as_float(a[gq * 4 + 3]));
+          }
+        }
+      }
+    }
+  } else {
+    reg_dealloc<88>();
+  }
+
+  if (warp == kTmaWarp) {
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_arrive_expect_tx(&bar.q_full, (uint32_t)C::kKBytes);
+#pragma unroll
+      for (int bx = 0; bx < C::kQB; ++bx)
+        tma_load_4d(smem + C::kOffQ + bx * kBoxBytes, &tmap_q, &bar.q_full, bx * 64, j * kT, h, p.q_bcast ? 0 : b);
+    }
+    for (int t = t0; t < t1; ++t) {
+      const uint32_t it = (uint32_t)(t - t0), slot = it % C::kKS;
+      mbar_wait(&bar.k_empty[slot], ((it / C::kKS) & 1u) ^ 1u, 42);
+      if (leader) {
+        uint8_t* st = smem + C::kOffKRing + slot * C::kKBytes;
+        mbar_arrive_expect_tx(&bar.k_full[slot], (uint32_t)C::kKBytes);
+#pragma unroll
+        for (int bx = 0; bx < C::kQB; ++bx)
+          tma_load_4d(st + bx * kBoxBytes, &tmap_k, &bar.k_full[slot], bx * 64, t * kT, h, b);
+      }
+    }
+  } else if (warp == kTmaWarp + 2) {
+    const bool leader = elect_one();
+    for (int t = t0; t < t1; ++t) {
+      const uint32_t it = (uint32_t)(t - t0), slot = it % C::kVS;
+      mbar_wait(&bar.v_empty[slot], ((it / C::kVS) & 1u) ^ 1u, 43);
+      if (leader) {
+        uint8_t* st = smem + C::kOffVRing + slot * C::kVBytes;
+        mbar_arrive_expect_tx(&bar.v_full[slot], (uint32_t)C::kVBytes);
+#pragma unroll
+        for (int bx = 0; bx < C::kVB; ++bx)
+          tma_load_4d(st + bx * kBoxBytes, &tmap_v, &bar.v_full[slot], bx * 64, t * kT, h, b);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(kT, kT, BF16, false);
+    constexpr uint32_t idesc_pv = make_idesc(kT, DV, BF16, true);
+    const uint32_t tmem = bar.tmem_base;
+    const uint64_t dQ = make_smem_desc(smem_u32(smem + C::kOffQ), 16, 1024);
+    auto issue_s = [&](uint32_t i) {  // S = Q_j K_t^T into S buffer i & 1
+      if (leader) {
+        const uint64_t db = make_smem_desc(smem_u32(smem + C::kOffKRing + (i % C::kKS) * C::kKBytes), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < DQK / 16; ++kk) {
+          const uint64_t off = (uint64_t)(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          mma_ss(tmem + (i & 1u) * 128u, dQ + off, db + off, idesc_s, kk > 0 ? 1u : 0u);
+        }
+      }
+    };
+    auto issue_pv = [&](uint32_t i, bool acc) {  // O += dropout(P)(TMEM) V_t   (V_t read MN-major)
+      if (leader) {
+        const uint64_t db = make_smem_desc(smem_u32(smem + C::kOffVRing + (i % C::kVS) * C::kVBytes), kBoxBytes, 1024);
+#pragma unroll
+        for (int kk = 0; kk < kT / 16; ++kk)
+          mma_ts(tmem + C::kColO, tmem + (i & 1u) * 128u + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8),
+                 db + (uint64_t)((kk * 2048) >> 4), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+      }
+    };
+    auto commit = [&](uint64_t* bp) {
+      if (leader) tc_commit(bp);
+    };
+    const int nt = t1 - t0;
+    mbar_wait(&bar.q_full, 0u, 44);
+    mbar_wait(&bar.k_full[0], 0u, 45);
+    tc_fence_after_sync();
+    issue_s(0);
+    commit(&bar.s_full[0]);
+    commit(&bar.k_empty[0]);
+    for (int i = 0; i < nt; ++i) {
+      const uint32_t ui = (uint32_t)i;
+      if (i + 1 < nt) {
+        const uint32_t un = ui + 1;  // its S buffer held P(i-1), consumed by PV(i-1) which is ahead in the pipe
+        mbar_wait(&bar.k_full[un % C::kKS], (un / C::kKS) & 1u, 46);
+        tc_fence_after_sync();
+        issue_s(un);
+        commit(&bar.s_full[un & 1u]);
+        commit(&bar.k_empty[un % C::kKS]);
+      }
+      mbar_wait(&bar.p_ready[ui & 1u], (ui >> 1) & 1u, 47);
+      mbar_wait(&bar.v_full[ui % C::kVS], (ui / C::kVS) & 1u, 48);
+      tc_fence_after_sync();
+      issue_pv(ui, i > 0);
+      commit(&bar.v_empty[ui % C::kVS]);
+    }
+    commit(&bar.o_full);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(bar.tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 bwd_encode_fn() {
@@ -954,6 +1320,19 @@ int bwd_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int row
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// dropout probability -> byte threshold (p rounded to 1/256, at least 1/256 when p > 0) and survivor scale
+void set_dropout(BwdParams& p, float dropout_p, uint64_t seed) {
+  p.drop_thresh = 0;
+  p.drop_rp = 1.f;
+  if (dropout_p > 0.f) {
+    const long t = std::min(255L, std::max(1L, std::lround((double)dropout_p * 256.0)));
+    p.drop_thresh = (uint32_t)t;
+    p.drop_rp = (float)(256.0 / (256.0 - (double)t));
+  }
+  p.seed_lo = (uint32_t)(seed & 0xffffffffu);
+  p.seed_hi = (uint32_t)(seed >> 32);
+}
 
 struct BwdLayout {
   int Npad, nq, nk, wpr, Bq;
@@ -1007,7 +1386,7 @@ bool attn_bwd_supported(const pcv_attn_bwd_params& a, const char** why) {
   if (a.B < 1 || a.H < 1 || a.N < 1 || a.M < 1) return no("empty problem");
   if (a.dqk < 8 || a.dv < 8 || a.dqk > 128 || a.dv > 128) return no("head dims must be in [8, 128]");
   if (a.dqk % 8 || a.dv % 8) return no("head dims must be multiples of 8");
-  if (a.dropout_p != 0.f) return no("attention dropout is not fused into the backward kernels");
+  if (!(a.dropout_p >= 0.f && a.dropout_p < 1.f)) return no("dropout_p must be in [0, 1)");
   auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
   if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out) || !al16(a.grad_out) || !al16(a.grad_q) ||
       !al16(a.grad_k) || !al16(a.grad_v))
@@ -1059,6 +1438,7 @@ int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
   p.dk_sb = a.gk_stride_b; p.dk_sm = a.gk_stride_m; p.dk_sh = a.gk_stride_h;
   p.dv_sb = a.gv_stride_b; p.dv_sm = a.gv_stride_m; p.dv_sh = a.gv_stride_h;
   p.total_tiles = a.B * a.H * L.nk;
+  set_dropout(p, a.dropout_p, a.dropout_seed);
   {
     const int64_t st[] = {a.gk_stride_b, a.gk_stride_m, a.gk_stride_h, a.gv_stride_b, a.gv_stride_m, a.gv_stride_h};
     bool wide = ((reinterpret_cast<uintptr_t>(a.grad_k) | reinterpret_cast<uintptr_t>(a.grad_v)) & 31u) == 0;
@@ -1144,6 +1524,176 @@ int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
     PCV_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
+  return PCV_OK;
+}
+
+// ---- forward with attention dropout + mask export --------------------------------------------------------------
+namespace {
+
+struct FwdDropLayout {
+  int Npad, nq, nk, wpr;
+  size_t off_stats, off_o32, off_pad, total;
+};
+
+FwdDropLayout fwd_drop_layout(const pcv_attn_params& a) {
+  FwdDropLayout L;
+  L.nq = (a.N + kT - 1) / kT;
+  L.nk = (a.M + kT - 1) / kT;
+  L.Npad = L.nq * kT;
+  L.wpr = L.nk * 4;
+  L.off_stats = 0;
+  L.off_o32 = align256((size_t)kStatsBytes * a.B * a.H * 2 * L.nq);
+  L.off_pad = L.off_o32 + align256(sizeof(float) * (size_t)a.B * a.N * a.H * a.dv);
+  L.total = L.off_pad + (a.pad_mask != nullptr ? align256(sizeof(uint32_t) * (size_t)a.B * L.wpr) : 0);
+  return L;
+}
+
+template <int DQK, int DV, bool BF16>
+int launch_fwd_drop_kernel(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const BwdParams& p,
+                           cudaStream_t stream) {
+  using C3 = Cfg3<DQK, DV>;
+  auto k3 = fwd_drop_kernel<DQK, DV, BF16>;
+  PCV_CHECK_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::kSmem));
+  const int grid = p.B * p.H * p.nq * p.splits;
+  k3<<<grid, kThreads, C3::kSmem, stream>>>(tq, tk, tv, p);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PCV_OK;
+}
+
+}  // namespace
+
+bool attn_fwd_dropout_supported(const pcv_attn_params& a, float dropout_p, const char** why) {
+  auto no = [&](const char* w) {
+    if (why) *why = w;
+    return false;
+  };
+  if (a.dtype != PCV_BF16 && a.dtype != PCV_F16) return no("dtype must be bf16 or fp16");
+  if (a.B < 1 || a.H < 1 || a.N < 1 || a.M < 1) return no("empty problem");
+  if (a.dqk < 8 || a.dv < 8 || a.dqk > 128 || a.dv > 128 || a.dqk % 8 || a.dv % 8)
+    return no("head dims must be multiples of 8 in [8, 128]");
+  if (!(dropout_p > 0.f && dropout_p < 1.f)) return no("dropout_p must be in (0, 1)");
+  if (a.m_total != a.M || a.m_offset != 0 || a.write_partial) return no("sharded / partial calls take no dropout");
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  if (!al16(a.q) || !al16(a.k) || !al16(a.v)) return no("tensors must be 16-byte aligned");
+  const int64_t strides[] = {a.q_stride_b, a.q_stride_n, a.q_stride_h, a.k_stride_b, a.k_stride_m,
+                             a.k_stride_h, a.v_stride_b, a.v_stride_m, a.v_stride_h};
+  for (int64_t st : strides)
+    if (st % 8) return no("strides must be multiples of 8 elements");
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return no("no CUDA device");
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return no("needs an sm_100 device");
+  return true;
+}
+
+int attn_fwd_dropout_workspace_bytes(const pcv_attn_params& a, size_t* bytes) {
+  PCV_REQUIRE(bytes != nullptr, PCV_ERR_INVALID, "attn_fwd_dropout_workspace_bytes: bytes is NULL");
+  *bytes = fwd_drop_layout(a).total;
+  return PCV_OK;
+}
+
+int launch_attn_fwd_dropout(const pcv_attn_params& a, const float* stat_m, const float* stat_l, float dropout_p,
+                            uint64_t seed, cudaStream_t stream) {
+  const char* why = "";
+  PCV_REQUIRE(attn_fwd_dropout_supported(a, dropout_p, &why), PCV_ERR_UNSUPPORTED, "attn_fwd_dropout: %s", why);
+  PCV_REQUIRE(stat_m != nullptr && stat_l != nullptr && a.out != nullptr, PCV_ERR_INVALID,
+              "attn_fwd_dropout: statistics / output pointer is NULL");
+  const FwdDropLayout L = fwd_drop_layout(a);
+  PCV_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= L.total, PCV_ERR_WORKSPACE,
+              "attn_fwd_dropout: workspace too small (%zu < %zu)", a.workspace_bytes, L.total);
+  PCV_REQUIRE((reinterpret_cast<uintptr_t>(a.workspace) & 255u) == 0, PCV_ERR_INVALID,
+              "attn_fwd_dropout: workspace must be 256-byte aligned");
+  int dev = 0, sms = 0;
+  PCV_CHECK_CUDA(cudaGetDevice(&dev));
+  PCV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a.workspace);
+  BwdParams p{};
+  p.B = a.B; p.H = a.H; p.N = a.N; p.M = a.M; p.dqk = a.dqk; p.dv = a.dv;
+  p.Npad = L.Npad; p.nq = L.nq; p.nk = L.nk;
+  p.q_bcast = (a.q_stride_b == 0 && a.B > 1) ? 1 : 0;
+  p.scale = a.scale;
+  p.scale_log2 = a.scale * kLog2e;
+  p.causal = a.causal;
+  p.cshift = a.M - a.N;
+  p.stats = reinterpret_cast<const float*>(ws + L.off_stats);
+  p.o32 = reinterpret_cast<float*>(ws + L.off_o32);
+  set_dropout(p, dropout_p, seed);
+  {
+    const int units = a.B * a.H * L.nq;
+    int splits = std::max(1, (L.nk + 63) / 64);
+    while (units * splits < 4 * sms && splits < L.nk && (L.nk + splits - 1) / splits > 4) ++splits;
+    p.tiles_per_split = (L.nk + splits - 1) / splits;
+    p.splits = (L.nk + p.tiles_per_split - 1) / p.tiles_per_split;
+  }
+  const size_t o32_bytes = sizeof(float) * (size_t)a.B * a.N * a.H * a.dv;
+  PCV_CHECK_CUDA(cudaMemsetAsync(p.o32, 0, o32_bytes, stream));
+  {
+    const int64_t rows = (int64_t)a.B * a.H * L.Npad;
+    const int blocks = (int)((rows + 7) / 8);
+    float* stats = reinterpret_cast<float*>(ws + L.off_stats);
+    // statistics only (no delta): out / grad_out pointers are not read
+    bwd_prep_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(nullptr, nullptr, stat_m, stat_l, stats, a.B, a.H, a.N,
+                                                               L.Npad, a.dv, 0, 0, 0, 0, 0, 0);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  if (a.pad_mask != nullptr) {
+    uint32_t* bits = reinterpret_cast<uint32_t*>(ws + L.off_pad);
+    const int64_t total = (int64_t)a.B * L.wpr;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 1024);
+    bwd_pack_pad_kernel<<<blocks, 256, 0, stream>>>(a.pad_mask, a.pad_stride_b, a.B, a.M, L.wpr, bits);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    p.pad_bits = bits;
+    p.pad_wpr = L.wpr;
+  }
+  const int Bq = a.q_stride_b == 0 ? 1 : a.B;
+  CUtensorMap tq, tk, tv;
+  int rc = bwd_tmap(&tq, a.q, a.dtype, a.dqk, a.N, a.H, Bq, a.q_stride_n, a.q_stride_h, a.q_stride_b);
+  if (rc != PCV_OK) return rc;
+  rc = bwd_tmap(&tk, a.k, a.dtype, a.dqk, a.M, a.H, a.B, a.k_stride_m, a.k_stride_h, a.k_stride_b);
+  if (rc != PCV_OK) return rc;
+  rc = bwd_tmap(&tv, a.v, a.dtype, a.dv, a.M, a.H, a.B, a.v_stride_m, a.v_stride_h, a.v_stride_b);
+  if (rc != PCV_OK) return rc;
+  const bool bf16 = a.dtype == PCV_BF16;
+  const int DQK = a.dqk <= 64 ? 64 : 128, DV = a.dv <= 64 ? 64 : 128;
+#define PCV_FWD_DROP_CASE(dq_, dv_)                                                            \
+  if (DQK == dq_ && DV == dv_)                                                                 \
+    rc = bf16 ? launch_fwd_drop_kernel<dq_, dv_, true>(tq, tk, tv, p, stream)                  \
+              : launch_fwd_drop_kernel<dq_, dv_, false>(tq, tk, tv, p, stream);
+  PCV_FWD_DROP_CASE(64, 64)
+  PCV_FWD_DROP_CASE(64, 128)
+  PCV_FWD_DROP_CASE(128, 64)
+  PCV_FWD_DROP_CASE(128, 128)
+#undef PCV_FWD_DROP_CASE
+  if (rc != PCV_OK) return rc;
+  {
+    const int64_t total = (int64_t)a.B * a.N * a.H * a.dv;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    if (bf16)
+      bwd_cast_dq_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(p.o32, reinterpret_cast<__nv_bfloat16*>(a.out), a.B,
+                                                                    a.N, a.H, a.dv, a.o_stride_b, a.o_stride_n,
+                                                                    a.o_stride_h);
+    else
+      bwd_cast_dq_kernel<__half><<<blocks, 256, 0, stream>>>(p.o32, reinterpret_cast<__half*>(a.out), a.B, a.N, a.H, a.dv,
+                                                             a.o_stride_b, a.o_stride_n, a.o_stride_h);
+    PCV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return PCV_OK;
+}
+
+int launch_dropout_mask(uint8_t* keep, int B, int H, int N, int M, float dropout_p, uint64_t seed, cudaStream_t stream) {
+  PCV_REQUIRE(keep != nullptr && B > 0 && H > 0 && N > 0 && M > 0, PCV_ERR_INVALID, "dropout_mask: bad arguments");
+  PCV_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PCV_ERR_INVALID, "dropout_mask: dropout_p must be in [0, 1)");
+  BwdParams p{};
+  set_dropout(p, dropout_p, seed);
+  const int64_t total = (int64_t)B * H * N * M;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 8192);
+  drop_mask_kernel<<<blocks, 256, 0, stream>>>(keep, B, H, N, M, p.drop_thresh, p.seed_lo, p.seed_hi);
+  PCV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return PCV_OK;
 }
 

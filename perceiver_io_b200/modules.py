@@ -113,11 +113,8 @@ def attend(mha, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_mask=None
     """Everything of ``MultiHeadAttention.forward`` after the q/k/v projections (reference modules.py:117-170):
     cache append, rotary, fused attention, ``o_proj``.  ``mha`` is this package's module or a patched reference
     one (only its attributes are used)."""
-    if mha.training and mha.dropout.p > 0.0:
-        raise NotImplementedError(
-            "attention-probability dropout is not fused into the sm_100a kernel yet; "
-            "run with dropout=0.0 (SURVEY.md §8(f) rank 2)"
-        )
+    # attention-probability dropout (reference :161): fused into the training kernels (ops.attention dropout_p)
+    drop_p = float(mha.dropout.p) if mha.training else 0.0
     if kv_cache is not None:
         k, v = ops.kv_append(kv_cache[0], kv_cache[1], k, v)
         kv_cache = (k, v)
@@ -136,7 +133,7 @@ def attend(mha, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pad_mask=None
         k_att = k if rot_pos_emb_k is None else _rotate_rows(rot_pos_emb_k, k, mha.num_heads)
 
     o = ops.attention(q, k_att, v, mha.num_heads, mha.dp_scale, pad_mask=pad_mask,
-                      causal=mha.causal_attention, impl=getattr(mha, "kernel_impl", "auto"))
+                      causal=mha.causal_attention, impl=getattr(mha, "kernel_impl", "auto"), dropout_p=drop_p)
     o = fused_linear(mha, "_pcv_o_fold", None, mha.o_proj, o, min_rows_key)
     return ModuleOutput(last_hidden_state=o, kv_cache=kv_cache)
 

@@ -179,7 +179,8 @@ def _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl):
 backward_config = {"max_score_bytes": 1 << 30, "impl": "auto"}
 
 
-def _fill_bwd_params(q, k, v, out, grad_out, stat_m, stat_l, num_heads, scale, pad_mask, causal):
+def _fill_bwd_params(q, k, v, out, grad_out, stat_m, stat_l, num_heads, scale, pad_mask, causal, dropout_p=0.0,
+                     dropout_seed=0):
     ap, keep = _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, None, 0, "auto")
     B, H, N, M, dqk, dv = ap.B, ap.H, ap.N, ap.M, ap.dqk, ap.dv
     for name, t in (("out", out), ("grad_out", grad_out)):
@@ -207,23 +208,26 @@ def _fill_bwd_params(q, k, v, out, grad_out, stat_m, stat_l, num_heads, scale, p
     p.B, p.H, p.N, p.M, p.dqk, p.dv = B, H, N, M, dqk, dv
     p.scale, p.dtype, p.causal = float(scale), ap.dtype, ap.causal
     p.pad_mask, p.pad_stride_b = ap.pad_mask, ap.pad_stride_b
+    p.dropout_p, p.dropout_seed = float(dropout_p), int(dropout_seed)
     return p, (gq, gk, gv), keep + (out, grad_out, stat_m, stat_l)
 
 
 def attention_backward(q, k, v, out, grad_out, stat_m, stat_l, num_heads: int, scale: float, pad_mask=None,
-                       causal: bool = False, check_only: bool = False):
+                       causal: bool = False, check_only: bool = False, dropout_p: float = 0.0, dropout_seed: int = 0):
     """Gradients (grad_q, grad_k, grad_v) of ``attention`` on the tcgen05 backward kernels (pcv_attn_bwd).
 
     ``out`` is the forward output, ``stat_m`` / ``stat_l`` the (B, H, N) row statistics of ``attention_partial`` over all
     keys.  grad_q has q's batch size (a batch-1 ``q`` shared by the batch receives the sum).  ``check_only`` launches
-    nothing and returns whether the kernels cover these operands."""
+    nothing and returns whether the kernels cover these operands.  ``dropout_p`` / ``dropout_seed``: the values the
+    forward (``attention_dropout_forward``) ran with — the kernels regenerate its mask."""
     q, k, v, _ = _prep(q, k, v)
     cdt = q.dtype
     out = _rows_contiguous(out if out.dtype == cdt else out.to(cdt))
     grad_out = _rows_contiguous(grad_out if grad_out.dtype == cdt else grad_out.to(cdt))
     _require_cuda(out, grad_out, stat_m, stat_l, pad_mask)
     with torch.cuda.device(k.device):
-        p, grads, keep = _fill_bwd_params(q, k, v, out, grad_out, stat_m, stat_l, num_heads, scale, pad_mask, causal)
+        p, grads, keep = _fill_bwd_params(q, k, v, out, grad_out, stat_m, stat_l, num_heads, scale, pad_mask, causal,
+                                          dropout_p, dropout_seed)
         if check_only:
             return bool(_lib.lib().pcv_attn_bwd_supported(C.byref(p)))
         need = C.c_size_t(0)
@@ -235,6 +239,49 @@ def attention_backward(q, k, v, out, grad_out, stat_m, stat_l, num_heads: int, s
     return grads
 
 
+def new_dropout_seed() -> int:
+    """A fresh 62-bit seed from torch's CPU generator: reproducible under ``torch.manual_seed``, no device sync."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def attention_dropout_forward(q, k, v, stat_m, stat_l, num_heads: int, scale: float, dropout_p: float, dropout_seed: int,
+                              pad_mask=None, causal: bool = False, check_only: bool = False):
+    """out = dropout(softmax(...)) V for training (reference modules.py:161), second pass after ``attention_partial``
+    over all keys (``stat_m`` / ``stat_l`` = its part_m / part_l): pcv_attn_fwd_dropout.  The keep decision of every
+    (b, h, query, key) is a pure function of ``dropout_seed`` (``dropout_keep_mask`` exports it); the drop probability is
+    ``dropout_p`` rounded to 1/256.  ``check_only``: launch nothing, return whether the kernel covers the operands."""
+    q, k, v, out_dtype = _prep(q, k, v)
+    _require_cuda(stat_m, stat_l, pad_mask)
+    with torch.cuda.device(k.device):
+        p, keep = _fill_attn_params(q, k, v, num_heads, scale, pad_mask, causal, None, 0, "auto")
+        if check_only:
+            return bool(_lib.lib().pcv_attn_fwd_dropout_supported(C.byref(p), float(dropout_p)))
+        for name, t in (("stat_m", stat_m), ("stat_l", stat_l)):
+            if tuple(t.shape) != (p.B, p.H, p.N) or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous float32 (B, H, N) tensor")
+        out = torch.empty(p.B, p.N, p.H * p.dv, dtype=q.dtype, device=k.device)
+        p.out = out.data_ptr()
+        p.o_stride_b, p.o_stride_n, p.o_stride_h = out.stride(0), out.stride(1), p.dv
+        need = C.c_size_t(0)
+        check(_lib.lib().pcv_attn_fwd_dropout_workspace_bytes(C.byref(p), C.byref(need)),
+              "pcv_attn_fwd_dropout_workspace_bytes")
+        ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=k.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), need.value
+        check(_lib.lib().pcv_attn_fwd_dropout(C.byref(p), stat_m.data_ptr(), stat_l.data_ptr(), float(dropout_p),
+                                              int(dropout_seed), _stream()), "pcv_attn_fwd_dropout")
+    del keep
+    return out if out.dtype == out_dtype else out.to(out_dtype)
+
+
+def dropout_keep_mask(B: int, H: int, N: int, M: int, dropout_p: float, dropout_seed: int, device="cuda") -> torch.Tensor:
+    """(B, H, N, M) bool keep mask the dropout kernels use for this seed (tests / debugging)."""
+    keep = torch.empty(B, H, N, M, dtype=torch.uint8, device=device)
+    with torch.cuda.device(keep.device):
+        check(_lib.lib().pcv_attn_dropout_mask(keep.data_ptr(), B, H, N, M, float(dropout_p), int(dropout_seed),
+                                               _stream()), "pcv_attn_dropout_mask")
+    return keep.bool()
+
+
 class _FusedAttention(torch.autograd.Function):
     """Forward = the fused CUDA kernel (partial-state mode, so the row max and denominator are kept).
     Backward = the tcgen05 backward kernels (``attention_backward`` -> pcv_attn_bwd: dK/dV and dQ kernels, SURVEY.md
@@ -244,8 +291,18 @@ class _FusedAttention(torch.autograd.Function):
     (8.6 GB at the north-star shape).  The inference forward never routes through this class."""
 
     @staticmethod
-    def forward(ctx, q, k, v, num_heads, scale, pad_mask, causal, impl):
+    def forward(ctx, q, k, v, num_heads, scale, pad_mask, causal, impl, dropout_p=0.0, dropout_seed=0):
         dv_true = _head_dim(v, num_heads)
+        ctx.dropout = (float(dropout_p), int(dropout_seed))
+        if dropout_p > 0.0:
+            # statistics from the fused kernel, then the dropout pass (second kernel) writes the output
+            po, pm, pl = attention_partial(q, k, v, num_heads, scale, pad_mask=pad_mask, causal=causal, impl=impl)
+            del po
+            out = attention_dropout_forward(q, k, v, pm, pl, num_heads, scale, dropout_p, dropout_seed, pad_mask, causal)
+            out = out if out.dtype == q.dtype else out.to(q.dtype)
+            ctx.save_for_backward(q, k, v, pad_mask, out, pm, pl)
+            ctx.meta = (num_heads, scale, causal)
+            return out
         if _head_dim(q, num_heads) % 8 or dv_true % 8 or impl == "decode":
             # head dims the partial-state kernels do not take without padding: plain forward, statistics recomputed
             out = _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl)
@@ -262,18 +319,24 @@ class _FusedAttention(torch.autograd.Function):
     def backward(ctx, grad_out):
         q, k, v, pad_mask, out, pm, pl = ctx.saved_tensors
         H, scale, causal = ctx.meta
+        drop_p, drop_seed = getattr(ctx, "dropout", (0.0, 0))
         mode = backward_config["impl"]
         if mode not in ("auto", "kernel", "shim"):
             raise ValueError(f"backward_config['impl'] = {mode!r}")
         if mode != "shim":
             ok = (pm is not None and q.is_cuda and q.dim() == 3 and k.dim() == 3 and v.dim() == 3
-                  and attention_backward(q, k, v, out, grad_out, pm, pl, H, scale, pad_mask, causal, check_only=True))
+                  and attention_backward(q, k, v, out, grad_out, pm, pl, H, scale, pad_mask, causal, check_only=True,
+                                         dropout_p=drop_p, dropout_seed=drop_seed))
             if ok:
-                gq, gk, gv = attention_backward(q, k, v, out, grad_out, pm, pl, H, scale, pad_mask, causal)
-                return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), None, None, None, None, None
+                gq, gk, gv = attention_backward(q, k, v, out, grad_out, pm, pl, H, scale, pad_mask, causal,
+                                                dropout_p=drop_p, dropout_seed=drop_seed)
+                return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), None, None, None, None, None, None, None
             if mode == "kernel":
                 raise RuntimeError("backward_config['impl'] = 'kernel' but pcv_attn_bwd does not cover this call: "
                                    + _lib.lib().pcv_last_error().decode())
+        if drop_p > 0.0:
+            raise RuntimeError("attention dropout needs the backward kernels (pcv_attn_bwd); the torch shim cannot "
+                               "regenerate the mask: " + _lib.lib().pcv_last_error().decode())
         B, M = k.shape[0], k.shape[1]
         N = q.shape[1]
         cdt = _compute_dtype(q.dtype)
@@ -329,18 +392,30 @@ class _FusedAttention(torch.autograd.Function):
             gq = gq.sum(0, keepdim=True)
         gk = (gk * scale).transpose(1, 2).reshape(B, M, -1)
         gv = gv.transpose(1, 2).reshape(B, M, -1)
-        return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), None, None, None, None, None
+        return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), None, None, None, None, None, None, None
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, scale: float,
-              pad_mask: Optional[torch.Tensor] = None, causal: bool = False, impl: str = "auto") -> torch.Tensor:
+              pad_mask: Optional[torch.Tensor] = None, causal: bool = False, impl: str = "auto",
+              dropout_p: float = 0.0, dropout_seed: Optional[int] = None) -> torch.Tensor:
     """softmax(scale * Q K^T + masks) V with heads split by stride.
 
     q: (B or 1, N, H*dqk), k: (B, M, H*dqk), v: (B, M, H*dv) -> (B, N, H*dv).
     Semantics of the reference's ``MultiHeadAttention.forward`` lines 123-167
     (/root/reference/perceiver/model/core/modules.py): q is scaled by ``scale``, ``pad_mask`` (True =
-    padding) and the right-aligned causal mask use the finite fill ``-finfo.max``.
+    padding) and the right-aligned causal mask use the finite fill ``-finfo.max``.  ``dropout_p`` > 0 applies the
+    reference's dropout on the attention probabilities (:161) with a counter-based mask derived from
+    ``dropout_seed`` (default: a fresh seed from torch's CPU generator); head dims must be multiples of 8 up to 128.
     """
+    if dropout_p > 0.0:
+        if not 0.0 < dropout_p < 1.0:
+            raise ValueError(f"dropout_p must be in [0, 1), got {dropout_p}")
+        if not attention_dropout_forward(q, k, v, None, None, num_heads, scale, dropout_p, 0, pad_mask, causal,
+                                         check_only=True):
+            raise NotImplementedError("attention dropout is not available for this call: "
+                                      + _lib.lib().pcv_last_error().decode())
+        seed = new_dropout_seed() if dropout_seed is None else int(dropout_seed)
+        return _FusedAttention.apply(q, k, v, num_heads, scale, pad_mask, causal, impl, float(dropout_p), seed)
     if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
         return _FusedAttention.apply(q, k, v, num_heads, scale, pad_mask, causal, impl)
     return _attention_forward(q, k, v, num_heads, scale, pad_mask, causal, impl)

@@ -57,6 +57,11 @@ def main():
     res["bwd_launches_per_call"] = (_lib.launch_count() - n0) / (a.steps + 3)
     res["bwd_kernel_tflops_algorithmic"] = 2.5 * flops_fwd / res["bwd_kernel_ms"] * 1e-9
     res["bwd_kernel_tflops_executed"] = 3.5 * flops_fwd / res["bwd_kernel_ms"] * 1e-9
+    # training step with attention dropout 0.1: statistics pass + dropout pass forward, backward regenerating the mask
+    res["fwd_dropout_pass_ms"] = timed(
+        lambda: ops.attention_dropout_forward(q, k, v, pm, pl, H, scale, 0.1, 1234), a.steps)
+    res["bwd_dropout_kernel_ms"] = timed(
+        lambda: ops.attention_backward(q, k, v, out, go, pm, pl, H, scale, dropout_p=0.1, dropout_seed=1234), a.steps)
     if a.shim:
         qq, kk, vv = (t.detach().clone().requires_grad_() for t in (q, k, v))
 
