@@ -434,6 +434,32 @@ def run_ours(args, rank, world, local_rank):
                   "note": "fused K/V producer: LayerNorm folded into one tcgen05 GEMM; q/o projections on the same kernel"}
         del xq_dev, xkv_dev
 
+    # ---- training: forward (statistics kept) + backward of the attention core on the tcgen05 backward kernels -------
+    # (reported next to the headline, not part of it).  FLOP counts: forward 4*B*N*M*d, backward
+    # 2.5x that (5 tile GEMMs; the two kernels execute 7).
+    training = None
+    if world == 1 and not args.skip_training and args.kernel == "auto" and args.kv_layout != "head_major":
+        go = torch.randn(B, N, d, device=dev).bfloat16()
+        po, pm, pl = ops.attention_partial(q, k, v, H, scale)
+        out_t = ops.combine_partials(po[None], pm[None], pl[None], torch.bfloat16)
+        del po
+        if ops.attention_backward(q, k, v, out_t, go, pm, pl, H, scale, check_only=True):
+            l0 = _lib.launch_count()
+            ms_bwd = timed(lambda: ops.attention_backward(q, k, v, out_t, go, pm, pl, H, scale), args.steps,
+                           min(args.warmup, 3))
+            l_bwd = (_lib.launch_count() - l0) // (args.steps + min(args.warmup, 3))
+            ms_drop_f = timed(lambda: ops.attention_dropout_forward(q, k, v, pm, pl, H, scale, 0.1, 1234), args.steps, 2)
+            ms_drop_b = timed(lambda: ops.attention_backward(q, k, v, out_t, go, pm, pl, H, scale, dropout_p=0.1,
+                                                             dropout_seed=1234), args.steps, 2)
+            training = {"api": "perceiver_io_b200.ops.attention_backward (pcv_attn_bwd: dK/dV kernel + dQ kernel)",
+                        "backward_ms": ms_bwd, "backward_flops": 2.5 * flops,
+                        "backward_value": 2.5 * flops / (ms_bwd * 1e-3) / 1e12, "unit": UNIT,
+                        "backward_executed_frac_of_tensor_peak": 3.5 * flops / (ms_bwd * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                        "library_launches_per_backward": l_bwd,
+                        "forward_plus_backward_ms": ms_core + ms_bwd,
+                        "dropout_0.1": {"forward_second_pass_ms": ms_drop_f, "backward_ms": ms_drop_b}}
+        del go, out_t, pm, pl
+
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
     cpu = None
     if world == 1 and rank == 0 and not args.skip_cpu:
@@ -471,6 +497,8 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu
         if module is not None:
             line["module"] = module
+        if training is not None:
+            line["training"] = training
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -498,6 +526,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-module", action="store_true")
+    ap.add_argument("--skip-training", action="store_true", help="skip the backward / dropout leg")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes/launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()
