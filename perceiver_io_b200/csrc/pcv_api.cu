@@ -115,7 +115,9 @@ int pcv_profile_end(double* main_kernel_ms_total, int32_t* main_kernel_launches)
 
 int pcv_debug_read(uint32_t* out, int32_t n) {
   PCV_REQUIRE(out != nullptr && n >= 0, PCV_ERR_INVALID, "debug_read: bad argument");
-  return debug_read(out, n);
+  const int rc = debug_read(out, n);
+  if (rc == PCV_OK && n > 0 && out[0] == 0u) return bwd_debug_read(out, n);  // nothing from the forward kernels
+  return rc;
 }
 
 int pcv_debug_trace_read(uint64_t* out, int32_t n) {

@@ -1321,6 +1321,25 @@ int bwd_tmap(CUtensorMap* tm, const void* base, int dtype, int channels, int row
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+// watchdog record of THIS translation unit's kernels (mbar_wait in pcv_sm100.cuh): mapped pinned host memory
+uint32_t* g_bwd_diag_host = nullptr;
+std::mutex g_bwd_diag_mu;
+int g_bwd_diag_dev = -1;
+
+int ensure_bwd_diag(int dev) {
+  std::lock_guard<std::mutex> lk(g_bwd_diag_mu);
+  if (g_bwd_diag_dev == dev) return PCV_OK;
+  if (g_bwd_diag_host == nullptr) {
+    PCV_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_bwd_diag_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    for (int i = 0; i < 16; ++i) g_bwd_diag_host[i] = 0;
+  }
+  uint32_t* dptr = nullptr;
+  PCV_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_bwd_diag_host, 0));
+  PCV_CHECK_CUDA(cudaMemcpyToSymbol(sm100::g_wait_diag, &dptr, sizeof(dptr)));
+  g_bwd_diag_dev = dev;
+  return PCV_OK;
+}
+
 // dropout probability -> byte threshold (p rounded to 1/256, at least 1/256 when p > 0) and survivor scale
 void set_dropout(BwdParams& p, float dropout_p, uint64_t seed) {
   p.drop_thresh = 0;
@@ -1422,6 +1441,10 @@ int launch_attn_bwd(const pcv_attn_bwd_params& a, cudaStream_t stream) {
   int dev = 0, sms = 0;
   PCV_CHECK_CUDA(cudaGetDevice(&dev));
   PCV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  {
+    const int rc = ensure_bwd_diag(dev);
+    if (rc != PCV_OK) return rc;
+  }
 
   uint8_t* ws = reinterpret_cast<uint8_t*>(a.workspace);
   BwdParams p{};
@@ -1607,6 +1630,10 @@ int launch_attn_fwd_dropout(const pcv_attn_params& a, const float* stat_m, const
   int dev = 0, sms = 0;
   PCV_CHECK_CUDA(cudaGetDevice(&dev));
   PCV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  {
+    const int rc = ensure_bwd_diag(dev);
+    if (rc != PCV_OK) return rc;
+  }
   uint8_t* ws = reinterpret_cast<uint8_t*>(a.workspace);
   BwdParams p{};
   p.B = a.B; p.H = a.H; p.N = a.N; p.M = a.M; p.dqk = a.dqk; p.dv = a.dv;
@@ -1681,6 +1708,13 @@ int launch_attn_fwd_dropout(const pcv_attn_params& a, const float* stat_m, const
     PCV_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
+  return PCV_OK;
+}
+
+// watchdog record of the backward / dropout kernels (same layout as debug_read; word 6 = 0xB3D marks the source)
+int bwd_debug_read(uint32_t* out, int n) {
+  for (int i = 0; i < n; ++i) out[i] = (g_bwd_diag_host != nullptr && i < 16) ? g_bwd_diag_host[i] : 0u;
+  if (n > 6 && out[0] != 0u) out[6] = 0xB3Du;
   return PCV_OK;
 }
 

@@ -107,6 +107,7 @@ bool attn_fwd_dropout_supported(const pcv_attn_params& p, float dropout_p, const
 int attn_fwd_dropout_workspace_bytes(const pcv_attn_params& p, size_t* bytes);
 int launch_attn_fwd_dropout(const pcv_attn_params& p, const float* stat_m, const float* stat_l, float dropout_p,
                             uint64_t seed, cudaStream_t stream);
+int bwd_debug_read(uint32_t* out, int n);
 int launch_dropout_mask(uint8_t* keep, int B, int H, int N, int M, float dropout_p, uint64_t seed, cudaStream_t stream);
 
 }  // namespace pcv
