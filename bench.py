@@ -269,7 +269,8 @@ def run_ours(args, rank, world, local_rank):
 
     import perceiver_io_b200 as P
     from perceiver_io_b200 import _lib, ops
-    from perceiver_io_b200.dist import cross_attention_sharded, shard_bounds, sharded_attention
+    from perceiver_io_b200.dist import (cross_attention_sharded, grid_position, m_shard_group, plan_grid, shard_bounds,
+                                        sharded_attention)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
@@ -284,8 +285,15 @@ def run_ours(args, rank, world, local_rank):
     if args.B:
         w["B"] = args.B
     B, M, N, d, H = w["B"], w["M"], w["N"], w["d"], w["H"]
-    m0, m1 = shard_bounds(M, world, rank)
+    # Rank grid: batch rows are independent (no exchange), the key axis needs a merge of partial softmax states, so ranks
+    # go to the batch axis first (dist.plan_grid); --decomp m forces the pure M-shard layout of SURVEY.md §8(e).
+    bg, mg = plan_grid(B, world) if args.decomp == "auto" else (1, world)
+    gb, gm = grid_position(rank, bg, mg)
+    Bl = B // bg
+    b0 = gb * Bl
+    m0, m1 = shard_bounds(M, mg, gm)
     Mg = m1 - m0
+    mgroup = m_shard_group(bg, mg) if world > 1 else None
     scale = (d // H) ** -0.5
     flops = core_flops(B, N, M, d)
 
@@ -293,13 +301,14 @@ def run_ours(args, rank, world, local_rank):
     q = torch.randn(B, N, d, device=dev).bfloat16()
     if world > 1:
         dist.broadcast(q, src=0)  # Q is replicated
+    q_loc = q[b0:b0 + Bl]
     if args.kv_layout == "head_major":
         # (B, H, M, dh) buffers viewed as (B, M, H, dh): every (b, h) streams a contiguous run of keys
-        k = torch.randn(B, H, Mg, d // H, device=dev).bfloat16().permute(0, 2, 1, 3)
-        v = torch.randn(B, H, Mg, d // H, device=dev).bfloat16().permute(0, 2, 1, 3)
+        k = torch.randn(Bl, H, Mg, d // H, device=dev).bfloat16().permute(0, 2, 1, 3)
+        v = torch.randn(Bl, H, Mg, d // H, device=dev).bfloat16().permute(0, 2, 1, 3)
     else:
-        k = torch.randn(B, Mg, d, device=dev).bfloat16()
-        v = torch.randn(B, Mg, d, device=dev).bfloat16()
+        k = torch.randn(Bl, Mg, d, device=dev).bfloat16()
+        v = torch.randn(Bl, Mg, d, device=dev).bfloat16()
 
     def barrier():
         if world > 1:
@@ -313,12 +322,12 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    if world == 1:
-        def core_step():
-            return ops.attention(q, k, v, H, scale, impl=args.kernel)
+    if mg == 1:
+        def core_step():  # this rank's batch rows, all keys: no exchange with other ranks
+            return ops.attention(q_loc, k, v, H, scale, impl=args.kernel)
     else:
         def core_step():
-            return sharded_attention(q, k, v, H, scale, M, m0, merge=args.merge, copy_out=False)
+            return sharded_attention(q_loc, k, v, H, scale, M, m0, merge=args.merge, copy_out=False, group=mgroup)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -350,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
     main_ms = max_over_ranks(main_ms)
     peaks = load_peaks()
     achieved = (flops / world) / (main_ms * 1e-3) / 1e12  # this rank's share of the FLOPs over its kernel time
-    hbm_bytes = 2.0 * B * Mg * d * 2 + 2.0 * B * N * d * 2
+    hbm_bytes = 2.0 * Bl * Mg * d * 2 + 2.0 * Bl * N * d * 2
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops"],
@@ -371,8 +380,8 @@ def run_ours(args, rank, world, local_rank):
         for prm in layer.parameters():
             dist.broadcast(prm.data, src=0)
     xq_host = torch.randn(1, N, d).bfloat16().pin_memory()
-    xkv_host = torch.randn(B, Mg, d).bfloat16().pin_memory()
-    out_host = torch.empty(B, N, d, dtype=torch.bfloat16).pin_memory()
+    xkv_host = torch.randn(Bl, Mg, d).bfloat16().pin_memory()
+    out_host = torch.empty(Bl, N, d, dtype=torch.bfloat16).pin_memory()
 
     from perceiver_io_b200.streaming import cross_attention_from_host
 
@@ -389,19 +398,19 @@ def run_ours(args, rank, world, local_rank):
             # public host-input entry point: PCIe copy of chunk i+1 overlaps LayerNorm/projections/attention of chunk i;
             # with several ranks every rank streams its own key shard and the states are merged over peer memory
             with torch.no_grad():
-                if world == 1:
+                if mg == 1:
                     cross_attention_from_host(layer, xq_host, xkv_host, chunk=args.e2e_chunk, out_host=out_host)
                 else:
                     cross_attention_from_host(layer, xq_host, xkv_host, chunk=min(args.e2e_chunk, max(Mg // 2, 1024)),
-                                              out_host=out_host, m_total=M, m_offset=m0)
+                                              out_host=out_host, m_total=M, m_offset=m0, group=mgroup)
             return
         xq = xq_host.to(dev, non_blocking=True)
         xkv = xkv_host.to(dev, non_blocking=True)
         with torch.no_grad():
-            if world == 1:
+            if mg == 1:
                 o = layer(xq, xkv).last_hidden_state
             else:
-                o = cross_attention_sharded(layer, xq, xkv, M, m0, merge=args.merge).last_hidden_state
+                o = cross_attention_sharded(layer, xq, xkv, M, m0, merge=args.merge, group=mgroup).last_hidden_state
         out_host.copy_(o, non_blocking=True)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -477,16 +486,18 @@ def run_ours(args, rank, world, local_rank):
             "config": {
                 "workload": "synthetic cross-attn sweep point M=65536 (BASELINE.json configs[4]; the metric's shape)",
                 "B": B, "M": M, "N": N, "d": d, "H": H, "global_batch": B, "seq_len": M,
-                "parallelism": f"m-shard x{world}" if world > 1 else "single GPU",
-                "keys_per_gpu": Mg,
-                "l2": f"no flush needed: K+V per GPU = {2 * B * Mg * d * 2 / 2**20:.0f} MiB > 126 MiB L2",
-                "kernel": args.kernel, "kv_layout": args.kv_layout, "merge": args.merge if world > 1 else None,
+                "parallelism": (f"batch x{bg} (independent rows, no collective) * m-shard x{mg}" if world > 1
+                                else "single GPU"),
+                "decomp": args.decomp, "batch_rows_per_gpu": Bl, "keys_per_gpu": Mg,
+                "l2": f"no flush needed: K+V per GPU = {2 * Bl * Mg * d * 2 / 2**20:.0f} MiB > 126 MiB L2",
+                "kernel": args.kernel, "kv_layout": args.kv_layout, "merge": args.merge if mg > 1 else None,
             },
             "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps,
                     "api": ("perceiver_io_b200.streaming.cross_attention_from_host (CrossAttention.forward semantics: LayerNorm + q/k/v/o "
                             "projections + attention; key axis chunked so the PCIe copy overlaps compute"
-                            + ("; every rank streams its own key shard, states merged over peer memory)" if world > 1 else ")")
+                            + ("; every rank streams its own key shard, states merged over peer memory)" if mg > 1 else
+                               "; every rank streams its own batch rows)" if world > 1 else ")")
                             if e2e_mode == "streamed" else
                             "perceiver_io_b200.CrossAttention.forward (LayerNorm + q/k/v/o projections + attention)")},
             "gpu_launches": int(launches_timed),
@@ -525,6 +536,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--decomp", choices=["auto", "m"], default="auto",
+                    help="rank grid: auto = batch axis first (no collective between batch rows), then M shards; "
+                         "m = shard the key axis only (partial-state merge over NVLink)")
     ap.add_argument("--skip-module", action="store_true")
     ap.add_argument("--skip-training", action="store_true", help="skip the backward / dropout leg")
     ap.add_argument("--traffic-bytes", type=float, default=None,

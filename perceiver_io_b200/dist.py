@@ -37,6 +37,46 @@ import torch
 import torch.distributed as dist
 
 
+def plan_grid(batch: int, world_size: int) -> Tuple[int, int]:
+    """(batch_groups, m_shards) with batch_groups * m_shards == world_size: ranks are spent on the batch axis first.
+
+    Batch rows are independent — sharding them needs no exchange at all — while every extra M shard adds a partial
+    softmax state to merge (17 MB per rank at the north-star shape).  So the batch axis takes the largest divisor of
+    ``world_size`` that also divides ``batch``; only the remaining factor shards the key axis.  B=8 on 8 GPUs is
+    (8, 1): one batch row per GPU, no collective; B=1 on 8 GPUs is (1, 8): the pure M-shard layout of SURVEY.md §8(e)."""
+    if batch < 1 or world_size < 1:
+        raise ValueError("batch and world_size must be positive")
+    bg = 1
+    for cand in range(1, world_size + 1):
+        if world_size % cand == 0 and batch % cand == 0:
+            bg = cand
+    return bg, world_size // bg
+
+
+def grid_position(rank: int, batch_groups: int, m_shards: int) -> Tuple[int, int]:
+    """(batch group, M shard) of ``rank``: the ranks of one batch group are consecutive (they merge with each other)."""
+    if not 0 <= rank < batch_groups * m_shards:
+        raise ValueError("rank outside the grid")
+    return rank // m_shards, rank % m_shards
+
+
+def m_shard_group(batch_groups: int, m_shards: int):
+    """The calling rank's process sub-group for the M-shard merge of its batch group (``None`` when there is nothing to
+    merge or the whole world is one group).  Collective: every rank must call it (``dist.new_group`` semantics)."""
+    if m_shards == 1 or not dist.is_initialized():
+        return None
+    if batch_groups == 1:
+        return dist.group.WORLD
+    mine = None
+    rank = dist.get_rank()
+    for gb in range(batch_groups):
+        ranks = list(range(gb * m_shards, (gb + 1) * m_shards))
+        g = dist.new_group(ranks)
+        if rank in ranks:
+            mine = g
+    return mine
+
+
 def shard_bounds(m_total: int, world_size: int, rank: int, align: int = 128) -> Tuple[int, int]:
     """Contiguous [begin, end) slice of the key axis owned by ``rank``: equal counts of ``align``-key
     tiles, remainder tiles to the lowest ranks, the ragged tail to the last non-empty rank."""
