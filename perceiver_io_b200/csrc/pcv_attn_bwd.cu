@@ -78,37 +78,28 @@ struct BwdParams {
 
 // ---- attention-probability dropout (modules.py:161: nn.Dropout on the softmax output) -----------------------------
 // Counter-based: the keep decision of element (b, h, query q, key k) is a pure function of (seed, b*H+h, q, k), so the
-// forward kernel and both backward kernels regenerate the same mask without storing it.  One 32-bit murmur3 hash per
-// 2 x 2 block (query pair q>>1, key pair k>>1) yields four random bytes, byte (q&1)*2 + (k&1) belongs to (q, k); an
-// element is dropped iff its byte < drop_thresh, i.e. with probability drop_thresh/256 (the requested p rounded to
-// 1/256; the survivors are scaled by exactly 1/(1 - drop_thresh/256)).  A thread that walks keys (query fixed) or
-// queries (key fixed) needs one hash per two columns either way.
-__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+// forward kernel and both backward kernels regenerate the same mask without storing it.  One 32-bit hash per 2 x 2 block
+// (query pair q>>1, key pair k>>1) yields four random bytes, byte (q&1)*2 + (k&1) belongs to (q, k); an element is
+// dropped iff its byte < drop_thresh, i.e. with probability drop_thresh/256 (the requested p rounded to 1/256; the
+// survivors are scaled by exactly 1/(1 - drop_thresh/256)).  A thread that walks keys (query fixed) or queries (key
+// fixed) needs one hash per two columns either way, and its own side of the input is a per-thread constant.
+// Hash: x = qside ^ kside, then two Philox-style rounds x <- hi(x*C) ^ lo(x*C) ^ K (one IMAD.WIDE + one LOP3 each).
+// Checked on 8M-element masks: keep rate, row / column rates, autocorrelation at lags up to 64 in both directions, across
+// heads and across adjacent seeds all at the sampling-noise floor (one round is NOT enough: seeds correlate at 3 %).
 __device__ __forceinline__ uint32_t drop_qword(uint32_t bh, uint32_t q) { return bh * 0x9E3779B1u + (q >> 1); }
-// murmur3 block mix of one 32-bit word
-__device__ __forceinline__ uint32_t drop_mixk(uint32_t k) {
-  k *= 0xCC9E2D51u;
-  k = rotl32(k, 15);
-  return k * 0x1B873593u;
+__device__ __forceinline__ uint32_t drop_qside(uint32_t seed_lo, uint32_t qword) { return qword * 0x9E3779B1u ^ seed_lo; }
+__device__ __forceinline__ uint32_t drop_kside(uint32_t seed_hi, uint32_t k) { return (k >> 1) * 0x85EBCA6Bu ^ seed_hi; }
+__device__ __forceinline__ uint32_t drop_round(uint32_t x, uint32_t c, uint32_t k) {
+  const uint64_t pr = (uint64_t)x * c;
+  return (uint32_t)(pr >> 32) ^ (uint32_t)pr ^ k;
 }
-__device__ __forceinline__ uint32_t drop_mixh(uint32_t h, uint32_t mixed_k) {
-  h ^= mixed_k;
-  h = rotl32(h, 13);
-  return h * 5u + 0xE6546B64u;
-}
-// hash of (seed_lo; block 1 = qword; block 2 = (k >> 1) ^ seed_hi), given h1 = drop_mixh(seed_lo, drop_mixk(qword)) and
-// mk = drop_mixk((k >> 1) ^ seed_hi): the per-thread constant half is hoisted by the callers
-__device__ __forceinline__ uint32_t drop_finish(uint32_t h1, uint32_t mk) {
-  uint32_t h = drop_mixh(h1, mk);
-  h ^= h >> 16;
-  h *= 0x85EBCA6Bu;
-  h ^= h >> 13;
-  h *= 0xC2B2AE35u;
-  h ^= h >> 16;
-  return h;
+__device__ __forceinline__ uint32_t drop_finish(uint32_t qside, uint32_t kside) {
+  uint32_t x = qside ^ kside;
+  x = drop_round(x, 0xD2511F53u, 0x9E3779B9u);
+  return drop_round(x, 0xCD9E8D57u, 0xBB67AE85u);
 }
 __device__ __forceinline__ uint32_t drop_bits(uint32_t seed_lo, uint32_t seed_hi, uint32_t bh, uint32_t q, uint32_t k) {
-  return drop_finish(drop_mixh(seed_lo, drop_mixk(drop_qword(bh, q))), drop_mixk((k >> 1) ^ seed_hi));
+  return drop_finish(drop_qside(seed_lo, drop_qword(bh, q)), drop_kside(seed_hi, k));
 }
 __device__ __forceinline__ bool drop_keep(uint32_t bits, uint32_t q, uint32_t k, uint32_t thresh) {
   return ((bits >> (((q & 1u) * 2u + (k & 1u)) * 8u)) & 0xffu) >= thresh;
@@ -295,7 +286,7 @@ struct Bars1 {
 // One sub-step of one thread: key row (TMEM lane) x all 64 query columns, in two passes of 32.  MASKED: some score of
 // the CTA's tile is filled / out of range (padding keys, causal diagonal, ragged last key tile).
 //   st: the 32 float4 {nlse, nlse, delta, delta} of the sub-step's 64 queries; fp: their 64 fill probabilities.
-// DROP: attention dropout; `dq0` = drop_qword of the sub-step's first query, `dmk` = drop_mixk of this thread's key pair,
+// DROP: attention dropout; `dq0` = drop_qword of the sub-step's first query, `dmk` = drop_kside of this thread's key,
 // `ksh` = bit offset of the key's byte within a query's half of the hash (8 * (key & 1)).
 template <bool BF16, bool MASKED, bool DROP>
 __device__ __forceinline__ void dkdv_substep(Bars1& bar, uint32_t set, uint32_t par, uint32_t tS, uint32_t tP,
@@ -341,7 +332,7 @@ __device__ __forceinline__ void dkdv_substep(Bars1& bar, uint32_t set, uint32_t 
       pf[hh * 32 + i + 1] = p1;
       if (DROP) {  // dV sees the dropped-out, rescaled probabilities; dS below the plain ones
         const uint32_t bits =
-            drop_finish(drop_mixh(p.seed_lo, drop_mixk(dq0 + (uint32_t)(hh * 16 + (i >> 1)))), dmk);
+            drop_finish(drop_qside(p.seed_lo, dq0 + (uint32_t)(hh * 16 + (i >> 1))), dmk);
         const bool k0 = ((bits >> ksh) & 0xffu) >= p.drop_thresh;
         const bool k1 = ((bits >> (ksh + 16u)) & 0xffu) >= p.drop_thresh;
         keepm[hh] |= (k0 ? 1u : 0u) << i;
@@ -432,7 +423,7 @@ __device__ __forceinline__ void softmax_dkdv(const BwdParams& p, Bars1& bar, uin
           dkdv_substep<BF16, true, false>(bar, set, par, tS, tP, st, fp, p.scale_log2, pad, oob, nfill, p, 0u, 0u, 0u);
       } else {
         const uint32_t dq0 = drop_qword((uint32_t)bh, (uint32_t)q0);
-        const uint32_t dmk = drop_mixk(((uint32_t)key >> 1) ^ p.seed_hi), ksh = ((uint32_t)key & 1u) * 8u;
+        const uint32_t dmk = drop_kside(p.seed_hi, (uint32_t)key), ksh = ((uint32_t)key & 1u) * 8u;
         if (!masked)
           dkdv_substep<BF16, false, true>(bar, set, par, tS, tP, st, fp, p.scale_log2, false, false, 0, p, dq0, dmk, ksh);
         else
@@ -752,7 +743,7 @@ __device__ __forceinline__ void dq_tile(Bars2& bar, uint32_t i_t, uint32_t tS, u
     for (int i = 0; i < 64; i += 2) {
       float2 dp = make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1]));
       if (DROP) {
-        const uint32_t bits = drop_finish(dh1, drop_mixk(((k0 + (uint32_t)i) >> 1) ^ p.seed_hi));
+        const uint32_t bits = drop_finish(dh1, drop_kside(p.seed_hi, k0 + (uint32_t)i));
         dp.x = (((bits >> qsh) & 0xffu) >= p.drop_thresh) ? dp.x * p.drop_rp : 0.f;
         dp.y = (((bits >> (qsh + 8u)) & 0xffu) >= p.drop_thresh) ? dp.y * p.drop_rp : 0.f;
       }
@@ -786,7 +777,7 @@ __device__ __forceinline__ void softmax_dq(const BwdParams& p, Bars2& bar, int w
   const float* blk = p.stats + (((size_t)b * p.H + h) * (2 * p.nq) + (size_t)(nrow >> 6)) * (kStatsBytes / 4);
   const float nlse = blk[stat_nlse_idx(r & 63)], delta = blk[stat_delta_idx(r & 63)], fillp = blk[stat_fillp_idx(r & 63)];
   // dropout: this query's half of the hash and the bit offset of its two bytes within a key pair's hash
-  const uint32_t dh1 = drop_mixh(p.seed_lo, drop_mixk(drop_qword((uint32_t)(b * p.H + h), (uint32_t)nrow)));
+  const uint32_t dh1 = drop_qside(p.seed_lo, drop_qword((uint32_t)(b * p.H + h), (uint32_t)nrow));
   const uint32_t qsh = ((uint32_t)nrow & 1u) * 16u;
 
   for (int t = t0; t < t1; ++t) {
@@ -1078,7 +1069,7 @@ __device__ __forceinline__ void fwd_drop_tile(Bars3& bar, uint32_t i_t, uint32_t
       if (i >= oob_from) p0 = 0.f;
       if (i + 1 >= oob_from) p1 = 0.f;
     }
-    const uint32_t bits = drop_finish(dh1, drop_mixk(((k0 + (uint32_t)i) >> 1) ^ p.seed_hi));
+    const uint32_t bits = drop_finish(dh1, drop_kside(p.seed_hi, k0 + (uint32_t)i));
     p0 = (((bits >> qsh) & 0xffu) >= p.drop_thresh) ? p0 * p.drop_rp : 0.f;
     p1 = (((bits >> (qsh + 8u)) & 0xffu) >= p.drop_thresh) ? p1 * p.drop_rp : 0.f;
     pk[i >> 1] = pack2(p0, p1, BF16);
@@ -1143,7 +1134,7 @@ fwd_drop_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t tS0 = bar.tmem_base + lanef + (uint32_t)(half * 64);
     const float* blk = p.stats + (((size_t)b * p.H + h) * (2 * p.nq) + (size_t)(nrow >> 6)) * (kStatsBytes / 4);
     const float nlse = blk[stat_nlse_idx(r & 63)], fillp = blk[stat_fillp_idx(r & 63)];
-    const uint32_t dh1 = drop_mixh(p.seed_lo, drop_mixk(drop_qword((uint32_t)bh, (uint32_t)nrow)));
+    const uint32_t dh1 = drop_qside(p.seed_lo, drop_qword((uint32_t)bh, (uint32_t)nrow));
     const uint32_t qsh = ((uint32_t)nrow & 1u) * 16u;
     for (int t = t0; t < t1; ++t) {
       const uint32_t i_t = (uint32_t)(t - t0);

@@ -20,11 +20,13 @@ def main():
     ap.add_argument("--d", type=int, default=128)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--shim", action="store_true", help="also time the torch shim (slow)")
+    ap.add_argument("--per-batch-q", action="store_true", help="q of shape (B, N, C) instead of one latent array shared by the batch")
+    ap.add_argument("--no-flush", action="store_true", help="back-to-back calls, no L2 flush in between")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     B, N, M, H, d = a.B, a.N, a.M, a.H, a.d
     g = torch.Generator(device="cuda").manual_seed(0)
-    q = torch.randn(1, N, H * d, device="cuda", generator=g).to(torch.bfloat16)
+    q = torch.randn(B if a.per_batch_q else 1, N, H * d, device="cuda", generator=g).to(torch.bfloat16)
     k = torch.randn(B, M, H * d, device="cuda", generator=g).to(torch.bfloat16)
     v = torch.randn(B, M, H * d, device="cuda", generator=g).to(torch.bfloat16)
     go = torch.randn(B, N, H * d, device="cuda", generator=g).to(torch.bfloat16)
@@ -39,7 +41,8 @@ def main():
         torch.cuda.synchronize()
         ts = []
         for _ in range(steps):
-            flush.zero_()
+            if not a.no_flush:
+                flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
