@@ -69,6 +69,8 @@ struct Segment {
   int unit;    // >= 0: index of the split unit (UnitRec) this segment is a part of; -1: whole key range
 };
 
+constexpr int kOwnerMergeMax = 4;  // split units with at most this many parts are merged by their first part (see epilogue_row)
+
 struct UnitRec {  // a (b,h,query-block) whose key range was split over several segments
   int b, h, q0;
   int slot_begin, slot_count;
@@ -432,13 +434,16 @@ __device__ __forceinline__ void wait_slot_rows(const TcParams& p, int slot, int 
 
 // O row of this thread (TMEM, `DV` accumulator columns starting at tO) -> global memory: the normalised output,
 // the caller's partial state, or a split-M slot.  Channels [0, dv_pass) of the accumulator map to output channels
-// [dv_off, dv_off + dv_pass) (dv_off > 0 only in the second pass of the big-head kernel).  With FIXUP the part of a
-// split unit that starts at key tile 0 merges the other parts' slots on the fly and writes the unit's result.
+// [dv_off, dv_off + dv_pass) (dv_off > 0 only in the second pass of the big-head kernel).  With FIXUP split units are
+// merged inside the kernel: see `owner` below and fixup_merge.
 template <int DV, bool BF16, bool FIXUP>
 __device__ __forceinline__ void epilogue_row(const TcParams& p, const Segment& seg, uint32_t tO, int n,
                                              int row_in_unit, float l, float m_ref) {
   const bool valid = n < p.N;
-  const bool owner = FIXUP && seg.slot >= 0 && seg.t0 == 0;
+  // lightly split units (<= kOwnerMergeMax parts): the part that starts at key tile 0 keeps its rows in TMEM and folds the
+  // other parts' slots into them, one thread per row (all 256 rows in flight: best when there are few slots to read);
+  // heavily split units are merged by fixup_merge below, where every part publishes its rows
+  const bool owner = FIXUP && seg.slot >= 0 && seg.t0 == 0 && p.units[seg.unit].slot_count <= kOwnerMergeMax;
   if (seg.slot >= 0 && !owner) {
     // one part of a split unit: un-normalised rows into the slot, then (FIXUP) tell the owning part
     const int64_t r = (int64_t)seg.slot * p.slot_rows + row_in_unit;
@@ -538,6 +543,135 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, const Segment& s
         const int col = ch * 32 + c4 * 4;
         if (col < p.dv_pass)
           *reinterpret_cast<uint4*>(dst + col) = make_uint4(o[c4 * 4], o[c4 * 4 + 1], o[c4 * 4 + 2], o[c4 * 4 + 3]);
+      }
+    }
+  }
+}
+
+// In-kernel merge of HEAVILY split units (more than kOwnerMergeMax parts), run by the 8 softmax warps AFTER the CTA's last
+// segment.  Every part of such a unit has written its un-normalised rows to its slot (epilogue_row); part i of the S parts merges rows
+// [i*R/S, (i+1)*R/S) of the unit — one warp per row: the lanes wait for the S publishing warps of that row, reduce the
+// row maxima and denominators with shuffles, then stream the S numerator rows (512 coalesced bytes each, all in flight)
+// and write the row's result.  The merge work of a unit is thereby spread over all CTAs that worked on it and runs with
+// coalesced loads: with few, heavily split units (B*H small) the owner-merges-everything scheme serialises
+// S x 133 KB of strided 16-byte reads behind one CTA (B=1 at the north-star shape: 0.219 -> 0.151 ms per launch; the row-serial
+// warps lose to the owner scheme when S is 2-3: B=8 0.864 vs 0.912 ms, hence the split by kOwnerMergeMax).
+// No part ever waits before its own rows are published, and parts are merged only after the CTA's last segment, so the
+// waits cannot form a cycle (all CTAs of the persistent grid are resident).
+//   tile_rows: query rows per tile (128; 256 in the CTA-pair kernel); part_rank / part_ranks: the CTAs of a pair share
+//   their segments and split the rows between them.
+template <int DV, bool BF16>
+__device__ __forceinline__ void fixup_merge(const TcParams& p, int seg_lo, int seg_hi, int warp8, int lane,
+                                            int tile_rows, int part_rank, int part_ranks) {
+  // lane owns columns {lane*4 + 128*v .. +3} (DV >= 128: kV float4 per slot row) or {lane*2, lane*2+1} (DV == 64)
+  constexpr bool kNarrow = DV < 128;
+  constexpr int kV = kNarrow ? 1 : (DV + 127) / 128;
+  for (int sg = seg_lo; sg < seg_hi; ++sg) {
+    const Segment seg = p.segs[sg];
+    if (seg.slot < 0) continue;
+    const UnitRec u = p.units[seg.unit];
+    const int S = u.slot_count, part = seg.slot - u.slot_begin;
+    if (S <= kOwnerMergeMax) continue;  // merged by the owning part in its epilogue
+    const int R = min(seg.ntile * tile_rows, p.N - seg.q0);
+    const int r0 = (int)(((int64_t)R * part) / S), r1 = (int)(((int64_t)R * (part + 1)) / S);
+    for (int r = r0 + warp8 * part_ranks + part_rank; r < r1; r += 8 * part_ranks) {
+      const int rw = r >> 5;
+      // the row of every part is published; row maximum
+      float m = -INFINITY;
+      for (int s0 = 0; s0 < S; s0 += 32) {
+        const int sidx = s0 + lane;
+        float ms = -INFINITY;
+        if (sidx < S) {
+          const unsigned long long* f = p.slot_flags + (int64_t)(u.slot_begin + sidx) * kFlagsPerSlot + rw;
+          uint32_t spins = 0;
+          uint64_t t0 = 0;
+          while (ld_acquire_gpu_u64(f) != p.fixup_tag) {
+            if ((++spins & 0xFFu) == 0) {
+              const uint64_t now = globaltimer_ns();
+              if (t0 == 0) {
+                t0 = now;
+              } else if (now - t0 > kWaitTimeoutNs) {
+                uint32_t* d = g_wait_diag;
+                if (d != nullptr && atomicCAS(d, 0u, 1u) == 0u) {
+                  d[1] = 40;
+                  d[2] = blockIdx.x;
+                  d[3] = threadIdx.x;
+                  d[4] = (uint32_t)(u.slot_begin + sidx);
+                  d[5] = spins;
+                  __threadfence_system();
+                }
+                __trap();
+              }
+            }
+          }
+          ms = __ldcg(p.slot_m + (int64_t)(u.slot_begin + sidx) * p.slot_rows + r);
+        }
+        __syncwarp();
+        m = fmaxf(m, warp_max(ms));
+      }
+      // weights, denominator, numerator
+      float l = 0.f;
+      float4 acc[kV];
+#pragma unroll
+      for (int v = 0; v < kV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s0 = 0; s0 < S; s0 += 32) {
+        const int sidx = s0 + lane;
+        float w = 0.f, wl = 0.f;
+        if (sidx < S) {
+          const int64_t rr = (int64_t)(u.slot_begin + sidx) * p.slot_rows + r;
+          const float ms = __ldcg(p.slot_m + rr);
+          w = (ms == -INFINITY) ? 0.f : exp2f(ms - m);
+          wl = w * __ldcg(p.slot_l + rr);
+        }
+        l += warp_sum(wl);
+        const int cnt = min(32, S - s0);
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+          const float wj = __shfl_sync(0xffffffffu, w, j);
+          const float* src = p.slot_o + ((int64_t)(u.slot_begin + s0 + j) * p.slot_rows + r) * DV;
+          if (kNarrow) {
+            const float2 x = __ldcg(reinterpret_cast<const float2*>(src + lane * 2));
+            acc[0].x = fmaf(x.x, wj, acc[0].x);
+            acc[0].y = fmaf(x.y, wj, acc[0].y);
+          } else {
+#pragma unroll
+            for (int v = 0; v < kV; ++v) {
+              if (v * 128 + lane * 4 >= DV) continue;
+              const float4 x = __ldcg(reinterpret_cast<const float4*>(src + v * 128 + lane * 4));
+              acc[v].x = fmaf(x.x, wj, acc[v].x);
+              acc[v].y = fmaf(x.y, wj, acc[v].y);
+              acc[v].z = fmaf(x.z, wj, acc[v].z);
+              acc[v].w = fmaf(x.w, wj, acc[v].w);
+            }
+          }
+        }
+      }
+      const int n = seg.q0 + r;
+      const int64_t fr = ((int64_t)seg.b * p.H + seg.h) * p.N + n;
+      const float inv = 1.f / l;
+      char* orow = reinterpret_cast<char*>(p.out) +
+                   2 * ((int64_t)seg.b * p.osb + (int64_t)n * p.osn + (int64_t)seg.h * p.osh + p.dv_off);
+      float* frow = p.fin_o + fr * p.dv + p.dv_off;
+#pragma unroll
+      for (int v = 0; v < kV; ++v) {
+        const int col = kNarrow ? lane * 2 : v * 128 + lane * 4;
+        if (col >= p.dv_pass || col >= DV) continue;
+        if (!p.write_partial) {
+          if (kNarrow)
+            *reinterpret_cast<uint32_t*>(orow + 2 * col) = pack2(acc[v].x * inv, acc[v].y * inv, BF16);
+          else
+            *reinterpret_cast<uint2*>(orow + 2 * col) =
+                make_uint2(pack2(acc[v].x * inv, acc[v].y * inv, BF16), pack2(acc[v].z * inv, acc[v].w * inv, BF16));
+        } else {
+          if (kNarrow)
+            *reinterpret_cast<float2*>(frow + col) = make_float2(acc[v].x, acc[v].y);
+          else
+            *reinterpret_cast<float4*>(frow + col) = acc[v];
+        }
+      }
+      if (p.write_partial && lane == 0) {
+        p.fin_m[fr] = m;
+        p.fin_l[fr] = l;
       }
     }
   }
@@ -853,6 +987,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp < 8) {
     reg_alloc<208>();  // 256*208 + 128*88 == 384*168: exactly the registers the CTA was launched with  // softmax warpgroups take the registers the control warpgroup gives up
     softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi);
+    fixup_merge<DV, BF16>(p, seg_lo, seg_hi, warp, lane, kTileM, 0, 1);
     if (p.tail.enabled) peer_tail<DV, BF16>(p);
   } else {
     reg_dealloc<88>();
@@ -1141,6 +1276,7 @@ attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp < 8) {
     reg_alloc<216>();
     softmax_role<DQK, DV, BF16>(p, bar, warp >> 2, threadIdx.x & 127, seg_lo, seg_hi, (int)rank);
+    fixup_merge<DV, BF16>(p, seg_lo, seg_hi, warp, lane, 2 * kTileM, (int)rank, 2);
     if (p.tail.enabled) peer_tail<DV, BF16>(p);
   } else {
     reg_dealloc<72>();
