@@ -222,3 +222,58 @@ def test_cached_generation_under_autocast_promotes_like_torch_cat():
         full = m(t[:, :299], prefix_len=100, kv_cache=[])
         step = m(t[:, 299:], prefix_len=100, kv_cache=full.kv_cache)
     assert torch.isfinite(step.logits).all() and step.kv_cache[0][0].shape[1] == 300
+
+
+def test_patched_reference_encoder_trains_with_attention_dropout():
+    """A real reference PerceiverEncoder built with dropout=0.1, patched, in TRAINING mode: the attention-probability
+    dropout of modules.py:161 runs inside the kernels (round 1 raised here).  Checks: reproducible under
+    torch.manual_seed, differs from the eval forward, mean over seeds approaches it, loss.backward() reaches the input
+    and every parameter through the backward kernels (impl='kernel' raises otherwise), eval is untouched."""
+    from perceiver_io_b200 import ops
+
+    torch.manual_seed(0)
+    B, M, C, N, D = 2, 1500, 256, 192, 256
+    enc = core.PerceiverEncoder(
+        _PassThroughInput(C), num_latents=N, num_latent_channels=D, num_cross_attention_heads=4,
+        num_cross_attention_layers=1, num_self_attention_heads=4, num_self_attention_layers_per_block=2,
+        num_self_attention_blocks=1, dropout=0.1)
+    _randomize(enc, 21)
+    mine = _patched_bf16(enc)
+    x = (torch.randn(B, M, C, generator=torch.Generator().manual_seed(22)) + 0.1).bfloat16().cuda()
+    pad = torch.zeros(B, M, dtype=torch.bool)
+    pad[1, 1200:] = True
+    pad = pad.cuda()
+    mine.eval()
+    with torch.no_grad():
+        ev = mine(x, pad_mask=pad).float()
+    mine.train()
+    with torch.no_grad():
+        torch.manual_seed(5)
+        a = mine(x, pad_mask=pad).float()
+        torch.manual_seed(5)
+        b = mine(x, pad_mask=pad).float()
+        assert torch.equal(a, b)
+        spread = (a - ev).abs().mean().item()
+        assert spread > 1e-4
+        acc = torch.zeros_like(ev)
+        n = 16
+        for i in range(n):
+            torch.manual_seed(50 + i)
+            acc += mine(x, pad_mask=pad).float()
+        bias = (acc / n - ev).abs().mean().item()
+        print(f"[dropout encoder] mean |E[train] - eval| {bias:.3e} vs single-sample spread {spread:.3e}")
+        assert bias < 0.6 * spread
+    ops.backward_config["impl"] = "kernel"
+    try:
+        xg = x.clone().requires_grad_()
+        torch.manual_seed(7)
+        out = mine(xg, pad_mask=pad)
+        out.float().square().mean().backward()
+    finally:
+        ops.backward_config["impl"] = "auto"
+    assert torch.isfinite(xg.grad).all() and xg.grad.abs().max().item() > 0
+    missing = [n_ for n_, p_ in mine.named_parameters() if p_.requires_grad and (p_.grad is None or not torch.isfinite(p_.grad).all())]
+    assert not missing, missing
+    mine.eval()
+    with torch.no_grad():
+        assert torch.equal(mine(x, pad_mask=pad).float(), ev)
