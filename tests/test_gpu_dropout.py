@@ -157,3 +157,17 @@ def test_module_dropout_train_and_eval():
         ops.backward_config["impl"] = "auto"
     assert torch.isfinite(xq.grad).all() and xq.grad.abs().max().item() > 0
     assert all(torch.isfinite(p_.grad).all() for p_ in mha.parameters() if p_.grad is not None)
+
+
+def test_device_mask_equals_the_numpy_oracle_bit_for_bit():
+    """Integer path: the device generator (drop_bits / drop_keep in csrc/pcv_attn_bwd.cu, exported by
+    pcv_attn_dropout_mask) against its numpy restatement oracle/dropout_oracle.py — exact equality."""
+    import numpy as np
+
+    from oracle import dropout_oracle as D
+
+    for (B, H, N, M, p, seed) in [(2, 3, 70, 130, 0.1, 1), (1, 2, 33, 257, 0.5, 0xFFFFFFFFFFFF), (1, 1, 128, 512, 0.25, 424242),
+                                  (2, 1, 5, 7, 0.9, (1 << 62) - 3)]:
+        dev = ops.dropout_keep_mask(B, H, N, M, p, seed).cpu().numpy()
+        ref = D.keep_mask(B, H, N, M, p, seed)
+        assert np.array_equal(dev, ref), (B, H, N, M, p, seed, int((dev != ref).sum()))
