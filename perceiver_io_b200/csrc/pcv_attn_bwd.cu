@@ -1,4 +1,5 @@
-// pcv_attn_bwd.cu — backward of the fused attention core on the 5th-generation tensor cores.
+// pcv_attn_bwd.cu — training kernels of the fused attention core on the 5th-generation tensor cores (SURVEY.md
+// §8(f)2): backward (C ABI pcv_attn_bwd) and attention-probability dropout (pcv_attn_fwd_dropout, pcv_attn_dropout_mask).
 //
 // Reference: autograd through perceiver/model/core/modules.py:141-167 (einsum scores, masked_fill_ with the finite
 // fill, softmax, dropout, einsum with V).  With P = softmax(scale * Q K^T + fill), O = P V and the saved row statistics
@@ -9,20 +10,25 @@
 // kernels that never hold the (B, H, N, M) score tensor and need no atomics on the large axis:
 //
 //   bwd_dkdv_kernel  key-tile outer, persistent.  One CTA owns a 128-key tile (K, V resident in shared memory) and walks
-//                    the query tiles.  Scores are computed TRANSPOSED, S^T = K Q^T and dP^T = V dO^T (TMEM lanes =
-//                    keys), so P^T and dS^T, rounded to bf16/fp16, go back into TMEM and feed dV += P^T dO and
-//                    dK += dS^T Q as the A operand straight from TMEM (B = dO / Q tile read MN-major): P and dS never
-//                    touch shared memory.  dK, dV accumulate in TMEM over the query tiles and are written once.
-//   bwd_dq_kernel    query-tile outer.  One CTA owns (b, h, 128 queries) and a range of key tiles (K, V streamed through
-//                    a TMA ring); S = Q K^T, dP = dO V^T, dS -> TMEM, dQ += dS K (K tile read MN-major, as V is in
-//                    the forward).  dQ accumulates in TMEM over the CTA's key range and is added into an fp32 buffer
-//                    with one vector reduction per element per CTA (a few hundred KB in total).
+//                    the queries in sub-steps of 64.  Scores are computed TRANSPOSED, S^T = K Q^T and dP^T = V dO^T
+//                    (TMEM lanes = keys), so P^T and dS^T, rounded to bf16/fp16, go back into TMEM and feed
+//                    dV += P^T dO and dK += dS^T Q as the A operand straight from TMEM (B = dO / Q stage read
+//                    MN-major): P and dS never touch shared memory.  Two (S^T, dP^T) sets of 64 columns alternate next
+//                    to the dK / dV accumulators (512 TMEM columns in all); Q / dO arrive through a 5-deep TMA ring.
+//   bwd_dq_kernel    query-tile outer.  One CTA owns (b, h, 128 queries) and a range of key tiles (K and V streamed
+//                    through their own TMA rings); S = Q K^T, dP = dO V^T (double buffered), dS -> TMEM,
+//                    dQ += dS K (K tile read MN-major, as V is in the forward).  dQ accumulates in TMEM over the CTA's
+//                    key range and is added into an fp32 buffer with one vector reduction per element per CTA.
+//   fwd_drop_kernel  the dQ kernel's skeleton with O += dropout(P) V instead: the second forward pass of a training
+//                    step with dropout > 0 (normalised probabilities from the saved statistics, no running maximum).
 //
-// Recomputing S and dP in both kernels costs 7 tile GEMMs per (query tile, key tile) instead of 5; the one-kernel
-// alternative has to reduce a 128 x d fp32 dQ tile into global memory for EVERY (query tile, key tile) pair
+// Recomputing S and dP in both backward kernels costs 7 tile GEMMs per (query tile, key tile) instead of 5; the
+// one-kernel alternative has to reduce a 128 x d fp32 dQ tile into global memory for EVERY (query tile, key tile) pair
 // (8.6 GB of reductions at the north-star shape, ~1.3 cycles per lane each), which is slower than the two extra
-// GEMMs.  Both kernels are warp specialised like the forward: warps 0-7 softmax/epilogue (thread = TMEM lane,
-// two warps per lane quarter splitting the 128 columns), warp 8 TMA producer, warp 9 MMA issuer.
+// GEMMs.  All kernels are warp specialised like the forward: warps 0-7 softmax/epilogue (thread = TMEM lane; the two
+// warps of a lane quarter take alternate sub-steps in the dK/dV kernel and split the 128 key columns in the others),
+// warp 8 TMA producer (warp 10: the V ring of the query-outer kernels), warp 9 MMA issuer.  Measurements, versions and
+// the what-if analysis of the dK/dV kernel: profiles/r02_bwd_whatif.md, DESIGN.md §3.9 / §3.10.
 #include "pcv_common.cuh"
 #include "pcv_sm100.cuh"
 
