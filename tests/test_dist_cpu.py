@@ -93,3 +93,51 @@ def test_two_rank_gloo_merge_equals_unsharded(causal):
     assert sorted(r[1] for r in results) == [(0, 256), (256, 300)]
     for rank, _, err in results:
         assert err < 1e-5, (rank, err)
+
+
+def _grid_worker(rank, world, port, result_queue):
+    """2-D rank grid (dist.plan_grid): B=2 on 4 ranks = 2 batch groups x 2 key shards.  Each batch group merges its own
+    partial states over its own process sub-group; nothing crosses batch groups."""
+    from perceiver_io_b200.dist import grid_position, m_shard_group, plan_grid
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        B, H, N, M, d = 2, 2, 6, 300, 8
+        q = torch.randn(B, N, H * d, generator=g) * 2
+        k = torch.randn(B, M, H * d, generator=g)
+        v = torch.randn(B, M, H * d, generator=g)
+        pad = torch.zeros(B, M, dtype=torch.bool)
+        pad[1, 290:] = True
+        bg, mg = plan_grid(B, world)
+        gb, gm = grid_position(rank, bg, mg)
+        group = m_shard_group(bg, mg)
+        rows = slice(gb * (B // bg), (gb + 1) * (B // bg))
+        b, e = shard_bounds(M, mg, gm)
+        out = sharded_attention(q[rows], k[rows, b:e], v[rows, b:e], H, d ** -0.5, M, b, pad[rows, b:e], False, group=group,
+                                kernels=_oracle_kernels(H))
+        ref = O.merge_heads(O.core_attention(O.split_heads(q.double(), H), O.split_heads(k.double(), H),
+                                             O.split_heads(v.double(), H), d ** -0.5, pad, False))[rows]
+        result_queue.put((rank, (bg, mg, gb, gm), dist.get_world_size(group), float((out.double() - ref).abs().max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_four_rank_gloo_batch_by_key_grid():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_grid_worker, args=(r, 4, port, queue)) for r in range(4)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[1] for r in results) == [(2, 2, 0, 0), (2, 2, 0, 1), (2, 2, 1, 0), (2, 2, 1, 1)]
+    for rank, _, group_size, err in results:
+        assert group_size == 2 and err < 1e-5, (rank, group_size, err)
