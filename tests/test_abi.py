@@ -101,3 +101,24 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+
+
+def test_training_entry_points_validate_before_any_cuda_call():
+    """pcv_attn_bwd / pcv_attn_fwd_dropout / pcv_attn_dropout_mask reject bad arguments on a CPU-only box (no launch)."""
+    lib = _lib.lib()
+    assert lib.pcv_attn_bwd(None, None) == 1 and b"NULL" in lib.pcv_last_error()
+    assert lib.pcv_attn_bwd_supported(None) == 0
+    need = ctypes.c_size_t(0)
+    assert lib.pcv_attn_bwd_workspace_bytes(None, ctypes.byref(need)) == 1
+    p = _lib.AttnBwdParams()
+    p.B, p.H, p.N, p.M, p.dqk, p.dv, p.dtype = 2, 4, 200, 1000, 64, 64, _lib.AttnParams().dtype
+    p.q_stride_b = 1  # non-zero: one latent array per batch row
+    assert lib.pcv_attn_bwd_workspace_bytes(ctypes.byref(p), ctypes.byref(need)) == 0
+    # statistics blocks (768 B per 64 queries) + fp32 dQ accumulator, each rounded up to 256 bytes
+    stats = 768 * 2 * 4 * 4
+    dq32 = 4 * 2 * 200 * 4 * 64
+    assert need.value == (stats + 255) // 256 * 256 + (dq32 + 255) // 256 * 256
+    assert lib.pcv_attn_fwd_dropout(None, None, None, ctypes.c_float(0.1), ctypes.c_uint64(1), None) == 1
+    assert lib.pcv_attn_fwd_dropout_supported(None, ctypes.c_float(0.1)) == 0
+    assert lib.pcv_attn_dropout_mask(None, 1, 1, 8, 8, ctypes.c_float(0.1), ctypes.c_uint64(1), None) == 1
+    assert b"dropout_mask" in lib.pcv_last_error()
