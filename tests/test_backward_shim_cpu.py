@@ -63,3 +63,25 @@ def test_chunked_backward_matches_autograd(causal, with_stats, monkeypatch):
         assert got.shape == ref.shape
         assert (got.double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), name
     assert all(x is None for x in r[3:])
+
+
+def test_backward_dispatch_rules(monkeypatch):
+    """Which backward runs: an unknown mode is an error; the shim cannot regenerate a dropout mask, so a dropout forward
+    whose gradients cannot go through the kernels must fail loudly instead of returning dropout-free gradients."""
+    B, N, M, H, d = 1, 4, 64, 1, 8
+    g = torch.Generator().manual_seed(1)
+    q, k, v = (torch.randn(B, n, H * d, generator=g) for n in (N, M, M))
+    o = _eager(q.double(), k.double(), v.double(), H, d ** -0.5, None, False).float()
+    ctx = _Ctx()
+    ctx.saved_tensors = (q, k, v, None, o, None, None)
+    ctx.meta = (H, d ** -0.5, False)
+    monkeypatch.setattr(ops, "_compute_dtype", lambda dt: torch.float32)
+    monkeypatch.setitem(ops.backward_config, "impl", "fastest")
+    with pytest.raises(ValueError, match="backward_config"):
+        ops._FusedAttention.backward(ctx, torch.ones_like(o))
+    monkeypatch.setitem(ops.backward_config, "impl", "auto")
+    r = ops._FusedAttention.backward(ctx, torch.ones_like(o))     # CPU tensors, no statistics: the shim
+    assert r[0].shape == q.shape and len(r) == 10 and all(x is None for x in r[3:])
+    ctx.dropout = (0.1, 7)
+    with pytest.raises(RuntimeError, match="dropout"):
+        ops._FusedAttention.backward(ctx, torch.ones_like(o))
